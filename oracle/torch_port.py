@@ -1,0 +1,169 @@
+"""Device-agnostic torch restatement of the reference's hot-path modules.
+
+TEST INFRASTRUCTURE ONLY (tests/, smoke(), bench.py cpu_baseline / --impl reference).
+Nothing under depthinspace_b200/ imports this file.
+
+Why it exists next to the plain-C oracle: the reference path is a composition of torch
+ops, and two of its arithmetic details depend on which torch backend runs them
+(tensor/scalar division and grid_sample's un-normalisation differ between the CPU and
+CUDA kernels).  Running the SAME op sequence with torch on the GPU box gives the
+reference's CUDA arithmetic without needing /root/reference there, and running it on
+the host cores gives the multi-threaded CPU baseline the bench reports
+(`cpu_baseline.kind = "port"`).  tests/test_oracle_pinning.py checks, in the build
+container, that every function here reproduces the imported reference bit-for-bit on CPU.
+
+Each function cites the reference lines it restates.
+"""
+import torch
+import torch.nn.functional as F
+
+LOSS_TYPES = ("mse", "sad", "census_mse", "census_sad")
+
+
+def lcn(x, radius=5, eps=0.05):
+    """model/networks.py:667-689 -> (normalised, std)."""
+    k = 2 * radius + 1
+    ones = torch.ones(1, 1, k, k, dtype=x.dtype, device=x.device)
+
+    def box(t):
+        return F.conv2d(F.pad(t, (radius,) * 4, mode="reflect"), ones)
+
+    s1 = box(x)
+    mean = s1 / k ** 2
+    s2 = box(x ** 2)
+    std = torch.sqrt(torch.clamp(s2 / k ** 2 - mean ** 2 + 1e-6, min=0)) + eps
+    return (x - mean) / std, std
+
+
+def photometric(es, ta, block_size, type="mse", eps=0.1):
+    """model/ext_functions.py:156-183 (the in-tree definition of the ext kernel)."""
+    type = type.lower()
+    if type not in LOSS_TYPES:
+        raise Exception("invalid loss type")
+    r = block_size // 2
+    n, c, h, w = es.shape
+
+    def windows(t):
+        cols = F.unfold(F.pad(t, (r, r, r, r), mode="replicate"), kernel_size=block_size)
+        return cols.view(n, c, -1, h, w)
+
+    we, wt = windows(es), windows(ta)
+    if type == "mse":
+        per_tap = (we - wt) ** 2
+    elif type == "sad":
+        per_tap = (we - wt).abs()
+    else:
+        de = we - es.unsqueeze(2)
+        dt = wt - ta.unsqueeze(2)
+        he = 0.5 * (1 + de / torch.sqrt(de * de + eps))
+        ht = 0.5 * (1 + dt / torch.sqrt(dt * dt + eps))
+        delta = he - ht
+        per_tap = delta * delta if type == "census_mse" else delta.abs()
+    return per_tap.view(n, -1, h, w).sum(dim=1, keepdim=True) / block_size ** 2
+
+
+def _pixel_grid(h, w, device, dtype):
+    v, u = torch.meshgrid(torch.arange(h, device=device, dtype=dtype),
+                          torch.arange(w, device=device, dtype=dtype), indexing="ij")
+    return u, v
+
+
+def pattern_warp(disp, pattern):
+    """model/networks.py:356-367: x = u - disp, y = v, normalise, grid_sample(border)."""
+    n, _, h, w = disp.shape
+    u, v = _pixel_grid(h, w, disp.device, disp.dtype)
+    xs = u.reshape(1, -1) - disp.contiguous().view(n, -1)
+    ys = v.reshape(1, -1).expand(n, -1)
+    gx = 2 * (xs / (w - 1) - 0.5)
+    gy = 2 * (ys / (h - 1) - 0.5)
+    grid = torch.stack((gx, gy), dim=-1).view(n, h, w, 2)
+    return F.grid_sample(pattern.expand(n, -1, -1, -1), grid, padding_mode="border", align_corners=True)
+
+
+def pattern_loss(disp, im, std, pattern, loss_type="census_sad", loss_eps=0.5, block_size=9,
+                 output_mean=True, chunk=None):
+    """RectifiedPatternSimilarityLoss.tforward, model/networks.py:354-377.
+    ``pattern`` is the module's stored [1,1,H,W] (mean over the 3 channels, :344).
+    ``chunk`` evaluates the unfold-based window loss a few frames at a time (the reference
+    would need k*k times the batch in memory); the ratio is still formed over the batch."""
+    proj = pattern_warp(disp, pattern)
+    mask = torch.ones_like(im)
+    if std is not None:
+        mask = mask * std
+    n = disp.shape[0]
+    step = chunk or n
+    if output_mean:
+        num = 0
+        for i in range(0, n, step):
+            d = photometric(proj[i:i + step].contiguous(), im[i:i + step].contiguous(), block_size, loss_type, loss_eps)
+            num = num + (mask[i:i + step] * d).sum()
+        return num / mask.sum(), proj
+    diff = torch.cat([photometric(proj[i:i + step].contiguous(), im[i:i + step].contiguous(), block_size,
+                                  loss_type, loss_eps) for i in range(0, n, step)])
+    return diff, proj
+
+
+_SOBEL5 = [[-5, -4, 0, 4, 5], [-8, -10, 0, 10, 8], [-10, -20, 0, 20, 10], [-8, -10, 0, 10, 8], [-5, -4, 0, 4, 5]]
+_SOBEL3 = [[-1, 0, 1], [-2, 0, 2], [-1, 0, 1]]
+
+
+def sobel(x, ksize=5, norm=False):
+    """model/networks.py:697-730 -> [N,2,H,W] (gx, gy); weights rounded to float32 first."""
+    base, div = (_SOBEL5, 240.0) if ksize == 5 else (_SOBEL3, 8.0)
+    kx = (torch.tensor(base, dtype=torch.float64) / div).float().to(device=x.device, dtype=x.dtype)
+    r = ksize // 2
+    xp = F.pad(x, (r, r, r, r), mode="replicate")
+    gx = F.conv2d(xp, kx[None, None])
+    gy = F.conv2d(xp, kx.t().contiguous()[None, None])
+    if norm:
+        return torch.sqrt(gx ** 2 + gy ** 2 + 1e-8)
+    return torch.cat((gx, gy), dim=1)
+
+
+def smooth_loss(disp, im):
+    """DisparitySmoothLoss.tforward, model/networks.py:419-431."""
+    return (sobel(disp) * torch.exp(-(255 * sobel(im)).abs())).abs().mean()
+
+
+def flow_warp(x, flow):
+    """model/multi_frame_networks.py:83-99 (zeros padding, align_corners=True)."""
+    h, w = x.shape[-2:]
+    u, v = _pixel_grid(h, w, x.device, flow.dtype)
+    grid = flow.clone().permute(0, 2, 3, 1)
+    grid[..., 0] += u
+    grid[..., 1] += v
+    grid[..., 0] = 2 * (grid[..., 0] / (w - 1) - 0.5)
+    grid[..., 1] = 2 * (grid[..., 1] / (h - 1) - 0.5)
+    return F.grid_sample(x, grid, padding_mode="zeros", align_corners=True)
+
+
+def fb_mask(flow_fwd, flow_bwd_warped, a=0.01, b=0.5):
+    """forward-backward consistency mask, model/multi_frame_networks.py:205-207."""
+    mag = (flow_fwd ** 2).sum(1, keepdim=True) + (flow_bwd_warped ** 2).sum(1, keepdim=True)
+    diff = ((flow_fwd + flow_bwd_warped) ** 2).sum(1, keepdim=True)
+    return (diff < a * mag + b).float()
+
+
+def single_frame_loss(disps, im_lcn, std, ambient, pattern, chunk=None, pseudo_gt=None):
+    """Photometric + smoothness part of single_frame_worker.Worker.loss_forward
+    (model/single_frame_worker.py:101-125, 152-155): list of weighted 0-dim terms.
+    disps: list of [N,1,H,W] (scale s weighted 1/2^s); smoothness on scale 0, weight 0.4."""
+    vals = []
+    for s, d in enumerate(disps):
+        v, _ = pattern_loss(d, im_lcn, std, pattern, chunk=chunk)
+        vals.append(v / (2 ** s))
+    vals.append(smooth_loss(disps[0], ambient) * 0.4)
+    if pseudo_gt is not None:
+        for s, d in enumerate(disps):
+            vals.append((d - pseudo_gt).abs().mean() * 0.1 / (2 ** s))
+    return vals
+
+
+def multi_frame_loss(disp, im_lcn, std, ambient, pattern, chunk=None, primary_disp=None):
+    """Photometric + smoothness part of multi_frame_worker.Worker.loss_forward
+    (model/multi_frame_worker.py:103-126, 160-165): smoothness weight 0.8."""
+    v, _ = pattern_loss(disp, im_lcn, std, pattern, chunk=chunk)
+    vals = [v, smooth_loss(disp, ambient) * 0.8]
+    if primary_disp is not None:
+        vals.append((disp - primary_disp).abs().mean() * 0.1)
+    return vals
