@@ -1,0 +1,230 @@
+"""Tensor-level wrappers over the C-ABI: validate, allocate outputs with torch, pass raw device
+pointers and the current CUDA stream.  torch is plumbing here (memory + streams); every FLOP of the
+path runs in libdis_b200.so.  CPU tensors are rejected: there is no CPU fallback.
+"""
+import torch
+
+from . import _lib
+
+LOSS_TYPES = {"mse": 0, "sad": 1, "census_mse": 2, "census_sad": 3}
+
+
+def loss_type_id(type):
+    """String -> int map of model/ext_functions.py:142-154 (raises like the reference)."""
+    if isinstance(type, int):
+        if type not in (0, 1, 2, 3):
+            raise Exception("invalid loss type")
+        return type
+    t = LOSS_TYPES.get(str(type).lower())
+    if t is None:
+        raise Exception("invalid loss type")
+    return t
+
+
+def _chk(t, name, ndim=4):
+    if not isinstance(t, torch.Tensor):
+        raise TypeError(f"{name} must be a torch.Tensor")
+    if not t.is_cuda:
+        raise RuntimeError(f"{name} must be a CUDA tensor: depthinspace_b200 has no CPU path")
+    if t.dtype != torch.float32:
+        raise TypeError(f"{name} must be float32, got {t.dtype}")
+    if ndim is not None and t.dim() != ndim:
+        raise ValueError(f"{name} must have {ndim} dims, got shape {tuple(t.shape)}")
+    return t.contiguous()
+
+
+def _ptr(t):
+    return None if t is None else t.data_ptr()
+
+
+def _stream(t):
+    return torch.cuda.current_stream(t.device).cuda_stream
+
+
+class _on:
+    """Device guard (kernels launch on the tensor's device)."""
+
+    def __init__(self, t):
+        self.g = torch.cuda.device(t.device)
+
+    def __enter__(self):
+        self.g.__enter__()
+        return _lib.load()
+
+    def __exit__(self, *a):
+        return self.g.__exit__(*a)
+
+
+def lcn_forward(x, radius, eps):
+    x = _chk(x, "data")
+    N, C, H, W = x.shape
+    lcn, std = torch.empty_like(x), torch.empty_like(x)
+    with _on(x) as lib:
+        _lib.check(lib.dis_lcn_forward(_ptr(x), _ptr(lcn), _ptr(std), N * C, H, W, int(radius), float(eps), _stream(x)))
+    return lcn, std
+
+
+def photometric_loss_forward(es, ta, block_size, type, eps):
+    es, ta = _chk(es, "es"), _chk(ta, "ta")
+    if es.shape != ta.shape:
+        raise ValueError(f"es {tuple(es.shape)} and ta {tuple(ta.shape)} differ")
+    N, C, H, W = es.shape
+    out = torch.empty((N, 1, H, W), dtype=es.dtype, device=es.device)
+    with _on(es) as lib:
+        _lib.check(lib.dis_photometric_loss_forward(_ptr(es), _ptr(ta), _ptr(out), N, C, H, W, int(block_size),
+                                                    loss_type_id(type), float(eps), _stream(es)))
+    return out
+
+
+def photometric_loss_backward(es, ta, grad_out, block_size, type, eps):
+    es, ta, grad_out = _chk(es, "es"), _chk(ta, "ta"), _chk(grad_out, "grad_out")
+    N, C, H, W = es.shape
+    if tuple(grad_out.shape) != (N, 1, H, W):
+        raise ValueError(f"grad_out must be {(N, 1, H, W)}, got {tuple(grad_out.shape)}")
+    grad_es = torch.empty_like(es)
+    with _on(es) as lib:
+        _lib.check(lib.dis_photometric_loss_backward(_ptr(es), _ptr(ta), _ptr(grad_out), _ptr(grad_es), N, C, H, W,
+                                                     int(block_size), loss_type_id(type), float(eps), _stream(es)))
+    return grad_es
+
+
+def pattern_warp(disp, pattern, want_dproj=False, want_corners=False):
+    disp = _chk(disp, "disp0")
+    N, C, H, W = disp.shape
+    pattern = _chk(pattern, "pattern", None).reshape(H, W)
+    proj = torch.empty_like(disp)
+    dproj = torch.empty_like(disp) if want_dproj else None
+    cx = torch.empty(disp.shape, dtype=torch.int32, device=disp.device) if want_corners else None
+    cy = torch.empty_like(cx) if want_corners else None
+    with _on(disp) as lib:
+        _lib.check(lib.dis_pattern_warp_forward(_ptr(disp), _ptr(pattern), _ptr(proj), _ptr(dproj), _ptr(cx), _ptr(cy),
+                                                N * C, H, W, _stream(disp)))
+    return proj, dproj, cx, cy
+
+
+def pattern_loss_forward(disp, im, std, pattern, block_size, type, eps, want_proj, want_diff, want_grad):
+    """-> (out3 [num, den, num/den], proj|None, diff|None, grad_num|None)"""
+    disp, im = _chk(disp, "disp0"), _chk(im, "im")
+    N, C, H, W = disp.shape
+    if C != 1 or tuple(im.shape) != (N, 1, H, W):
+        raise ValueError(f"disp0 and im must both be [N,1,H,W]; got {tuple(disp.shape)} and {tuple(im.shape)}")
+    if std is not None:
+        std = _chk(std, "std")
+        if std.shape != disp.shape:
+            raise ValueError("std must match disp0")
+    pattern = _chk(pattern, "pattern", None)
+    if pattern.numel() != H * W:
+        raise ValueError(f"pattern has {pattern.numel()} elements, expected {H}x{W}")
+    new = lambda: torch.empty_like(disp)
+    proj = new() if want_proj else None
+    diff = new() if want_diff else None
+    gnum = new() if want_grad else None
+    out3 = torch.empty(3, dtype=torch.float32, device=disp.device)
+    with _on(disp) as lib:
+        npart = lib.dis_pattern_loss_num_partials(N, H, W)
+        partials = torch.empty(2 * max(npart, 1), dtype=torch.float32, device=disp.device)
+        s = _stream(disp)
+        _lib.check(lib.dis_pattern_loss_forward(_ptr(disp), _ptr(im), _ptr(std), _ptr(pattern), _ptr(proj), _ptr(diff),
+                                                _ptr(gnum), _ptr(partials), N, H, W, int(block_size),
+                                                loss_type_id(type), float(eps), s))
+        _lib.check(lib.dis_reduce_pairs(_ptr(partials), npart, _ptr(out3), s))
+    return out3, proj, diff, gnum
+
+
+def scale_by_device_scalar(x, numer, denom=None):
+    """x * numer / denom with numer, denom one-element device tensors (no host sync)."""
+    x = x.contiguous()
+    out = torch.empty_like(x)
+    numer = numer.reshape(1).to(torch.float32).contiguous()
+    with _on(x) as lib:
+        _lib.check(lib.dis_scale_by_device_scalar(_ptr(x), _ptr(out), x.numel(), _ptr(numer), _ptr(denom), _stream(x)))
+    return out
+
+
+def mul(a, b):
+    a, b = a.contiguous(), b.contiguous()
+    out = torch.empty_like(a)
+    with _on(a) as lib:
+        _lib.check(lib.dis_mul(_ptr(a), _ptr(b), _ptr(out), a.numel(), _stream(a)))
+    return out
+
+
+def sobel_forward(x, ksize):
+    x = _chk(x, "x")
+    N, C, H, W = x.shape
+    if C != 1:
+        raise ValueError("SobelFilter expects [N,1,H,W]")
+    out = torch.empty((N, 2, H, W), dtype=x.dtype, device=x.device)
+    with _on(x) as lib:
+        _lib.check(lib.dis_sobel_forward(_ptr(x), _ptr(out), N, H, W, int(ksize), _stream(x)))
+    return out
+
+
+def sobel_backward(grad_out, ksize):
+    grad_out = _chk(grad_out, "grad_out")
+    N, _, H, W = grad_out.shape
+    gx = torch.empty((N, 1, H, W), dtype=grad_out.dtype, device=grad_out.device)
+    with _on(grad_out) as lib:
+        _lib.check(lib.dis_sobel_backward(_ptr(grad_out), _ptr(gx), N, H, W, int(ksize), _stream(grad_out)))
+    return gx
+
+
+def smooth_loss_forward(disp, im, want_grad):
+    """-> (out3 [sum, count, mean], grad_sum|None)"""
+    disp, im = _chk(disp, "disp"), _chk(im, "im")
+    if disp.shape != im.shape or disp.shape[1] != 1:
+        raise ValueError(f"disp and im must both be [N,1,H,W]; got {tuple(disp.shape)} and {tuple(im.shape)}")
+    N, _, H, W = disp.shape
+    gsum = torch.empty_like(disp) if want_grad else None
+    out3 = torch.empty(3, dtype=torch.float32, device=disp.device)
+    with _on(disp) as lib:
+        npart = lib.dis_smooth_loss_num_partials(N, H, W)
+        partials = torch.empty(2 * max(npart, 1), dtype=torch.float32, device=disp.device)
+        s = _stream(disp)
+        _lib.check(lib.dis_smooth_loss_forward(_ptr(disp), _ptr(im), _ptr(gsum), _ptr(partials), N, H, W, s))
+        _lib.check(lib.dis_reduce_pairs(_ptr(partials), npart, _ptr(out3), s))
+    return out3, gsum
+
+
+def flow_warp_forward(x, flow, want_fb_mask=False, want_corners=False):
+    x, flow = _chk(x, "x"), _chk(flow, "flow")
+    N, C, H, W = x.shape
+    if tuple(flow.shape) != (N, 2, H, W):
+        raise ValueError(f"flow must be {(N, 2, H, W)}, got {tuple(flow.shape)}")
+    out = torch.empty_like(x)
+    mask = torch.empty((N, 1, H, W), dtype=x.dtype, device=x.device) if want_fb_mask else None
+    cx = torch.empty((N, 1, H, W), dtype=torch.int32, device=x.device) if want_corners else None
+    cy = torch.empty_like(cx) if want_corners else None
+    with _on(x) as lib:
+        _lib.check(lib.dis_flow_warp_forward(_ptr(x), _ptr(flow), _ptr(out), _ptr(mask), _ptr(cx), _ptr(cy), N, C, H, W,
+                                             _stream(x)))
+    return out, mask, cx, cy
+
+
+def flow_warp_backward(x, flow, grad_out, want_x=True, want_flow=False):
+    flow, grad_out = _chk(flow, "flow"), _chk(grad_out, "grad_out")
+    N, C, H, W = grad_out.shape
+    x = _chk(x, "x") if x is not None else None
+    gx = torch.empty_like(grad_out) if want_x else None
+    gf = torch.empty_like(flow) if want_flow else None
+    with _on(grad_out) as lib:
+        _lib.check(lib.dis_flow_warp_backward(_ptr(x), _ptr(flow), _ptr(grad_out), _ptr(gx), _ptr(gf), N, C, H, W,
+                                              _stream(grad_out)))
+    return gx, gf
+
+
+def lcn_backward(data, lcn, std, g_lcn, g_std, radius, eps):
+    lib = _lib.load()
+    if not hasattr(lib, "dis_lcn_backward"):
+        raise NotImplementedError(
+            "LCN backward: the reference never differentiates through LCN (its inputs are data, "
+            "model/worker.py:430-445); this ABI revision ships the forward only")
+    data = _chk(data, "data")
+    N, C, H, W = data.shape
+    g_lcn = torch.zeros_like(data) if g_lcn is None else _chk(g_lcn, "g_lcn")
+    g_std = torch.zeros_like(data) if g_std is None else _chk(g_std, "g_std")
+    out = torch.empty_like(data)
+    with _on(data) as lib:
+        _lib.check(lib.dis_lcn_backward(_ptr(data), _ptr(g_lcn), _ptr(g_std), _ptr(out), N * C, H, W, int(radius),
+                                        float(eps), _stream(data)))
+    return out

@@ -1,0 +1,262 @@
+// extern "C" surface of libdis_b200.so (declared in include/dis_b200.h): argument validation, batch
+// chunking (grid.z <= 65535) and dispatch to the per-radius kernel instantiations.  No global mutable
+// state: the only static is a thread_local error string.
+#include <string.h>
+#include "photometric_kernels.cuh"
+
+namespace dis {
+
+static thread_local char g_last_error[256] = "";
+void set_last_cuda_error(cudaError_t e) {
+  strncpy(g_last_error, cudaGetErrorString(e), sizeof(g_last_error) - 1);
+  g_last_error[sizeof(g_last_error) - 1] = 0;
+}
+
+// defined in lcn.cu / misc.cu / smooth.cu / flow_warp.cu
+int lcn_forward(const float*, float*, float*, int, int, int, int, float, int, cudaStream_t);
+int pattern_warp_forward(const float*, const float*, float*, float*, int32_t*, int32_t*, int, int, int, cudaStream_t);
+int reduce_pairs(const float*, int, float*, cudaStream_t);
+int scale_by_device_scalar(const float*, float*, size_t, const float*, const float*, cudaStream_t);
+int mul(const float*, const float*, float*, size_t, cudaStream_t);
+int smooth_loss_num_partials(int, int, int);
+int smooth_loss_forward(const float*, const float*, float*, float*, int, int, int, cudaStream_t);
+int sobel_forward(const float*, float*, int, int, int, int, cudaStream_t);
+int sobel_backward(const float*, float*, int, int, int, int, cudaStream_t);
+int flow_warp_forward(const float*, const float*, float*, float*, int32_t*, int32_t*, int, int, int, int, cudaStream_t);
+int flow_warp_backward(const float*, const float*, const float*, float*, float*, int, int, int, int, cudaStream_t);
+
+namespace {
+
+constexpr int MAX_GRID_Z = 65535;
+
+template <typename... P>
+bool aligned16(P... ptrs) {
+  uintptr_t acc = 0;
+  ((acc |= reinterpret_cast<uintptr_t>(ptrs)), ...);
+  return (acc & 15) == 0;
+}
+
+int check_block(int block_size, int type) {
+  if (type < 0 || type > 3) return DIS_ERR_INVALID_LOSS_TYPE;
+  if (block_size < 1 || (block_size & 1) == 0 || block_size / 2 > MAX_R) return DIS_ERR_UNSUPPORTED_BLOCK_SIZE;
+  return DIS_OK;
+}
+
+int dispatch_photometric(int R, const PhotoArgs& a, int type, bool backward, cudaStream_t s) {
+  switch (R) {
+    case 0: return launch_photometric<0>(a, type, backward, s);
+    case 1: return launch_photometric<1>(a, type, backward, s);
+    case 2: return launch_photometric<2>(a, type, backward, s);
+    case 3: return launch_photometric<3>(a, type, backward, s);
+    case 4: return launch_photometric<4>(a, type, backward, s);
+    case 5: return launch_photometric<5>(a, type, backward, s);
+    case 6: return launch_photometric<6>(a, type, backward, s);
+    case 7: return launch_photometric<7>(a, type, backward, s);
+  }
+  return DIS_ERR_UNSUPPORTED_BLOCK_SIZE;
+}
+
+int dispatch_pattern_loss(int R, const PatternLossArgs& a, int type, cudaStream_t s) {
+  switch (R) {
+    case 0: return launch_pattern_loss<0>(a, type, s);
+    case 1: return launch_pattern_loss<1>(a, type, s);
+    case 2: return launch_pattern_loss<2>(a, type, s);
+    case 3: return launch_pattern_loss<3>(a, type, s);
+    case 4: return launch_pattern_loss<4>(a, type, s);
+    case 5: return launch_pattern_loss<5>(a, type, s);
+    case 6: return launch_pattern_loss<6>(a, type, s);
+    case 7: return launch_pattern_loss<7>(a, type, s);
+  }
+  return DIS_ERR_UNSUPPORTED_BLOCK_SIZE;
+}
+
+}  // namespace
+}  // namespace dis
+
+using namespace dis;
+
+extern "C" {
+
+int dis_abi_version(void) { return 1; }
+
+const char* dis_status_string(int status) {
+  switch (status) {
+    case DIS_OK: return "ok";
+    case DIS_ERR_INVALID_LOSS_TYPE: return "invalid loss type";
+    case DIS_ERR_BAD_SHAPE: return "bad shape";
+    case DIS_ERR_UNSUPPORTED_BLOCK_SIZE: return "unsupported block_size (odd, 1..15)";
+    case DIS_ERR_NULL_POINTER: return "null pointer";
+    case DIS_ERR_CUDA_LAUNCH: return "CUDA launch failed";
+    case DIS_ERR_UNSUPPORTED_KSIZE: return "unsupported Sobel ksize (3 or 5)";
+    case DIS_ERR_WORKSPACE_TOO_SMALL: return "workspace too small";
+  }
+  return "unknown status";
+}
+
+const char* dis_last_cuda_error(void) { return g_last_error; }
+
+int dis_lcn_forward(const float* x, float* lcn, float* std_out, int N, int H, int W, int radius, float eps,
+                    void* stream) {
+  if (!x || !lcn || !std_out) return DIS_ERR_NULL_POINTER;
+  if (N < 0 || H < 1 || W < 1 || radius < 1 || radius > 8 || radius >= H || radius >= W) return DIS_ERR_BAD_SHAPE;
+  if (N == 0) return DIS_OK;
+  const int vec_ok = (W % 4 == 0) && aligned16(lcn, std_out);
+  const size_t hw = (size_t)H * W;
+  for (int n0 = 0; n0 < N; n0 += MAX_GRID_Z) {
+    const int nb = N - n0 < MAX_GRID_Z ? N - n0 : MAX_GRID_Z;
+    if (int rc = lcn_forward(x + n0 * hw, lcn + n0 * hw, std_out + n0 * hw, nb, H, W, radius, eps, vec_ok,
+                             as_stream(stream)))
+      return rc;
+  }
+  return DIS_OK;
+}
+
+int dis_photometric_loss_forward(const float* es, const float* ta, float* out, int N, int C, int H, int W,
+                                 int block_size, int type, float eps, void* stream) {
+  if (int rc = check_block(block_size, type)) return rc;
+  if (!es || !ta || !out) return DIS_ERR_NULL_POINTER;
+  if (N < 0 || C < 1 || H < 1 || W < 1) return DIS_ERR_BAD_SHAPE;
+  if (N == 0) return DIS_OK;
+  const size_t hw = (size_t)H * W;
+  for (int n0 = 0; n0 < N; n0 += MAX_GRID_Z) {
+    PhotoArgs a{};
+    a.es = es + (size_t)n0 * C * hw; a.ta = ta + (size_t)n0 * C * hw; a.out = out + (size_t)n0 * hw;
+    a.N = N - n0 < MAX_GRID_Z ? N - n0 : MAX_GRID_Z; a.C = C; a.H = H; a.W = W;
+    a.eps = eps; a.inv_k2 = 1.0f / (float)(block_size * block_size);
+    a.vec_ok = (W % 4 == 0) && aligned16(out);
+    if (int rc = dispatch_photometric(block_size / 2, a, type, false, as_stream(stream))) return rc;
+  }
+  return DIS_OK;
+}
+
+int dis_photometric_loss_backward(const float* es, const float* ta, const float* grad_out, float* grad_es, int N,
+                                  int C, int H, int W, int block_size, int type, float eps, void* stream) {
+  if (int rc = check_block(block_size, type)) return rc;
+  if (!es || !ta || !grad_out || !grad_es) return DIS_ERR_NULL_POINTER;
+  if (N < 0 || C < 1 || H < 1 || W < 1 || C > MAX_GRID_Z) return DIS_ERR_BAD_SHAPE;
+  if (N == 0) return DIS_OK;
+  const size_t hw = (size_t)H * W;
+  const int step = MAX_GRID_Z / C;
+  for (int n0 = 0; n0 < N; n0 += step) {
+    PhotoArgs a{};
+    a.es = es + (size_t)n0 * C * hw; a.ta = ta + (size_t)n0 * C * hw; a.grad_out = grad_out + (size_t)n0 * hw;
+    a.grad_es = grad_es + (size_t)n0 * C * hw;
+    a.N = N - n0 < step ? N - n0 : step; a.C = C; a.H = H; a.W = W;
+    a.eps = eps; a.inv_k2 = 1.0f / (float)(block_size * block_size);
+    a.vec_ok = (W % 4 == 0) && aligned16(grad_es);
+    if (int rc = dispatch_photometric(block_size / 2, a, type, true, as_stream(stream))) return rc;
+  }
+  return DIS_OK;
+}
+
+int dis_pattern_warp_forward(const float* disp, const float* pattern, float* proj, float* dproj_ddisp,
+                             int32_t* corner_x0, int32_t* corner_y0, int N, int H, int W, void* stream) {
+  if (!disp || !pattern || !proj) return DIS_ERR_NULL_POINTER;
+  if (N < 0 || H < 2 || W < 2) return DIS_ERR_BAD_SHAPE;
+  if (N == 0) return DIS_OK;
+  return pattern_warp_forward(disp, pattern, proj, dproj_ddisp, corner_x0, corner_y0, N, H, W, as_stream(stream));
+}
+
+int dis_pattern_loss_num_partials(int N, int H, int W) {
+  if (N < 0 || H < 1 || W < 1) return DIS_ERR_BAD_SHAPE;
+  return N * ((H + TH - 1) / TH) * ((W + TW - 1) / TW);
+}
+
+int dis_pattern_loss_forward(const float* disp, const float* im, const float* std_in, const float* pattern,
+                             float* proj, float* diff, float* grad_num, float* partials, int N, int H, int W,
+                             int block_size, int type, float eps, void* stream) {
+  if (int rc = check_block(block_size, type)) return rc;
+  if (!disp || !im || !pattern || !partials) return DIS_ERR_NULL_POINTER;
+  if (N < 0 || H < 2 || W < 2) return DIS_ERR_BAD_SHAPE;
+  if (N == 0) return DIS_OK;
+  const size_t hw = (size_t)H * W;
+  const int per_frame = ((H + TH - 1) / TH) * ((W + TW - 1) / TW);
+  for (int n0 = 0; n0 < N; n0 += MAX_GRID_Z) {
+    PatternLossArgs a{};
+    a.disp = disp + n0 * hw; a.im = im + n0 * hw; a.std_in = std_in ? std_in + n0 * hw : nullptr;
+    a.pattern = pattern;
+    a.proj = proj ? proj + n0 * hw : nullptr; a.diff = diff ? diff + n0 * hw : nullptr;
+    a.grad_num = grad_num ? grad_num + n0 * hw : nullptr;
+    a.partials = partials + (size_t)2 * n0 * per_frame;
+    a.N = N - n0 < MAX_GRID_Z ? N - n0 : MAX_GRID_Z; a.H = H; a.W = W;
+    a.eps = eps; a.inv_k2 = 1.0f / (float)(block_size * block_size);
+    a.inv_w = 1.0f / (float)(W - 1); a.inv_h = 1.0f / (float)(H - 1);
+    a.vec_ok = (W % 4 == 0) && aligned16(proj, diff, grad_num);
+    if (int rc = dispatch_pattern_loss(block_size / 2, a, type, as_stream(stream))) return rc;
+  }
+  return DIS_OK;
+}
+
+int dis_reduce_pairs(const float* partials, int n, float* out3, void* stream) {
+  if (!partials || !out3) return DIS_ERR_NULL_POINTER;
+  if (n < 0) return DIS_ERR_BAD_SHAPE;
+  return reduce_pairs(partials, n, out3, as_stream(stream));
+}
+
+int dis_scale_by_device_scalar(const float* in, float* out, size_t n, const float* numer, const float* denom,
+                               void* stream) {
+  if (!in || !out || !numer) return DIS_ERR_NULL_POINTER;
+  if (n == 0) return DIS_OK;
+  return scale_by_device_scalar(in, out, n, numer, denom, as_stream(stream));
+}
+
+int dis_mul(const float* a, const float* b, float* out, size_t n, void* stream) {
+  if (!a || !b || !out) return DIS_ERR_NULL_POINTER;
+  if (n == 0) return DIS_OK;
+  return mul(a, b, out, n, as_stream(stream));
+}
+
+int dis_sobel_forward(const float* x, float* out, int N, int H, int W, int ksize, void* stream) {
+  if (ksize != 3 && ksize != 5) return DIS_ERR_UNSUPPORTED_KSIZE;
+  if (!x || !out) return DIS_ERR_NULL_POINTER;
+  if (N < 0 || H < 1 || W < 1) return DIS_ERR_BAD_SHAPE;
+  if (N == 0) return DIS_OK;
+  return sobel_forward(x, out, N, H, W, ksize, as_stream(stream));
+}
+
+int dis_sobel_backward(const float* grad_out, float* grad_x, int N, int H, int W, int ksize, void* stream) {
+  if (ksize != 3 && ksize != 5) return DIS_ERR_UNSUPPORTED_KSIZE;
+  if (!grad_out || !grad_x) return DIS_ERR_NULL_POINTER;
+  if (N < 0 || H < 1 || W < 1) return DIS_ERR_BAD_SHAPE;
+  if (N == 0) return DIS_OK;
+  return sobel_backward(grad_out, grad_x, N, H, W, ksize, as_stream(stream));
+}
+
+int dis_smooth_loss_num_partials(int N, int H, int W) {
+  if (N < 0 || H < 1 || W < 1) return DIS_ERR_BAD_SHAPE;
+  return smooth_loss_num_partials(N, H, W);
+}
+
+int dis_smooth_loss_forward(const float* disp, const float* im, float* grad_sum, float* partials, int N, int H,
+                            int W, void* stream) {
+  if (!disp || !im || !partials) return DIS_ERR_NULL_POINTER;
+  if (N < 0 || H < 1 || W < 1) return DIS_ERR_BAD_SHAPE;
+  if (N == 0) return DIS_OK;
+  const size_t hw = (size_t)H * W;
+  const int per_frame = smooth_loss_num_partials(1, H, W);
+  for (int n0 = 0; n0 < N; n0 += MAX_GRID_Z) {
+    const int nb = N - n0 < MAX_GRID_Z ? N - n0 : MAX_GRID_Z;
+    if (int rc = smooth_loss_forward(disp + n0 * hw, im + n0 * hw, grad_sum ? grad_sum + n0 * hw : nullptr,
+                                     partials + (size_t)2 * n0 * per_frame, nb, H, W, as_stream(stream)))
+      return rc;
+  }
+  return DIS_OK;
+}
+
+int dis_flow_warp_forward(const float* x, const float* flow, float* out, float* fb_mask_out, int32_t* corner_x0,
+                          int32_t* corner_y0, int N, int C, int H, int W, void* stream) {
+  if (!x || !flow || !out) return DIS_ERR_NULL_POINTER;
+  if (N < 0 || C < 1 || H < 2 || W < 2 || (fb_mask_out && C != 2)) return DIS_ERR_BAD_SHAPE;
+  if (N == 0) return DIS_OK;
+  return flow_warp_forward(x, flow, out, fb_mask_out, corner_x0, corner_y0, N, C, H, W, as_stream(stream));
+}
+
+int dis_flow_warp_backward(const float* x, const float* flow, const float* grad_out, float* grad_x,
+                           float* grad_flow, int N, int C, int H, int W, void* stream) {
+  if (!flow || !grad_out || (!grad_x && !grad_flow) || (grad_flow && !x)) return DIS_ERR_NULL_POINTER;
+  if (N < 0 || C < 1 || H < 2 || W < 2) return DIS_ERR_BAD_SHAPE;
+  if (N == 0) return DIS_OK;
+  return flow_warp_backward(x, flow, grad_out, grad_x, grad_flow, N, C, H, W, as_stream(stream));
+}
+
+}  // extern "C"

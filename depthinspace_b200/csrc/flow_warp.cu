@@ -1,0 +1,124 @@
+// Optical-flow warp used by DIS-MF fusion.
+// reference: warp(x, flow), model/multi_frame_networks.py:83-99
+//   (u + flow_x, v + flow_y) -> 2 * (c / (size-1) - 0.5) -> grid_sample(bilinear, zeros, align_corners=True)
+// plus the forward-backward consistency mask of gather_warped_xyz (:205-207).
+//
+// The sampling coordinates and the four corner weights depend only on (n, h, w), so one thread owns
+// one pixel and loops over the C channels: the coordinate math is paid once and every channel costs
+// four (mostly L1-resident) gathers and one coalesced store.
+// Backward w.r.t. x is a true scatter; like ATen (GridSampler.cuh safe_add_2d) it uses fp32 global
+// reductions (RED.ADD), so it is reproducible up to summation order only.  Backward w.r.t. flow is a
+// per-pixel gather and is exact/deterministic.
+#include "common.cuh"
+
+namespace dis {
+namespace {
+
+__device__ __forceinline__ void flow_bilinear(const float* __restrict__ flow, size_t n, int h, int w, int H, int W,
+                                              float inv_w, float inv_h, Bilinear& b, float& fx, float& fy) {
+  const size_t hw = (size_t)H * W;
+  fx = ld_stream(flow + (n * 2 + 0) * hw + (size_t)h * W + w);
+  fy = ld_stream(flow + (n * 2 + 1) * hw + (size_t)h * W + w);
+  const float gx = normalize_coord(fadd(fx, (float)w), inv_w);
+  const float gy = normalize_coord(fadd(fy, (float)h), inv_h);
+  bilinear_setup<false>(gx, gy, H, W, b);
+}
+
+__global__ void __launch_bounds__(256) flow_warp_fwd_kernel(const float* __restrict__ x, const float* __restrict__ flow,
+                                                            float* __restrict__ out, float* __restrict__ fb_mask,
+                                                            int32_t* __restrict__ cx0, int32_t* __restrict__ cy0,
+                                                            int C, int H, int W, float inv_w, float inv_h, size_t total) {
+  const size_t hw = (size_t)H * W;
+  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (size_t)gridDim.x * blockDim.x) {
+    const size_t n = idx / hw;
+    const int pix = (int)(idx - n * hw), h = pix / W, w = pix - h * W;
+    Bilinear b;
+    float fx, fy;
+    flow_bilinear(flow, n, h, w, H, W, inv_w, inv_h, b, fx, fy);
+    if (cx0) cx0[idx] = b.x0;
+    if (cy0) cy0[idx] = b.y0;
+    float o0 = 0.f, o1 = 0.f;
+    for (int c = 0; c < C; ++c) {
+      const Corners cr = fetch_corners(x + (n * C + c) * hw, H, W, b);
+      const float v = blend(cr, b);
+      __stcs(out + (n * C + c) * hw + pix, v);
+      if (c == 0) o0 = v;
+      if (c == 1) o1 = v;
+    }
+    if (fb_mask) {
+      // (f + f_warped)^2 summed < 0.01 * (|f|^2 + |f_warped|^2) + 0.5   (multi_frame_networks.py:205-207)
+      const float sx = fadd(fx, o0), sy = fadd(fy, o1);
+      const float diff = fadd(fmul(sx, sx), fmul(sy, sy));
+      const float mag = fadd(fadd(fmul(fx, fx), fmul(fy, fy)), fadd(fmul(o0, o0), fmul(o1, o1)));
+      fb_mask[idx] = (diff < fadd(fmul(0.01f, mag), 0.5f)) ? 1.0f : 0.0f;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) flow_warp_bwd_kernel(const float* __restrict__ x, const float* __restrict__ flow,
+                                                            const float* __restrict__ go, float* __restrict__ gx,
+                                                            float* __restrict__ gflow, int C, int H, int W,
+                                                            float inv_w, float inv_h, size_t total) {
+  const size_t hw = (size_t)H * W;
+  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (size_t)gridDim.x * blockDim.x) {
+    const size_t n = idx / hw;
+    const int pix = (int)(idx - n * hw), h = pix / W, w = pix - h * W;
+    Bilinear b;
+    float fx, fy;
+    flow_bilinear(flow, n, h, w, H, W, inv_w, inv_h, b, fx, fy);
+    const bool bnw = in_bounds(b.y0, b.x0, H, W), bne = in_bounds(b.y0, b.x0 + 1, H, W);
+    const bool bsw = in_bounds(b.y0 + 1, b.x0, H, W), bse = in_bounds(b.y0 + 1, b.x0 + 1, H, W);
+    const ptrdiff_t o_nw = (ptrdiff_t)b.y0 * W + b.x0;
+    float gfx = 0.f, gfy = 0.f;
+    for (int c = 0; c < C; ++c) {
+      const float g = ld_stream(go + (n * C + c) * hw + pix);
+      if (gx) {
+        float* p = gx + (n * C + c) * hw + o_nw;
+        if (bnw) atomicAdd(p, b.wnw * g);
+        if (bne) atomicAdd(p + 1, b.wne * g);
+        if (bsw) atomicAdd(p + W, b.wsw * g);
+        if (bse) atomicAdd(p + W + 1, b.wse * g);
+      }
+      if (gflow) {
+        const Corners cr = fetch_corners(x + (n * C + c) * hw, H, W, b);
+        gfx = fmaf(blend_dx(cr, b), g, gfx);
+        gfy = fmaf(blend_dy(cr, b), g, gfy);
+      }
+    }
+    if (gflow) {
+      gflow[(n * 2 + 0) * hw + pix] = ((b.gx_mult * gfx) * 2.0f) * inv_w;
+      gflow[(n * 2 + 1) * hw + pix] = ((b.gy_mult * gfy) * 2.0f) * inv_h;
+    }
+  }
+}
+
+inline int flat_grid(size_t total) {
+  const size_t want = (total + 255) / 256, cap = 148 * 32;
+  return (int)(want < cap ? (want ? want : 1) : cap);
+}
+
+}  // namespace
+
+int flow_warp_forward(const float* x, const float* flow, float* out, float* fb_mask, int32_t* cx0, int32_t* cy0, int N,
+                      int C, int H, int W, cudaStream_t s) {
+  const size_t total = (size_t)N * H * W;
+  flow_warp_fwd_kernel<<<flat_grid(total), 256, 0, s>>>(x, flow, out, fb_mask, cx0, cy0, C, H, W,
+                                                        1.0f / (float)(W - 1), 1.0f / (float)(H - 1), total);
+  return check_launch();
+}
+
+int flow_warp_backward(const float* x, const float* flow, const float* go, float* gx, float* gflow, int N, int C, int H,
+                       int W, cudaStream_t s) {
+  const size_t total = (size_t)N * H * W;
+  if (gx) {
+    cudaError_t e = cudaMemsetAsync(gx, 0, sizeof(float) * total * C, s);
+    if (e != cudaSuccess) { set_last_cuda_error(e); return DIS_ERR_CUDA_LAUNCH; }
+  }
+  flow_warp_bwd_kernel<<<flat_grid(total), 256, 0, s>>>(x, flow, go, gx, gflow, C, H, W, 1.0f / (float)(W - 1),
+                                                        1.0f / (float)(H - 1), total);
+  return check_launch();
+}
+
+}  // namespace dis

@@ -1,0 +1,76 @@
+// One translation unit per window radius R = DIS_R (block_size = 2R+1): keeps every k x k loop fully
+// unrolled without a single multi-minute compile.  build.py compiles R = 0..7 in parallel.
+#include "photometric_kernels.cuh"
+
+#ifndef DIS_R
+#error "compile with -DDIS_R=<window radius>"
+#endif
+
+namespace dis {
+namespace {
+
+template <typename K>
+int prepare(K kernel, size_t smem) {
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) { set_last_cuda_error(e); return DIS_ERR_CUDA_LAUNCH; }
+  }
+  return DIS_OK;
+}
+
+dim3 tile_grid(int H, int W, int z) { return dim3((W + TW - 1) / TW, (H + TH - 1) / TH, z); }
+
+template <int TYPE, int R>
+int photometric_t(const PhotoArgs& a, bool backward, cudaStream_t s) {
+  const dim3 block(16, 16);
+  if (!backward) {
+    const size_t smem = photo_smem_bytes<R>(false);
+    if (int rc = prepare(photometric_fwd_kernel<TYPE, R>, smem)) return rc;
+    photometric_fwd_kernel<TYPE, R><<<tile_grid(a.H, a.W, a.N), block, smem, s>>>(a);
+  } else {
+    const size_t smem = photo_smem_bytes<R>(true);
+    if (int rc = prepare(photometric_bwd_kernel<TYPE, R>, smem)) return rc;
+    photometric_bwd_kernel<TYPE, R><<<tile_grid(a.H, a.W, a.N * a.C), block, smem, s>>>(a);
+  }
+  return check_launch();
+}
+
+template <int TYPE, int R>
+int pattern_loss_t(const PatternLossArgs& a, cudaStream_t s) {
+  const dim3 block(16, 16);
+  const size_t smem = pattern_smem_bytes<R>();
+  if (a.grad_num) {
+    if (int rc = prepare(pattern_loss_kernel<TYPE, R, true>, smem)) return rc;
+    pattern_loss_kernel<TYPE, R, true><<<tile_grid(a.H, a.W, a.N), block, smem, s>>>(a);
+  } else {
+    if (int rc = prepare(pattern_loss_kernel<TYPE, R, false>, smem)) return rc;
+    pattern_loss_kernel<TYPE, R, false><<<tile_grid(a.H, a.W, a.N), block, smem, s>>>(a);
+  }
+  return check_launch();
+}
+
+}  // namespace
+
+template <>
+int launch_photometric<DIS_R>(const PhotoArgs& a, int type, bool backward, cudaStream_t s) {
+  switch (type) {
+    case MSE: return photometric_t<MSE, DIS_R>(a, backward, s);
+    case SAD: return photometric_t<SAD, DIS_R>(a, backward, s);
+    case CENSUS_MSE: return photometric_t<CENSUS_MSE, DIS_R>(a, backward, s);
+    case CENSUS_SAD: return photometric_t<CENSUS_SAD, DIS_R>(a, backward, s);
+  }
+  return DIS_ERR_INVALID_LOSS_TYPE;
+}
+
+template <>
+int launch_pattern_loss<DIS_R>(const PatternLossArgs& a, int type, cudaStream_t s) {
+  switch (type) {
+    case MSE: return pattern_loss_t<MSE, DIS_R>(a, s);
+    case SAD: return pattern_loss_t<SAD, DIS_R>(a, s);
+    case CENSUS_MSE: return pattern_loss_t<CENSUS_MSE, DIS_R>(a, s);
+    case CENSUS_SAD: return pattern_loss_t<CENSUS_SAD, DIS_R>(a, s);
+  }
+  return DIS_ERR_INVALID_LOSS_TYPE;
+}
+
+}  // namespace dis

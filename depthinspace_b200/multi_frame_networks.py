@@ -1,0 +1,41 @@
+"""Host-side mirror of the hot-path pieces of the reference's model/multi_frame_networks.py.
+
+    warp(x, flow) -> x_prj                                     reference :83-99
+    warp_with_fb_mask(flow_ji, flow_ij) -> (flow_ji warped, mask)   reference :202-209 (gather_warped_xyz)
+
+Bilinear resampling with zeros padding and align_corners=True, bit-compatible with the reference's
+normalise -> grid_sample round trip, executed by libdis_b200.so.  Gradients flow to x (and to flow when
+it requires grad, which the reference never needs).
+"""
+import torch
+
+from . import _ops
+
+
+class _FlowWarp(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, flow):
+        out, _, _, _ = _ops.flow_warp_forward(x, flow)
+        ctx.save_for_backward(x if ctx.needs_input_grad[1] else None, flow)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        x, flow = ctx.saved_tensors
+        gx, gf = _ops.flow_warp_backward(x, flow, grad_out.contiguous(), want_x=ctx.needs_input_grad[0],
+                                         want_flow=ctx.needs_input_grad[1])
+        return gx, gf
+
+
+def warp(x, flow):
+    """x [bs,C,h,w], flow [bs,2,h,w] (pixels) -> x sampled at (u + flow_x, v + flow_y)."""
+    return _FlowWarp.apply(x, flow)
+
+
+def warp_with_fb_mask(flow_back, flow_fwd):
+    """flow10 = warp(flow_back, flow_fwd) and the forward-backward mask
+    |f + f10|^2 < 0.5 + 0.01 (|f|^2 + |f10|^2) as float [bs,1,h,w] -- one fused, gradient-free call
+    (the reference computes it under torch.no_grad(), :202-209)."""
+    with torch.no_grad():
+        out, mask, _, _ = _ops.flow_warp_forward(flow_back, flow_fwd, want_fb_mask=True)
+    return out, mask

@@ -1,0 +1,208 @@
+"""Host-side mirror of the hot-path modules of the reference's model/networks.py.
+
+Same constructor / call signatures and return values as the reference classes, with every
+forward and backward executed by libdis_b200.so:
+
+    LCN(radius, epsilon)(data) -> (lcn, std)                                   reference :663-689
+    RectifiedPatternSimilarityLoss(im_height, im_width, pattern,
+        loss_type='census_sad', loss_eps=0.5)(disp0, im, std=None,
+        output_mean=True) -> (val, pattern_proj)                               reference :336-377
+    DisparitySmoothLoss()(disp, im) -> scalar                                  reference :411-431
+    SobelFilter(norm=False, ksize=5)(x) -> [N,2,H,W] | [N,1,H,W]               reference :693-730
+
+Differences that are deliberate:
+  * no torch.cuda.synchronize() around forward (the reference's TimedModule does, :66-71);
+  * batch-wide ratios can be formed over a torch.distributed process group
+    (``process_group=``) so that data-parallel ranks reproduce single-process semantics;
+  * ``RectifiedPatternSimilarityLoss(..., return_pattern_proj=False)`` skips materialising
+    pattern_proj (the workers ignore it, single_frame_worker.py:114).
+"""
+import torch
+
+from . import _ops
+from .parallel import all_reduce_sum_
+
+
+class LCN(torch.nn.Module):
+    """Local contrast normalisation, reference model/networks.py:663-689."""
+
+    def __init__(self, radius, epsilon):
+        super().__init__()
+        self.radius = radius
+        self.epsilon = epsilon
+
+    def forward(self, data):
+        if data.requires_grad and torch.is_grad_enabled():
+            return _LCNFunction.apply(data, self.radius, self.epsilon)
+        return _ops.lcn_forward(data, self.radius, self.epsilon)
+
+    tforward = forward
+
+
+class _LCNFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, data, radius, eps):
+        lcn, std = _ops.lcn_forward(data, radius, eps)
+        ctx.save_for_backward(data, lcn, std)
+        ctx.radius, ctx.eps = radius, eps
+        return lcn, std
+
+    @staticmethod
+    def backward(ctx, g_lcn, g_std):
+        data, lcn, std = ctx.saved_tensors
+        return _ops.lcn_backward(data, lcn, std, g_lcn, g_std, ctx.radius, ctx.eps), None, None
+
+
+class _PatternLossMean(torch.autograd.Function):
+    """val = sum(mask * diff) / sum(mask) with the un-normalised gradient stashed by the forward pass."""
+
+    @staticmethod
+    def forward(ctx, disp0, im, std, pattern, block_size, type_id, eps, want_proj, group):
+        ctx.set_materialize_grads(False)
+        need_grad = ctx.needs_input_grad[0]
+        out3, proj, _, gnum = _ops.pattern_loss_forward(disp0, im, std, pattern, block_size, type_id, eps,
+                                                        want_proj=want_proj, want_diff=False, want_grad=need_grad)
+        if group is not None:
+            all_reduce_sum_(out3[:2], group)
+            val = out3[0] / out3[1]
+        else:
+            val = out3[2].clone()
+        ctx.save_for_backward(gnum, out3, disp0 if want_proj else None, pattern if want_proj else None)
+        if proj is None:
+            proj = disp0.new_empty(0)
+            ctx.mark_non_differentiable(proj)
+        return val, proj
+
+    @staticmethod
+    def backward(ctx, g_val, g_proj):
+        gnum, out3, disp0, pattern = ctx.saved_tensors
+        if g_val is None:
+            g_val = torch.zeros((), dtype=torch.float32, device=gnum.device)
+        grad = _ops.scale_by_device_scalar(gnum, g_val, out3[1:2])
+        if g_proj is not None and disp0 is not None and g_proj.numel() == disp0.numel():
+            _, dproj, _, _ = _ops.pattern_warp(disp0, pattern, want_dproj=True)
+            grad = grad + _ops.mul(g_proj.contiguous(), dproj)
+        return grad, None, None, None, None, None, None, None, None
+
+
+class _PatternLossMap(torch.autograd.Function):
+    """output_mean=False: per-pixel loss map (reference :375-376)."""
+
+    @staticmethod
+    def forward(ctx, disp0, im, std, pattern, block_size, type_id, eps):
+        ctx.set_materialize_grads(False)
+        _, proj, diff, _ = _ops.pattern_loss_forward(disp0, im, None, pattern, block_size, type_id, eps,
+                                                     want_proj=True, want_diff=True, want_grad=False)
+        ctx.save_for_backward(disp0, im, pattern, proj)
+        ctx.cfg = (block_size, type_id, eps)
+        return diff, proj
+
+    @staticmethod
+    def backward(ctx, g_diff, g_proj):
+        disp0, im, pattern, proj = ctx.saved_tensors
+        block_size, type_id, eps = ctx.cfg
+        if g_diff is not None:
+            g_e = _ops.photometric_loss_backward(proj, im, g_diff.contiguous(), block_size, type_id, eps)
+            if g_proj is not None:
+                g_e = g_e + g_proj
+        elif g_proj is not None:
+            g_e = g_proj.contiguous()
+        else:
+            return (None,) * 7
+        _, dproj, _, _ = _ops.pattern_warp(disp0, pattern, want_dproj=True)
+        return _ops.mul(g_e, dproj), None, None, None, None, None, None
+
+
+class RectifiedPatternSimilarityLoss(torch.nn.Module):
+    """Photometric loss between the disparity-warped projector pattern and the LCN image,
+    reference model/networks.py:336-377."""
+
+    def __init__(self, im_height, im_width, pattern, loss_type='census_sad', loss_eps=0.5,
+                 block_size=9, return_pattern_proj=True, process_group=None):
+        super().__init__()
+        self.im_height = im_height
+        self.im_width = im_width
+        # the reference averages the (3 identical) channels once, :344
+        self.pattern = pattern.mean(dim=1, keepdim=True).contiguous()
+        self.loss_type = loss_type
+        self.loss_eps = loss_eps
+        self.block_size = block_size          # hard-coded 9 in the reference, :372
+        self.return_pattern_proj = return_pattern_proj
+        self.process_group = process_group
+
+    def forward(self, disp0, im, std=None, output_mean=True):
+        if tuple(disp0.shape[-2:]) != (self.im_height, self.im_width):
+            raise ValueError(f"disp0 is {tuple(disp0.shape)}, loss was built for {self.im_height}x{self.im_width}")
+        self.pattern = self.pattern.to(device=disp0.device, dtype=torch.float32)
+        type_id = _ops.loss_type_id(self.loss_type)
+        im = im.contiguous()
+        if output_mean:
+            val, proj = _PatternLossMean.apply(disp0, im, std, self.pattern, self.block_size, type_id, self.loss_eps,
+                                               self.return_pattern_proj, self.process_group)
+            return val, (proj if self.return_pattern_proj else None)
+        return _PatternLossMap.apply(disp0, im, std, self.pattern, self.block_size, type_id, self.loss_eps)
+
+    tforward = forward
+
+
+class _SobelFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, ksize):
+        ctx.ksize = ksize
+        return _ops.sobel_forward(x, ksize)
+
+    @staticmethod
+    def backward(ctx, g):
+        return _ops.sobel_backward(g.contiguous(), ctx.ksize), None
+
+
+class SobelFilter(torch.nn.Module):
+    """reference model/networks.py:693-730 (weights are constants here, not nn.Parameters: the reference
+    never optimises them and only pays for their useless weight gradients)."""
+
+    def __init__(self, norm=False, ksize=5):
+        super().__init__()
+        if ksize not in (3, 5):
+            raise ValueError("ksize must be 3 or 5")
+        self.ksize = ksize
+        self.norm = norm
+
+    def forward(self, x):
+        g = _SobelFunction.apply(x, self.ksize)
+        if self.norm:
+            return torch.sqrt(g[:, 0:1] ** 2 + g[:, 1:2] ** 2 + 1e-8)
+        return g
+
+    tforward = forward
+
+
+class _SmoothLoss(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, disp, im, group):
+        out3, gsum = _ops.smooth_loss_forward(disp, im, want_grad=ctx.needs_input_grad[0])
+        if group is not None:
+            all_reduce_sum_(out3[:2], group)
+            val = out3[0] / out3[1]
+        else:
+            val = out3[2].clone()
+        ctx.save_for_backward(gsum, out3)
+        return val
+
+    @staticmethod
+    def backward(ctx, g_val):
+        gsum, out3 = ctx.saved_tensors
+        return _ops.scale_by_device_scalar(gsum, g_val, out3[1:2]), None, None
+
+
+class DisparitySmoothLoss(torch.nn.Module):
+    """Edge-aware smoothness, reference model/networks.py:411-431 (gradient flows to disp only:
+    the ambient image is data)."""
+
+    def __init__(self, process_group=None):
+        super().__init__()
+        self.process_group = process_group
+
+    def forward(self, disp, im):
+        return _SmoothLoss.apply(disp, im.contiguous(), self.process_group)
+
+    tforward = forward

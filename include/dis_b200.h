@@ -1,0 +1,130 @@
+/*
+ * dis_b200.h -- C-ABI of libdis_b200.so: the B200 (sm_100a) implementation of
+ * DepthInSpace's self-supervision hot path (LCN -> pattern / flow warp -> block-window
+ * photometric loss -> edge-aware smoothness, forward and backward).
+ *
+ * This is the drop-in boundary.  The reference (idiap/DepthInSpace) binds this path
+ * through the pybind module `ext_cuda` of the un-vendored Connecting-the-Dots torchext
+ * (model/ext_functions.py:32-39) and through torch ops inside nn.Modules
+ * (model/networks.py, model/multi_frame_networks.py).  Each entry point below names the
+ * reference interface it replaces.  INTEGRATION.md shows the binding a maintainer adds.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer to contiguous fp32 NCHW data owned by the caller;
+ *     nothing is retained across calls, no global mutable state, re-entrant (the backward
+ *     half runs on autograd's worker thread, model/ext_functions.py:130-140);
+ *   - `stream` is a cudaStream_t (CUstream) passed as void*; work is enqueued, never
+ *     synchronised;
+ *   - return value: DIS_OK (0) or a negative dis_status; dis_status_string() names it.
+ *     The Python shim raises (the reference raises Exception('invalid loss type'),
+ *     model/ext_functions.py:153);
+ *   - loss `type`: 0 mse, 1 sad, 2 census_mse, 3 census_sad (model/ext_functions.py:142-154);
+ *   - block_size: odd, 1..15.
+ */
+#ifndef DIS_B200_H_
+#define DIS_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define DIS_API __attribute__((visibility("default")))
+#else
+#define DIS_API
+#endif
+
+typedef enum {
+  DIS_OK = 0,
+  DIS_ERR_INVALID_LOSS_TYPE = -1, /* model/ext_functions.py:153 */
+  DIS_ERR_BAD_SHAPE = -2,
+  DIS_ERR_UNSUPPORTED_BLOCK_SIZE = -3,
+  DIS_ERR_NULL_POINTER = -4,
+  DIS_ERR_CUDA_LAUNCH = -5,
+  DIS_ERR_UNSUPPORTED_KSIZE = -6,
+  DIS_ERR_WORKSPACE_TOO_SMALL = -7
+} dis_status;
+
+DIS_API int dis_abi_version(void);
+DIS_API const char* dis_status_string(int status);
+/* last CUDA error text seen by this thread inside the library (for DIS_ERR_CUDA_LAUNCH) */
+DIS_API const char* dis_last_cuda_error(void);
+
+/* ---- a1  LCN.tforward, model/networks.py:679-689 ------------------------------------
+ * x [N,1,H,W] -> lcn, std [N,1,H,W].  radius 1..8.  Window sums are accumulated in fp64. */
+DIS_API int dis_lcn_forward(const float* x, float* lcn, float* std_out, int N, int H, int W,
+                            int radius, float eps, void* stream);
+
+/* ---- a4  ext_cuda.photometric_loss_forward / _backward, model/ext_functions.py:124,137 --
+ * es, ta [N,C,H,W] -> out [N,1,H,W];  grad_out [N,1,H,W] -> grad_es [N,C,H,W]
+ * (gradient w.r.t. es only, model/ext_functions.py:140). */
+DIS_API int dis_photometric_loss_forward(const float* es, const float* ta, float* out, int N, int C,
+                                         int H, int W, int block_size, int type, float eps,
+                                         void* stream);
+DIS_API int dis_photometric_loss_backward(const float* es, const float* ta, const float* grad_out,
+                                          float* grad_es, int N, int C, int H, int W,
+                                          int block_size, int type, float eps, void* stream);
+
+/* ---- a3  disparity-driven pattern warp, model/networks.py:356-367 --------------------
+ * pattern [H,W] (batch-shared), disp [N,1,H,W] -> proj [N,1,H,W]; optional outputs:
+ * dproj_ddisp [N,1,H,W] (autograd chain of :358-367), corner_x0 / corner_y0 int32 [N,1,H,W]
+ * (floor()ed source indices, for bit-exact index checks). */
+DIS_API int dis_pattern_warp_forward(const float* disp, const float* pattern, float* proj,
+                                     float* dproj_ddisp, int32_t* corner_x0, int32_t* corner_y0,
+                                     int N, int H, int W, void* stream);
+
+/* ---- a3+a4 fused  RectifiedPatternSimilarityLoss.tforward, model/networks.py:354-377 --
+ * One pass: warp -> k x k window loss -> sigma-weighted partial sums, and (when grad_num != NULL)
+ * the un-normalised gradient  d(sum(mask*diff)) / d disp  [N,1,H,W].
+ *   std         may be NULL (mask = ones, :368-370)
+ *   proj, diff  optional [N,1,H,W] outputs (pattern_proj :367, per-pixel loss map :376)
+ *   partials    float[2 * dis_pattern_loss_num_partials(N,H,W)]: per-CTA (num, den) pairs
+ * Follow with dis_reduce_pairs() to obtain (num, den, num/den) on the device. */
+DIS_API int dis_pattern_loss_num_partials(int N, int H, int W);
+DIS_API int dis_pattern_loss_forward(const float* disp, const float* im, const float* std_in,
+                                     const float* pattern, float* proj, float* diff, float* grad_num,
+                                     float* partials, int N, int H, int W, int block_size, int type,
+                                     float eps, void* stream);
+
+/* Deterministic fixed-order reduction of n (a,b) pairs: out = {sum a, sum b, sum a / sum b}. */
+DIS_API int dis_reduce_pairs(const float* partials, int n, float* out3, void* stream);
+
+/* out[i] = in[i] * (*numer) / (*denom) (denom may be NULL = 1).  Scalars live on the device
+ * so no host synchronisation is needed between forward and backward. */
+DIS_API int dis_scale_by_device_scalar(const float* in, float* out, size_t n, const float* numer,
+                                       const float* denom, void* stream);
+/* out[i] = a[i] * b[i] */
+DIS_API int dis_mul(const float* a, const float* b, float* out, size_t n, void* stream);
+
+/* ---- a5  SobelFilter / DisparitySmoothLoss, model/networks.py:697-730, 419-431 ---------
+ * dis_sobel_forward: x [N,1,H,W] -> out [N,2,H,W] (gx, gy), replicate padding, ksize 3 or 5.
+ * dis_sobel_backward: adjoint, grad_out [N,2,H,W] -> grad_x [N,1,H,W].
+ * dis_smooth_loss_forward: one pass producing per-CTA partial sums of
+ *   | sobel(disp) * exp(-|255 sobel(im)|) |  (pairs (sum, 0)) and, when grad_sum != NULL,
+ *   d(sum)/d disp [N,1,H,W]  (divide by 2*N*H*W for the mean, :431). */
+DIS_API int dis_sobel_forward(const float* x, float* out, int N, int H, int W, int ksize, void* stream);
+DIS_API int dis_sobel_backward(const float* grad_out, float* grad_x, int N, int H, int W, int ksize,
+                               void* stream);
+DIS_API int dis_smooth_loss_num_partials(int N, int H, int W);
+DIS_API int dis_smooth_loss_forward(const float* disp, const float* im, float* grad_sum,
+                                    float* partials, int N, int H, int W, void* stream);
+
+/* ---- a6  warp(x, flow), model/multi_frame_networks.py:83-99 ---------------------------
+ * x [N,C,H,W], flow [N,2,H,W] -> out [N,C,H,W]; bilinear, zeros padding, align_corners.
+ * backward: grad_x (zero-filled here, then accumulated) and/or grad_flow may be NULL.
+ * fb_mask_out (optional, forward only, requires C==2): the forward-backward consistency
+ * mask of model/multi_frame_networks.py:205-207 computed from (flow, out). */
+DIS_API int dis_flow_warp_forward(const float* x, const float* flow, float* out, float* fb_mask_out,
+                                  int32_t* corner_x0, int32_t* corner_y0, int N, int C, int H, int W,
+                                  void* stream);
+DIS_API int dis_flow_warp_backward(const float* x, const float* flow, const float* grad_out,
+                                   float* grad_x, float* grad_flow, int N, int C, int H, int W,
+                                   void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DIS_B200_H_ */
