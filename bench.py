@@ -1,0 +1,330 @@
+#!/usr/bin/env python
+"""bench.py -- frames/s of the DepthInSpace self-supervision hot path (loss + warp, fwd + bwd) on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 ... bench.py --gpus N ...
+
+One "step" = one pass of the hot path over one batch of synthetic structured-light frames:
+    LCN(IR)  ->  4 x RectifiedPatternSimilarityLoss (census_sad 9x9, sigma-weighted, scales 1/2^s)
+             ->  DisparitySmoothLoss(scale 0) * 0.4  ->  backward to the 4 disparity maps
+i.e. BASELINE.json configs[1] "DIS-SF training step ... batch 64": 64 samples x 4 frames = 256 frames of
+512x432 per GPU (the DispNet convolutions are out of scope and stay on cuDNN; they are not in the step).
+Frames shard by sample with no data-path collective; with N > 1 ranks the only exchange is the NCCL
+all-reduce of the loss numerators / denominators.  "scaling": "weak" (256 frames per GPU).
+
+Printed JSON (rank 0, one line): the driver contract plus
+    roofline      dominant kernel (fused pattern-loss) algorithmic bytes / CUDA-event time vs measured HBM peak
+    cpu_baseline  the oracle's torch port of the reference timed on this box's host cores (bounded sample)
+    e2e           same step through the public modules with HOST (pinned) inputs, H2D + D2H inside the timed region
+--impl reference times the reference's CPU implementation of the path (oracle port; the reference is pure
+Python and its native dependency is un-vendored, so there is no oracle/_ref binary) on rank 0 only.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "frames/s loss+warp fwd+bwd (DIS-SF)"
+UNIT = "frames/s"
+HW = (512, 432)
+N_SCALES = 4
+FRAMES_PER_GPU = 256          # bs 64 x track length 4
+ALGO_BYTES_PER_FRAME = 144    # x P, SURVEY.md section 8(d): 12P LCN + 4 x 28P photometric + 20P smoothness
+KERNEL_ALGO_BYTES_PER_FRAME = 16  # x P, fused pattern-loss kernel: reads disp, im, sigma (12P), writes d/d disp (4P)
+
+
+def measured_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    FIELDS = ["index", "clocks.sm", "clocks.max.sm", "clocks_event_reasons.hw_slowdown",
+              "clocks_event_reasons.hw_thermal_slowdown", "clocks_event_reasons.sw_thermal_slowdown",
+              "clocks_event_reasons.sw_power_cap"]
+
+    def __init__(self, gpu_index):
+        self.gpu = str(gpu_index)
+        self.rows = []
+        self.proc = None
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "--query-gpu=" + ",".join(self.FIELDS),
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) == len(self.FIELDS) and parts[0] == self.gpu:
+                self.rows.append(parts)
+
+    def __exit__(self, *a):
+        if self.proc is not None:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=5)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self):
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        sm = [float(r[1]) for r in self.rows if r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(r[3 + i] == "Active" for r in self.rows)]
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": float(self.rows[0][2]),
+                "reasons": reasons, "samples": len(self.rows)}
+
+
+def make_host_inputs(n_frames, seed):
+    """Synthetic frames on the host: a handful of distinct frames tiled up to the batch (generation is numpy)."""
+    from depthinspace_b200 import synth
+    base = min(n_frames, 8)
+    d = synth.make_frames(base, HW, "default", n_scales=N_SCALES, max_disp=128.0, seed=seed)
+    reps = (n_frames + base - 1) // base
+
+    def tile(a):
+        return np.ascontiguousarray(np.concatenate([a] * reps, axis=0)[:n_frames])
+    return dict(pattern=d["pattern"], im=tile(d["im"]), ambient=tile(d["ambient"]),
+                disp=[tile(p) for p in d["disp_pred"]])
+
+
+# ------------------------------------------------------------------------------------------ CPU arm
+def cpu_reference_step(sample, threads):
+    """One pass of the hot path over `sample` frames with the oracle's torch port (the reference's own op
+    sequence, model/networks.py + model/ext_functions.py:156-183) on the host cores."""
+    from oracle import torch_port
+    torch.set_num_threads(threads)
+    im = torch.from_numpy(sample["im"])
+    amb = torch.from_numpy(sample["ambient"])
+    pat_l, _ = torch_port.lcn(torch.from_numpy(sample["pattern"]))
+    disps = [torch.from_numpy(p).requires_grad_(True) for p in sample["disp"]]
+    t0 = time.perf_counter()
+    im_l, im_s = torch_port.lcn(im)
+    vals = torch_port.single_frame_loss(disps, im_l, im_s, amb, pat_l, chunk=1)
+    total = sum(vals)
+    total.backward()
+    return time.perf_counter() - t0, float(total.detach())
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    n = 2 if args.steps <= 10 else 1      # bounded sample: keeps K steps within a few minutes of CPU time
+    sample = make_host_inputs(n, seed=42)
+    for _ in range(args.warmup):
+        cpu_reference_step(sample, threads)
+    times = [cpu_reference_step(sample, threads)[0] for _ in range(args.steps)]
+    t = sum(times)
+    value = n * args.steps / t
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"DIS-SF loss path, {n}-frame sample of the 256-frame batch, {HW[0]}x{HW[1]}, "
+                               "default pattern, 4 scales, census_sad 9x9, LCN r5",
+                   "note": "reference's CPU implementation = oracle torch port on host cores (pure-Python reference, "
+                           "native ext un-vendored)"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
+                         "sample": f"{n} frames x {args.steps} steps, all host threads"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------ GPU arm
+def run_ours(args):
+    import torch.distributed as dist
+    from depthinspace_b200 import _lib, _ops, losses, networks
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    group = None
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+        group = dist.group.WORLD
+
+    n = args.frames_per_gpu
+    host = make_host_inputs(n, seed=42 + rank)
+    P = HW[0] * HW[1]
+    pin = lambda a: torch.from_numpy(a).pin_memory()
+    h_im, h_amb = pin(host["im"]), pin(host["ambient"])
+    h_disp = [pin(p) for p in host["disp"]]
+
+    lcn = networks.LCN(5, 0.05)
+    pat = torch.from_numpy(host["pattern"]).to(dev)
+    pat_lcn, _ = lcn(pat)
+    loss = losses.SingleFrameLoss(HW[0], HW[1], torch.cat([pat_lcn] * 3, dim=1), process_group=group)
+
+    im, amb = h_im.to(dev), h_amb.to(dev)
+    disps = [p.to(dev).requires_grad_(True) for p in h_disp]
+
+    def step(im_d, amb_d, disps_d):
+        for d in disps_d:
+            d.grad = None
+        im_l, im_s = lcn(im_d)
+        vals = loss(disps_d, im_l, im_s, amb_d)
+        total = vals[0]
+        for v in vals[1:]:
+            total = total + v
+        total.backward()
+        return total
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step(im, amb, disps)
+    sync_all()
+
+    # ---- device-resident timing (value) ----
+    l0 = _lib.LAUNCHES
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local_rank) as clocks:
+        sync_all()
+        ev0.record()
+        for _ in range(args.steps):
+            total = step(im, amb, disps)
+        ev1.record()
+        sync_all()
+    ms = ev0.elapsed_time(ev1)
+    launches = _lib.LAUNCHES - l0
+    loss_value = float(total)
+
+    # ---- dominant kernel alone: fused pattern-loss (census_sad 9x9, with gradient stash) ----
+    im_l, im_s = lcn(im)
+    d0 = disps[0].detach()
+    gnum = torch.empty_like(d0)
+    lib = _lib.load()
+    npart = lib.dis_pattern_loss_num_partials(n, HW[0], HW[1])
+    partials = torch.empty(2 * npart, device=dev)
+    stream = torch.cuda.current_stream().cuda_stream
+
+    def dominant():
+        _lib.check(lib.dis_pattern_loss_forward(d0.data_ptr(), im_l.data_ptr(), im_s.data_ptr(), loss.ph_loss.pattern.data_ptr(),
+                                                None, None, gnum.data_ptr(), partials.data_ptr(), n, HW[0], HW[1], 9, 3, 0.5,
+                                                stream))
+    for _ in range(3):
+        dominant()
+    k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    reps = max(3, min(args.steps, 10))
+    k0.record()
+    for _ in range(reps):
+        dominant()
+    k1.record()
+    torch.cuda.synchronize()
+    kernel_ms = k0.elapsed_time(k1) / reps
+
+    # ---- end to end: host (pinned) inputs -> public modules -> loss scalar back on the host ----
+    def e2e_step():
+        im_d = h_im.to(dev, non_blocking=True)
+        amb_d = h_amb.to(dev, non_blocking=True)
+        disps_d = [p.to(dev, non_blocking=True).requires_grad_(True) for p in h_disp]
+        return float(step(im_d, amb_d, disps_d))    # .item(): D2H read of the step's loss
+
+    e2e_step()
+    sync_all()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        e2e_step()
+    sync_all()
+    e2e_s = time.perf_counter() - t0
+
+    # ---- max over ranks ----
+    times = torch.tensor([ms, e2e_s * 1e3, kernel_ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(times, op=dist.ReduceOp.MAX)
+    ms, e2e_ms, kernel_ms = times.tolist()
+    frames = n * world * args.steps
+    value = frames / (ms * 1e-3)
+    e2e_value = frames / (e2e_ms * 1e-3)
+    peak, peak_src = measured_peak()
+    achieved = KERNEL_ALGO_BYTES_PER_FRAME * P * n / (kernel_ms * 1e-3) / 1e9
+    step_gbs = ALGO_BYTES_PER_FRAME * P * (value / world) / 1e9
+
+    if rank == 0:
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            threads = os.cpu_count() or 1
+            sample = make_host_inputs(2, seed=42)
+            cpu_reference_step(make_host_inputs(1, seed=1), threads)     # warm-up (thread pools, allocator)
+            t, _ = cpu_reference_step(sample, threads)
+            cpu = {"value": 2 / t, "unit": UNIT, "cores": threads, "kind": "port",
+                   "sample": "2 of the 256 frames, 1 pass, oracle torch port of the reference modules, all host threads"}
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"BASELINE configs[1]: DIS-SF loss path, {n} frames/GPU (bs 64 x tl 4), {HW[0]}x{HW[1]}, "
+                                   "default pattern, LCN r5 + 4 x (pattern warp + census_sad 9x9, sigma-weighted) + smoothness, fwd+bwd",
+                       "frames_per_gpu": n, "l2": "inputs (2.7 GB/step) exceed the 126 MB L2; no flush needed",
+                       "loss": loss_value},
+            "clocks": clocks.summary(),
+            "e2e": {"value": e2e_value, "unit": UNIT,
+                    "h2d_bytes_per_step": int((2 + N_SCALES) * 4 * P * n), "d2h_bytes_per_step": 4},
+            "gpu_launches": launches,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "kernel": "pattern_loss_kernel<census_sad, R=4, grad>",
+                         "kernel_ms": kernel_ms, "peak_source": peak_src,
+                         "limiter": "XU (rsqrt) + FP32 issue, not HBM: ~160 rsqrt per pixel-scale (see DESIGN.md)",
+                         "step_algorithmic_gbs": step_gbs, "step_frac": step_gbs / peak},
+            "cpu_baseline": cpu,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--frames-per-gpu", type=int, default=FRAMES_PER_GPU)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 0)
+    if args.impl == "reference":
+        run_reference_arm(args)
+        return
+    if args.warmup < 3:
+        args.warmup = 3
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the hot path has no CPU fallback (use --impl reference for the CPU arm)")
+    run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

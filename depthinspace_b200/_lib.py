@@ -71,9 +71,14 @@ def load():
     return lib
 
 
-def check(status):
+LAUNCHES = 0  # kernels of libdis_b200 enqueued through check() by this process (bench.py reports it)
+
+
+def check(status, launches=1):
     """Raise on a non-zero dis_status (mirrors the reference raising from the ext boundary)."""
+    global LAUNCHES
     if status == 0:
+        LAUNCHES += launches
         return
     lib = load()
     msg = lib.dis_status_string(int(status)).decode()

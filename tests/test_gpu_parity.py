@@ -1,0 +1,394 @@
+"""Parity of the CUDA path (called through the C-ABI via the reference-shaped Python surface) against
+the oracle: the plain-C restatement on the same seeded inputs, the committed golden vectors generated
+from the reference, and the torch port run with torch's own CUDA kernels (the reference's production
+arithmetic).  Tolerances: helpers.py (1e-5 relative, norm-wise; integer/index work bit-exact).
+"""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from helpers import assert_close, assert_scalar_close, to_np
+from depthinspace_b200 import synth
+from oracle import c_oracle, torch_port
+
+pytestmark = pytest.mark.gpu
+TYPES = ("mse", "sad", "census_mse", "census_sad")
+SIGN_OUTLIERS = 2e-5  # see helpers.py: sign() of a value within rounding of zero
+
+
+def dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+@pytest.fixture(scope="module")
+def mods():
+    from depthinspace_b200 import ext_functions, multi_frame_networks, networks
+    return networks, ext_functions, multi_frame_networks
+
+
+# ----------------------------------------------------------------------------- photometric loss (a4)
+@pytest.mark.parametrize("t", TYPES)
+@pytest.mark.parametrize("k", [1, 3, 5, 7, 9, 11, 13, 15])
+def test_photometric_vs_c_oracle(mods, t, k):
+    _, ext, _ = mods
+    rng = np.random.default_rng(100 + k)
+    shape = (2, 1, 45, 77)  # ragged: not a multiple of the 64x32 tile nor of 4
+    es, ta = rng.standard_normal(shape).astype(np.float32), rng.standard_normal(shape).astype(np.float32)
+    go = rng.standard_normal((shape[0], 1) + shape[2:]).astype(np.float32)
+    e = dev(es).requires_grad_(True)
+    out = ext.photometric_loss(e, dev(ta), k, t, 0.5)
+    out.backward(dev(go))
+    tid = c_oracle.TYPES[t]
+    ref_out = c_oracle.photometric_forward(es, ta, k, tid, 0.5, "f64")
+    ref_grad = c_oracle.photometric_backward(es, ta, go, k, tid, 0.5, "f64")
+    assert_close(out, ref_out, name=f"fwd {t} k={k}")
+    assert_close(e.grad, ref_grad, name=f"bwd {t} k={k}", outlier_frac=SIGN_OUTLIERS if t in ("sad", "census_sad") else 0)
+
+
+@pytest.mark.parametrize("t", TYPES)
+@pytest.mark.parametrize("shape", [(1, 1, 3, 5), (1, 3, 9, 4), (3, 2, 33, 65), (1, 1, 64, 128), (2, 1, 1, 40), (1, 1, 40, 1)])
+def test_photometric_edge_shapes(mods, t, shape):
+    """Tiny (smaller than the window), multi-channel, exact tile multiples and 1-pixel-wide images."""
+    _, ext, _ = mods
+    rng = np.random.default_rng(sum(shape))
+    es, ta = rng.standard_normal(shape).astype(np.float32), rng.standard_normal(shape).astype(np.float32)
+    go = rng.random((shape[0], 1) + shape[2:]).astype(np.float32)
+    e = dev(es).requires_grad_(True)
+    out = ext.photometric_loss(e, dev(ta), 9, t, 0.1)
+    out.backward(dev(go))
+    tid = c_oracle.TYPES[t]
+    assert_close(out, c_oracle.photometric_forward(es, ta, 9, tid, 0.1, "f64"), name="fwd")
+    assert_close(e.grad, c_oracle.photometric_backward(es, ta, go, 9, tid, 0.1, "f64"), name="bwd",
+                 outlier_frac=1e-3 if t in ("sad", "census_sad") else 0)
+
+
+@pytest.mark.parametrize("case", ["k9", "k5c2", "k3"])
+@pytest.mark.parametrize("t", TYPES)
+def test_photometric_golden(mods, golden, case, t):
+    _, ext, _ = mods
+    g = golden("photometric")
+    e = dev(g[f"{case}_es"]).requires_grad_(True)
+    out = ext.photometric_loss(e, dev(g[f"{case}_ta"]), int(g[f"{case}_k"]), t, float(g[f"{case}_eps"]))
+    out.backward(dev(g[f"{case}_go"]))
+    assert_close(out, g[f"{case}_{t}_out_f64"], name="fwd vs reference fp64")
+    assert_close(e.grad, g[f"{case}_{t}_grad_f64"], name="bwd vs reference fp64")
+    assert_close(out, g[f"{case}_{t}_out"], name="fwd vs reference fp32")
+    assert_close(e.grad, g[f"{case}_{t}_grad"], name="bwd vs reference fp32")
+
+
+def test_photometric_identical_inputs_give_exact_zero(mods):
+    """|.| has subgradient 0 at 0 in the reference (torch.abs); es == ta must give 0 loss and 0 gradient."""
+    _, ext, _ = mods
+    x = torch.randn(2, 1, 70, 90, device="cuda")
+    for t in TYPES:
+        e = x.clone().requires_grad_(True)
+        out = ext.photometric_loss(e, x.clone(), 9, t, 0.5)
+        out.sum().backward()
+        assert float(out.abs().max()) == 0.0, t
+        assert float(e.grad.abs().max()) == 0.0, t
+
+
+def test_photometric_reference_dropin_module_path(mods):
+    """The reference imports `ext_cuda` from CTD_DIR/torchext and calls it with an int type
+    (model/ext_functions.py:124,137): same call through our stand-in module."""
+    p = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "depthinspace_b200", "torchext")
+    sys.path.insert(0, p)
+    try:
+        import ext_cuda
+    finally:
+        sys.path.remove(p)
+    es, ta = torch.randn(2, 1, 40, 48, device="cuda"), torch.randn(2, 1, 40, 48, device="cuda")
+    out = ext_cuda.photometric_loss_forward(es, ta, 9, 3, 0.5)
+    go = torch.rand_like(out)
+    grad = ext_cuda.photometric_loss_backward(es, ta, go, 9, 3, 0.5)
+    assert_close(out, c_oracle.photometric_forward(to_np(es), to_np(ta), 9, 3, 0.5, "f64"))
+    assert_close(grad, c_oracle.photometric_backward(to_np(es), to_np(ta), to_np(go), 9, 3, 0.5, "f64"), outlier_frac=1e-4)
+    with pytest.raises(Exception, match="invalid loss type"):
+        ext_cuda.photometric_loss_forward(es, ta, 9, 5, 0.5)
+
+
+@pytest.mark.parametrize("t", TYPES)
+def test_photometric_vs_torch_cuda_port_dataset_shape(mods, t):
+    """512x432 (the dataset's frame shape) against the reference's formula run by torch on the GPU."""
+    _, ext, _ = mods
+    torch.manual_seed(1)
+    es = torch.randn(2, 1, 512, 432, device="cuda", requires_grad=True)
+    ta = torch.randn(2, 1, 512, 432, device="cuda")
+    out = ext.photometric_loss(es, ta, 9, t, 0.5)
+    go = torch.rand_like(out)
+    out.backward(go)
+    g = es.grad.clone()
+    es.grad = None
+    ref = torch_port.photometric(es.double(), ta.double(), 9, t, 0.5)
+    ref.backward(go.double())
+    assert_close(out, ref, name="fwd")
+    assert_close(g, es.grad, name="bwd", outlier_frac=SIGN_OUTLIERS)
+
+
+# ----------------------------------------------------------------------------- pattern warp + fused loss (a2, a3)
+def _frames(n, hw, kind="default", seed=3, scales=1, max_disp=64):
+    d = synth.make_frames(n, hw, kind, n_scales=scales, max_disp=max_disp, seed=seed)
+    im_l, im_s = c_oracle.lcn_forward(d["im"], 5, 0.05, "f64")
+    pat_l, _ = c_oracle.lcn_forward(d["pattern"], 5, 0.05, "f64")
+    return d, im_l.astype(np.float32), im_s.astype(np.float32), pat_l.astype(np.float32)
+
+
+def test_pattern_warp_indices_and_values_bit_exact_vs_c_oracle():
+    """Corner indices (integer work) and the blended value must equal the fp32 C oracle bit for bit."""
+    from depthinspace_b200 import _ops
+    hw = (96, 120)
+    d, _, _, pat = _frames(2, hw, "kinect")
+    disp = d["disp_pred"][0].copy()
+    disp[0, 0, :6, :] = 0.0            # integer coordinates: exercises the fp32 round trip (rows that floor to h-1)
+    disp[0, 0, 8, :] = 500.0           # clipped at the left border
+    disp[1, 0, 9, :] = -500.0          # clipped at the right border
+    disp[1, 0, 10, :] = np.arange(hw[1], dtype=np.float32) - 0.5
+    proj, dproj, cx, cy = _ops.pattern_warp(dev(disp), dev(pat), want_dproj=True, want_corners=True)
+    o_proj, o_dproj, o_cx, o_cy = c_oracle.pattern_warp(disp, pat, "f32")
+    assert np.array_equal(to_np(cx), o_cx), "x corner indices differ"
+    assert np.array_equal(to_np(cy), o_cy), "y corner indices differ"
+    assert np.array_equal(to_np(proj), o_proj), "pattern_proj not bit-exact"
+    assert_close(dproj, o_dproj, 1e-6, "d proj / d disp")
+
+
+def test_pattern_warp_bit_exact_vs_torch_cuda_grid_sample():
+    """The reference's own op sequence (model/networks.py:356-367) executed by torch on the GPU."""
+    from depthinspace_b200 import _ops
+    for hw in ((512, 432), (480, 640), (96, 120)):
+        d, _, _, pat = _frames(2, hw, "default", seed=5)
+        disp = d["disp_pred"][0].copy()
+        disp[0, 0, :8, :] = 0.0
+        disp[1, 0, 5, :] = 1000.0
+        proj, _, _, _ = _ops.pattern_warp(dev(disp), dev(pat))
+        ref = torch_port.pattern_warp(dev(disp), dev(pat))
+        mism = (proj != ref)
+        assert not bool(mism.any()), f"{hw}: {int(mism.sum())} of {mism.numel()} pixels differ from torch CUDA grid_sample, max {float((proj-ref).abs().max()):.3e}"
+
+
+@pytest.mark.parametrize("lt", TYPES)
+@pytest.mark.parametrize("use_std", [True, False])
+def test_pattern_loss_vs_c_oracle(mods, lt, use_std):
+    net, _, _ = mods
+    hw = (70, 150)  # ragged tiles in both directions
+    d, im_l, im_s, pat = _frames(3, hw, "kinect", seed=8)
+    disp = d["disp_pred"][0].copy()
+    disp[0, 0, 3, :20] = 0.0
+    disp[2, 0, 11, :] = 300.0
+    mod = net.RectifiedPatternSimilarityLoss(hw[0], hw[1], dev(np.repeat(pat, 3, axis=1)), loss_type=lt)
+    dd = dev(disp).requires_grad_(True)
+    val, proj = mod(dd, dev(im_l), dev(im_s) if use_std else None)
+    (val * 1.7).backward()
+    o = c_oracle.pattern_loss(disp, im_l, im_s if use_std else None, to_np(mod.pattern), 9, c_oracle.TYPES[lt], 0.5, True, "f64")
+    o32 = c_oracle.pattern_loss(disp, im_l, im_s if use_std else None, to_np(mod.pattern), 9, c_oracle.TYPES[lt], 0.5, False, "f32")
+    assert val.dim() == 0 and proj.shape == dd.shape
+    assert_scalar_close(val.item(), o["val"], name="val")
+    assert np.array_equal(to_np(proj), o32["proj"]), "pattern_proj differs from the fp32 oracle"
+    assert_close(dd.grad, 1.7 * o["grad_disp"], name="grad_disp", outlier_frac=1e-4 if "sad" in lt else 0)
+
+
+def test_pattern_loss_golden(mods, golden):
+    net, _, _ = mods
+    g = golden("pattern_loss")
+    H, W = g["disp"].shape[-2:]
+    for lt in ("census_sad", "mse"):
+        for use_std in (True, False):
+            key = f"{lt}_{'std' if use_std else 'nostd'}"
+            mod = net.RectifiedPatternSimilarityLoss(H, W, dev(np.repeat(g["pattern_lcn"], 3, axis=1)), loss_type=lt)
+            dd = dev(g["disp"]).requires_grad_(True)
+            val, proj = mod(dd, dev(g["im_lcn"]), dev(g["im_std"]) if use_std else None)
+            val.backward()
+            assert_scalar_close(val.item(), g[f"{key}_val"], 2e-5, key)       # reference ran torch-CPU coordinates
+            assert_close(proj, g["proj"], 2e-5, "proj")
+            assert_close(dd.grad, g[f"{key}_grad"], 5e-5, key + " grad")
+    mod = net.RectifiedPatternSimilarityLoss(H, W, dev(np.repeat(g["pattern_lcn"], 3, axis=1)))
+    diff, proj = mod(dev(g["disp"]), dev(g["im_lcn"]), dev(g["im_std"]), output_mean=False)
+    assert_close(diff, g["census_sad_map"], 2e-5, "per-pixel map")
+
+
+def test_pattern_loss_map_backward_and_proj_gradient(mods):
+    """output_mean=False (model/networks.py:375-376) and gradients through the returned pattern_proj."""
+    net, _, _ = mods
+    hw = (40, 72)
+    d, im_l, im_s, pat = _frames(2, hw, "real", seed=2)
+    disp = d["disp_pred"][0]
+    mod = net.RectifiedPatternSimilarityLoss(hw[0], hw[1], dev(np.repeat(pat, 3, axis=1)))
+    dd = dev(disp).requires_grad_(True)
+    diff, proj = mod(dd, dev(im_l), dev(im_s), output_mean=False)
+    w = torch.rand_like(diff)
+    ((diff * w).sum() + 0.3 * proj.sum()).backward()
+    dt = torch.from_numpy(disp).double().cuda().requires_grad_(True)
+    rdiff, rproj = torch_port.pattern_loss(dt, dev(im_l).double(), None, mod.pattern.double(), output_mean=False)
+    ((rdiff * w.double()).sum() + 0.3 * rproj.sum()).backward()
+    assert_close(diff, rdiff, name="map")
+    assert_close(dd.grad, dt.grad, 2e-5, name="grad through map + proj", outlier_frac=1e-4)
+    # mean path with a gradient through pattern_proj as well
+    dd.grad = None
+    val, proj = mod(dd, dev(im_l), dev(im_s))
+    (val + 0.01 * (proj ** 2).sum()).backward()
+    dt.grad = None
+    rval, rproj = torch_port.pattern_loss(dt, dev(im_l).double(), dev(im_s).double(), mod.pattern.double())
+    (rval + 0.01 * (rproj ** 2).sum()).backward()
+    assert_close(dd.grad, dt.grad, 2e-5, name="grad through val + proj", outlier_frac=1e-4)
+
+
+def test_pattern_loss_dataset_shape_vs_torch_cuda_port(mods):
+    net, _, _ = mods
+    hw = synth.DATASET_HW
+    d, im_l, im_s, pat = _frames(4, hw, "default", seed=42, scales=2, max_disp=128)
+    mod = net.RectifiedPatternSimilarityLoss(hw[0], hw[1], dev(np.repeat(pat, 3, axis=1)), return_pattern_proj=False)
+    for s in range(2):
+        dd = dev(d["disp_pred"][s]).requires_grad_(True)
+        val, proj = mod(dd, dev(im_l), dev(im_s))
+        assert proj is None
+        val.backward()
+        dt = dev(d["disp_pred"][s]).requires_grad_(True)
+        rval, _ = torch_port.pattern_loss(dt, dev(im_l), dev(im_s), mod.pattern, chunk=1)
+        rval.backward()
+        assert_scalar_close(val.item(), rval.item(), name=f"val scale {s}")
+        assert_close(dd.grad, dt.grad, 2e-5, name=f"grad scale {s}", outlier_frac=1e-4)
+
+
+def test_pattern_loss_is_deterministic_and_batch_separable(mods):
+    net, _, _ = mods
+    hw = (128, 192)
+    d, im_l, im_s, pat = _frames(4, hw, seed=4)
+    mod = net.RectifiedPatternSimilarityLoss(hw[0], hw[1], dev(np.repeat(pat, 3, axis=1)))
+    runs = []
+    for _ in range(2):
+        dd = dev(d["disp_pred"][0]).requires_grad_(True)
+        val, _ = mod(dd, dev(im_l), dev(im_s))
+        val.backward()
+        runs.append((val.item(), dd.grad.clone()))
+    assert runs[0][0] == runs[1][0] and torch.equal(runs[0][1], runs[1][1]), "not bitwise reproducible"
+    # num/den of halves add up to the whole (what the multi-GPU path relies on)
+    from depthinspace_b200 import _ops
+    full, *_ = _ops.pattern_loss_forward(dev(d["disp_pred"][0]), dev(im_l), dev(im_s), mod.pattern, 9, 3, 0.5, False, False, False)
+    parts = [_ops.pattern_loss_forward(dev(d["disp_pred"][0][s]), dev(im_l[s]), dev(im_s[s]), mod.pattern, 9, 3, 0.5, False, False, False)[0]
+             for s in (slice(0, 2), slice(2, 4))]
+    assert_scalar_close((parts[0][0] + parts[1][0]).item(), full[0].item(), 1e-6)
+    assert_scalar_close((parts[0][1] + parts[1][1]).item(), full[1].item(), 1e-6)
+
+
+# ----------------------------------------------------------------------------- LCN (a1)
+@pytest.mark.parametrize("hw,radius", [((512, 432), 5), ((37, 53), 3), ((480, 640), 7), ((20, 24), 1), ((64, 64), 8)])
+def test_lcn_vs_fp64_oracle(mods, hw, radius):
+    net, _, _ = mods
+    d = synth.make_frames(2, hw, "default", seed=radius)
+    x = d["im"].copy()
+    x[0, 0, : hw[0] // 3] = 0.3  # flat + step: the reference's own fp32 error in std is 2.6e-3 here
+    lcn, std = net.LCN(radius, 0.05)(dev(x))
+    o_l, o_s = c_oracle.lcn_forward(x, radius, 0.05, "f64")
+    assert_close(std, o_s, 1e-6, "std vs fp64 evaluation of the reference formula")
+    assert_close(lcn, o_l, 1e-6, "lcn vs fp64 evaluation of the reference formula")
+    # and never further from the truth than the reference's own fp32 arithmetic (torch CUDA conv path)
+    r_l, r_s = torch_port.lcn(dev(x), radius, 0.05)
+    ours = float(np.abs(to_np(std) - o_s).max())
+    theirs = float(np.abs(to_np(r_s) - o_s).max())
+    assert ours <= theirs + 1e-7, (ours, theirs)
+    assert_close(lcn, r_l, 2e-5, "lcn vs reference fp32 arithmetic")
+
+
+def test_lcn_golden(mods, golden):
+    net, _, _ = mods
+    g = golden("lcn")
+    for case in ("a", "b"):
+        lcn, std = net.LCN(int(g[f"{case}_radius"]), 0.05)(dev(g[f"{case}_x"]))
+        assert_close(lcn, g[f"{case}_lcn_f64"], 1e-6, "lcn")
+        assert_close(std, g[f"{case}_std_f64"], 1e-6, "std")
+        assert_close(lcn, g[f"{case}_lcn"], 1e-5, "lcn vs fp32 reference")
+
+
+# ----------------------------------------------------------------------------- smoothness (a5)
+def _rough_disp(d, seed=0):
+    rng = np.random.default_rng(seed)
+    return (d["disp_gt"] + rng.standard_normal(d["disp_gt"].shape)).astype(np.float32)
+
+
+@pytest.mark.parametrize("hw", [(512, 432), (45, 70), (5, 9), (33, 64)])
+def test_smooth_loss_vs_oracle(mods, hw):
+    net, _, _ = mods
+    d = synth.make_frames(2, hw, seed=hw[0])
+    disp = _rough_disp(d)
+    dd = dev(disp).requires_grad_(True)
+    val = net.DisparitySmoothLoss()(dd, dev(d["ambient"]))
+    (val * 0.4).backward()
+    o_val, o_grad = c_oracle.smooth_loss(disp, d["ambient"], True, "f64")
+    assert_scalar_close(val.item(), o_val, name="val")
+    assert_close(dd.grad, 0.4 * o_grad, name="grad", outlier_frac=2e-4)
+
+
+def test_smooth_golden_and_sobel(mods, golden):
+    net, _, _ = mods
+    g = golden("smooth")
+    dd = dev(g["disp"]).requires_grad_(True)
+    val = net.DisparitySmoothLoss()(dd, dev(g["ambient"]))
+    val.backward()
+    assert_scalar_close(val.item(), float(g["val_f64"]), name="val")
+    assert_close(dd.grad, g["grad_f64"], name="grad", outlier_frac=2e-3)
+    x = dev(g["disp"]).requires_grad_(True)
+    s = net.SobelFilter()(x)
+    assert_close(s, g["sobel_f64"], name="sobel")
+    w = torch.randn_like(s)
+    s.backward(w)
+    assert_close(x.grad, c_oracle.sobel_backward(to_np(w), 5, "f64"), name="sobel backward")
+    for ksize in (3, 5):
+        y = net.SobelFilter(norm=True, ksize=ksize)(x)
+        assert_close(y, torch_port.sobel(x.detach().double(), ksize, norm=True), name=f"sobel norm k={ksize}")
+
+
+# ----------------------------------------------------------------------------- flow warp (a6, a7)
+@pytest.mark.parametrize("shape", [(2, 3, 256, 216), (2, 32, 128, 108), (1, 2, 37, 50)])
+def test_flow_warp_vs_oracle(mods, shape):
+    _, _, mf = mods
+    n, c, h, w = shape
+    rng = np.random.default_rng(c)
+    x = rng.standard_normal(shape).astype(np.float32)
+    f01, f10 = synth.make_flows(n, (h, w), max_mag=9.0, seed=c)
+    f01[0, :, :4, :4] = 0.0
+    f01[0, 0, 7, :] = 1e9           # far outside: zeros padding, safe int range
+    f01[-1, 1, 9, :10] = -3.25
+    xt = dev(x).requires_grad_(True)
+    ft = dev(f01).requires_grad_(True)
+    y = mf.warp(xt, ft)
+    go = rng.standard_normal(shape).astype(np.float32)
+    y.backward(dev(go))
+    o_y, o_cx, o_cy = c_oracle.flow_warp_forward(x, f01, "f32")
+    assert np.array_equal(to_np(y), o_y), "warp output not bit-exact vs the fp32 oracle"
+    o_gx, o_gf = c_oracle.flow_warp_backward(x, f01, go, True, "f64")
+    assert_close(xt.grad, o_gx, name="grad x (atomic accumulation order differs)")
+    assert_close(ft.grad, o_gf, 2e-5, name="grad flow")
+    # corner indices are integer work: bit-exact
+    from depthinspace_b200 import _ops
+    _, _, cx, cy = _ops.flow_warp_forward(dev(x), dev(f01), want_corners=True)
+    assert np.array_equal(to_np(cx), o_cx) and np.array_equal(to_np(cy), o_cy)
+
+
+def test_flow_warp_bit_exact_vs_torch_cuda_and_fb_mask(mods):
+    _, _, mf = mods
+    for (h, w) in ((256, 216), (128, 108)):
+        f01, f10 = synth.make_flows(3, (h, w), max_mag=6.0, seed=h)
+        x = torch.randn(3, 8, h, w, device="cuda")
+        y = mf.warp(x, dev(f01))
+        ref = torch_port.flow_warp(x, dev(f01))
+        assert torch.equal(y, ref), f"{int((y != ref).sum())} elements differ from torch CUDA grid_sample"
+        f10w, mask = mf.warp_with_fb_mask(dev(f10), dev(f01))
+        rf10w = torch_port.flow_warp(dev(f10), dev(f01))
+        assert torch.equal(f10w, rf10w)
+        rmask = torch_port.fb_mask(dev(f01), rf10w)
+        assert torch.equal(mask, rmask), "forward-backward mask must be bit-exact"
+        assert 0.5 < float(mask.mean()) < 1.0
+
+
+def test_flow_warp_golden(mods, golden):
+    _, _, mf = mods
+    g = golden("flow_warp")
+    xt = dev(g["x"]).requires_grad_(True)
+    y = mf.warp(xt, dev(g["flow"]))
+    y.backward(dev(g["go"]))
+    assert_close(y, g["out_f64"], 2e-5, "out")       # fp32 coordinates vs fp64 coordinates
+    assert_close(xt.grad, g["grad_x_f64"], 2e-5, "grad_x")
+    _, mask = mf.warp_with_fb_mask(dev(g["flow_back"]), dev(g["flow"]))
+    assert float((to_np(mask) != g["fb_mask"]).mean()) < 1e-3
