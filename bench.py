@@ -219,7 +219,7 @@ def run_ours(args):
         sync_all()
     ms = ev0.elapsed_time(ev1)
     launches = _lib.LAUNCHES - l0
-    loss_value = float(total)
+    loss_value = float(total.detach())
 
     # ---- dominant kernel alone: fused pattern-loss (census_sad 9x9, with gradient stash) ----
     im_l, im_s = lcn(im)
@@ -251,7 +251,7 @@ def run_ours(args):
         im_d = h_im.to(dev, non_blocking=True)
         amb_d = h_amb.to(dev, non_blocking=True)
         disps_d = [p.to(dev, non_blocking=True).requires_grad_(True) for p in h_disp]
-        return float(step(im_d, amb_d, disps_d))    # .item(): D2H read of the step's loss
+        return float(step(im_d, amb_d, disps_d).detach())    # .item(): D2H read of the step's loss
 
     e2e_step()
     sync_all()

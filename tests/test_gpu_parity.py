@@ -87,7 +87,7 @@ def test_photometric_identical_inputs_give_exact_zero(mods):
         e = x.clone().requires_grad_(True)
         out = ext.photometric_loss(e, x.clone(), 9, t, 0.5)
         out.sum().backward()
-        assert float(out.abs().max()) == 0.0, t
+        assert float(out.detach().abs().max()) == 0.0, t
         assert float(e.grad.abs().max()) == 0.0, t
 
 
@@ -186,7 +186,12 @@ def test_pattern_loss_vs_c_oracle(mods, lt, use_std):
     assert val.dim() == 0 and proj.shape == dd.shape
     assert_scalar_close(val.item(), o["val"], name="val")
     assert np.array_equal(to_np(proj), o32["proj"]), "pattern_proj differs from the fp32 oracle"
-    assert_close(dd.grad, 1.7 * o["grad_disp"], name="grad_disp", outlier_frac=1e-4 if "sad" in lt else 0)
+    # Bilinear interpolation has a kink at integer source coordinates: where the fp32 coordinate lands within
+    # rounding of an integer, the fp64 evaluation may pick the neighbouring cell (a different, equally valid
+    # one-sided derivative).  The fp32 oracle replays the CUDA op order, so it picks the same cell as the kernel.
+    o32g = c_oracle.pattern_loss(disp, im_l, im_s if use_std else None, to_np(mod.pattern), 9, c_oracle.TYPES[lt], 0.5, True, "f32")
+    assert_close(dd.grad, 1.7 * o32g["grad_disp"], name="grad_disp vs fp32 oracle", outlier_frac=1e-4 if "sad" in lt else 0)
+    assert_close(dd.grad, 1.7 * o["grad_disp"], 2e-5, name="grad_disp vs fp64 oracle", outlier_frac=2e-3)
 
 
 def test_pattern_loss_golden(mods, golden):
@@ -357,9 +362,14 @@ def test_flow_warp_vs_oracle(mods, shape):
     y.backward(dev(go))
     o_y, o_cx, o_cy = c_oracle.flow_warp_forward(x, f01, "f32")
     assert np.array_equal(to_np(y), o_y), "warp output not bit-exact vs the fp32 oracle"
-    o_gx, o_gf = c_oracle.flow_warp_backward(x, f01, go, True, "f64")
-    assert_close(xt.grad, o_gx, name="grad x (atomic accumulation order differs)")
-    assert_close(ft.grad, o_gf, 2e-5, name="grad flow")
+    # fp32 oracle = same coordinate rounding and cell choice as the kernel; only the order of the (atomic)
+    # accumulation differs.  Against fp64 coordinates the corner weights themselves differ by ~ulp(coordinate).
+    o_gx, o_gf = c_oracle.flow_warp_backward(x, f01, go, True, "f32")
+    assert_close(xt.grad, o_gx, 2e-6, name="grad x vs fp32 oracle")
+    assert_close(ft.grad, o_gf, 1e-5, name="grad flow vs fp32 oracle")
+    o_gx64, o_gf64 = c_oracle.flow_warp_backward(x, f01, go, True, "f64")
+    assert_close(xt.grad, o_gx64, 1e-4, name="grad x vs fp64 oracle")
+    assert_close(ft.grad, o_gf64, 1e-4, name="grad flow vs fp64 oracle", outlier_frac=1e-2)
     # corner indices are integer work: bit-exact
     from depthinspace_b200 import _ops
     _, _, cx, cy = _ops.flow_warp_forward(dev(x), dev(f01), want_corners=True)
@@ -367,19 +377,28 @@ def test_flow_warp_vs_oracle(mods, shape):
 
 
 def test_flow_warp_bit_exact_vs_torch_cuda_and_fb_mask(mods):
+    """torch routes grid_sample(bilinear, zeros, align_corners=True) on CUDA to cuDNN's (closed-source) spatial
+    transformer sampler when cuDNN is enabled, and to ATen's native kernel otherwise.  The native kernel's
+    arithmetic is public (ATen/native/cuda/GridSampler.cuh) and is what libdis_b200 replays bit for bit; the
+    cuDNN path is matched to tolerance."""
     _, _, mf = mods
     for (h, w) in ((256, 216), (128, 108)):
         f01, f10 = synth.make_flows(3, (h, w), max_mag=6.0, seed=h)
         x = torch.randn(3, 8, h, w, device="cuda")
         y = mf.warp(x, dev(f01))
-        ref = torch_port.flow_warp(x, dev(f01))
-        assert torch.equal(y, ref), f"{int((y != ref).sum())} elements differ from torch CUDA grid_sample"
         f10w, mask = mf.warp_with_fb_mask(dev(f10), dev(f01))
-        rf10w = torch_port.flow_warp(dev(f10), dev(f01))
+        with torch.backends.cudnn.flags(enabled=False):
+            ref = torch_port.flow_warp(x, dev(f01))
+            rf10w = torch_port.flow_warp(dev(f10), dev(f01))
+        assert torch.equal(y, ref), f"{int((y != ref).sum())} elements differ from ATen's CUDA grid_sample"
         assert torch.equal(f10w, rf10w)
         rmask = torch_port.fb_mask(dev(f01), rf10w)
         assert torch.equal(mask, rmask), "forward-backward mask must be bit-exact"
         assert 0.5 < float(mask.mean()) < 1.0
+        ref_cudnn = torch_port.flow_warp(x, dev(f01))
+        assert_close(y, ref_cudnn, 1e-5, "vs cuDNN spatial-transformer path")
+        mask_cudnn = torch_port.fb_mask(dev(f01), torch_port.flow_warp(dev(f10), dev(f01)))
+        assert float((mask != mask_cudnn).float().mean()) < 1e-4
 
 
 def test_flow_warp_golden(mods, golden):
