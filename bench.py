@@ -40,7 +40,7 @@ HW = (512, 432)
 N_SCALES = 4
 FRAMES_PER_GPU = 256          # bs 64 x track length 4
 ALGO_BYTES_PER_FRAME = 144    # x P, SURVEY.md section 8(d): 12P LCN + 4 x 28P photometric + 20P smoothness
-KERNEL_ALGO_BYTES_PER_FRAME = 16  # x P, fused pattern-loss kernel: reads disp, im, sigma (12P), writes d/d disp (4P)
+KERNEL_ALGO_BYTES_PER_FRAME = 40  # x P, 4-scale fused pattern-loss kernel: reads 4 disp + im + sigma (24P), writes 4 x d/d disp (16P)
 
 
 def measured_peak():
@@ -221,19 +221,22 @@ def run_ours(args):
     launches = _lib.LAUNCHES - l0
     loss_value = float(total.detach())
 
-    # ---- dominant kernel alone: fused pattern-loss (census_sad 9x9, with gradient stash) ----
+    # ---- dominant kernel alone: 4-scale fused pattern-loss (census_sad 9x9, with gradient stash) ----
+    import ctypes
     im_l, im_s = lcn(im)
-    d0 = disps[0].detach()
-    gnum = torch.empty_like(d0)
+    gnums = [torch.empty_like(d) for d in disps]
     lib = _lib.load()
-    npart = lib.dis_pattern_loss_num_partials(n, HW[0], HW[1])
-    partials = torch.empty(2 * npart, device=dev)
+    npart = lib.dis_pattern_loss_multi_num_partials(n, HW[0], HW[1])
+    partials = torch.empty(2 * N_SCALES * npart, device=dev)
     stream = torch.cuda.current_stream().cuda_stream
+    PtrArr = ctypes.c_void_p * N_SCALES
+    d_arr = PtrArr(*[d.data_ptr() for d in disps])
+    g_arr = PtrArr(*[g.data_ptr() for g in gnums])
 
     def dominant():
-        _lib.check(lib.dis_pattern_loss_forward(d0.data_ptr(), im_l.data_ptr(), im_s.data_ptr(), loss.ph_loss.pattern.data_ptr(),
-                                                None, None, gnum.data_ptr(), partials.data_ptr(), n, HW[0], HW[1], 9, 3, 0.5,
-                                                stream))
+        _lib.check(lib.dis_pattern_loss_multi_forward(d_arr, N_SCALES, im_l.data_ptr(), im_s.data_ptr(),
+                                                      loss.ph_loss.pattern.data_ptr(), g_arr, partials.data_ptr(),
+                                                      n, HW[0], HW[1], 9, 3, 0.5, stream))
     for _ in range(3):
         dominant()
     k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -295,9 +298,9 @@ def run_ours(args):
                     "h2d_bytes_per_step": int((2 + N_SCALES) * 4 * P * n), "d2h_bytes_per_step": 4},
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "kernel": "pattern_loss_kernel<census_sad, R=4, grad>",
+                         "traffic": None, "kernel": "pattern_multi_kernel<census_sad, R=4, 4 scales, grad>",
                          "kernel_ms": kernel_ms, "peak_source": peak_src,
-                         "limiter": "XU (rsqrt) + FP32 issue, not HBM: ~160 rsqrt per pixel-scale (see DESIGN.md)",
+                         "limiter": "XU (rsqrt) + FP32 issue, not HBM: ~100 rsqrt per pixel-scale (see DESIGN.md)",
                          "step_algorithmic_gbs": step_gbs, "step_frac": step_gbs / peak},
             "cpu_baseline": cpu,
         }

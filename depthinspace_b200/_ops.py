@@ -131,6 +131,38 @@ def pattern_loss_forward(disp, im, std, pattern, block_size, type, eps, want_pro
     return out3, proj, diff, gnum
 
 
+def pattern_loss_multi_forward(disps, im, std, pattern, block_size, type, eps, want_grad):
+    """S = 2 or 4 disparity maps of the same frames, census types only.
+    -> (out3 [S,3] rows (num_s, den, num_s/den), list of grad_num | None)"""
+    import ctypes
+    S = len(disps)
+    disps = [_chk(d, f"disp[{i}]") for i, d in enumerate(disps)]
+    im = _chk(im, "im")
+    N, C, H, W = disps[0].shape
+    if C != 1 or any(d.shape != disps[0].shape for d in disps) or tuple(im.shape) != (N, 1, H, W):
+        raise ValueError("all disparity maps and im must be [N,1,H,W] with equal shapes")
+    if std is not None:
+        std = _chk(std, "std")
+        if std.shape != im.shape:
+            raise ValueError("std must match im")
+    pattern = _chk(pattern, "pattern", None)
+    if pattern.numel() != H * W:
+        raise ValueError(f"pattern has {pattern.numel()} elements, expected {H}x{W}")
+    grads = [torch.empty_like(d) for d in disps] if want_grad else None
+    out3 = torch.empty((S, 3), dtype=torch.float32, device=im.device)
+    PtrArr = ctypes.c_void_p * S
+    d_arr = PtrArr(*[d.data_ptr() for d in disps])
+    g_arr = PtrArr(*[g.data_ptr() for g in grads]) if want_grad else None
+    with _on(im) as lib:
+        npart = lib.dis_pattern_loss_multi_num_partials(N, H, W)
+        partials = torch.empty(2 * S * max(npart, 1), dtype=torch.float32, device=im.device)
+        s = _stream(im)
+        _lib.check(lib.dis_pattern_loss_multi_forward(d_arr, S, _ptr(im), _ptr(std), _ptr(pattern), g_arr, _ptr(partials),
+                                                      N, H, W, int(block_size), loss_type_id(type), float(eps), s))
+        _lib.check(lib.dis_reduce_pairs_batched(_ptr(partials), npart, S, _ptr(out3), s))
+    return out3, grads
+
+
 def scale_by_device_scalar(x, numer, denom=None):
     """x * numer / denom with numer, denom one-element device tensors (no host sync)."""
     x = x.contiguous()

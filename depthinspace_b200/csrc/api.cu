@@ -3,6 +3,7 @@
 // state: the only static is a thread_local error string.
 #include <string.h>
 #include "photometric_kernels.cuh"
+#include "pattern_multi.cuh"
 
 namespace dis {
 
@@ -15,7 +16,7 @@ void set_last_cuda_error(cudaError_t e) {
 // defined in lcn.cu / misc.cu / smooth.cu / flow_warp.cu
 int lcn_forward(const float*, float*, float*, int, int, int, int, float, int, cudaStream_t);
 int pattern_warp_forward(const float*, const float*, float*, float*, int32_t*, int32_t*, int, int, int, cudaStream_t);
-int reduce_pairs(const float*, int, float*, cudaStream_t);
+int reduce_pairs(const float*, int, int, float*, cudaStream_t);
 int scale_by_device_scalar(const float*, float*, size_t, const float*, const float*, cudaStream_t);
 int mul(const float*, const float*, float*, size_t, cudaStream_t);
 int smooth_loss_num_partials(int, int, int);
@@ -70,6 +71,20 @@ int dispatch_pattern_loss(int R, const PatternLossArgs& a, int type, cudaStream_
   return DIS_ERR_UNSUPPORTED_BLOCK_SIZE;
 }
 
+int dispatch_pattern_multi(int R, const PatternMultiArgs& a, int S, int type, cudaStream_t s) {
+  switch (R) {
+    case 0: return launch_pattern_multi<0>(a, S, type, s);
+    case 1: return launch_pattern_multi<1>(a, S, type, s);
+    case 2: return launch_pattern_multi<2>(a, S, type, s);
+    case 3: return launch_pattern_multi<3>(a, S, type, s);
+    case 4: return launch_pattern_multi<4>(a, S, type, s);
+    case 5: return launch_pattern_multi<5>(a, S, type, s);
+    case 6: return launch_pattern_multi<6>(a, S, type, s);
+    case 7: return launch_pattern_multi<7>(a, S, type, s);
+  }
+  return DIS_ERR_UNSUPPORTED_BLOCK_SIZE;
+}
+
 }  // namespace
 }  // namespace dis
 
@@ -89,6 +104,7 @@ const char* dis_status_string(int status) {
     case DIS_ERR_CUDA_LAUNCH: return "CUDA launch failed";
     case DIS_ERR_UNSUPPORTED_KSIZE: return "unsupported Sobel ksize (3 or 5)";
     case DIS_ERR_WORKSPACE_TOO_SMALL: return "workspace too small";
+    case DIS_ERR_UNSUPPORTED_COMBINATION: return "unsupported combination of arguments for this entry point";
   }
   return "unknown status";
 }
@@ -190,7 +206,58 @@ int dis_pattern_loss_forward(const float* disp, const float* im, const float* st
 int dis_reduce_pairs(const float* partials, int n, float* out3, void* stream) {
   if (!partials || !out3) return DIS_ERR_NULL_POINTER;
   if (n < 0) return DIS_ERR_BAD_SHAPE;
-  return reduce_pairs(partials, n, out3, as_stream(stream));
+  return reduce_pairs(partials, n, 1, out3, as_stream(stream));
+}
+
+int dis_reduce_pairs_batched(const float* partials, int n, int count, float* out3, void* stream) {
+  if (!partials || !out3) return DIS_ERR_NULL_POINTER;
+  if (n < 0 || count < 0 || count > MAX_GRID_Z) return DIS_ERR_BAD_SHAPE;
+  if (count == 0) return DIS_OK;
+  return reduce_pairs(partials, n, count, out3, as_stream(stream));
+}
+
+int dis_pattern_loss_multi_num_partials(int N, int H, int W) {
+  if (N < 0 || H < 1 || W < 1) return DIS_ERR_BAD_SHAPE;
+  return N * ((H + MTH - 1) / MTH) * ((W + MTW - 1) / MTW);
+}
+
+int dis_pattern_loss_multi_forward(const float* const* disps, int S, const float* im, const float* std_in,
+                                   const float* pattern, float* const* grad_nums, float* partials, int N, int H,
+                                   int W, int block_size, int type, float eps, void* stream) {
+  if (int rc = check_block(block_size, type)) return rc;
+  if (type != CENSUS_MSE && type != CENSUS_SAD) return DIS_ERR_UNSUPPORTED_COMBINATION;
+  if (S != 2 && S != 4) return DIS_ERR_UNSUPPORTED_COMBINATION;
+  if (!disps || !im || !pattern || !partials) return DIS_ERR_NULL_POINTER;
+  bool any_grad = false, all_grad = true;
+  for (int s = 0; s < S; ++s) {
+    if (!disps[s]) return DIS_ERR_NULL_POINTER;
+    const bool g = grad_nums && grad_nums[s];
+    any_grad |= g;
+    all_grad &= g;
+  }
+  if (any_grad && !all_grad) return DIS_ERR_NULL_POINTER;
+  if (N < 0 || H < 2 || W < 2) return DIS_ERR_BAD_SHAPE;
+  if (N == 0) return DIS_OK;
+  const size_t hw = (size_t)H * W;
+  const int per_frame = ((H + MTH - 1) / MTH) * ((W + MTW - 1) / MTW);
+  for (int n0 = 0; n0 < N; n0 += MAX_GRID_Z) {
+    PatternMultiArgs a{};
+    uintptr_t align = 0;
+    for (int s = 0; s < S; ++s) {
+      a.disp[s] = disps[s] + n0 * hw;
+      a.grad_num[s] = any_grad ? grad_nums[s] + n0 * hw : nullptr;
+      align |= reinterpret_cast<uintptr_t>(a.grad_num[s]);
+    }
+    a.im = im + n0 * hw; a.std_in = std_in ? std_in + n0 * hw : nullptr; a.pattern = pattern;
+    a.partials = partials;
+    a.N = N - n0 < MAX_GRID_Z ? N - n0 : MAX_GRID_Z; a.H = H; a.W = W;
+    a.num_blocks = N * per_frame; a.block_offset = n0 * per_frame;
+    a.eps = eps; a.inv_k2 = 1.0f / (float)(block_size * block_size);
+    a.inv_w = 1.0f / (float)(W - 1); a.inv_h = 1.0f / (float)(H - 1);
+    a.vec_ok = (W % 2 == 0) && (align & 7) == 0;
+    if (int rc = dispatch_pattern_multi(block_size / 2, a, S, type, as_stream(stream))) return rc;
+  }
+  return DIS_OK;
 }
 
 int dis_scale_by_device_scalar(const float* in, float* out, size_t n, const float* numer, const float* denom,

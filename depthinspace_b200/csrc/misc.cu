@@ -30,6 +30,8 @@ __global__ void __launch_bounds__(256) pattern_warp_kernel(const float* __restri
 // Fixed-order, single-CTA reduction of n (a,b) pairs in fp64: bitwise reproducible run to run.
 __global__ void __launch_bounds__(1024) reduce_pairs_kernel(const float* __restrict__ p, int n, float* __restrict__ out3) {
   __shared__ double sa[1024], sb[1024];
+  p += (size_t)2 * n * blockIdx.x;   // one CTA per independent segment
+  out3 += 3 * blockIdx.x;
   double a = 0.0, b = 0.0;
   for (int i = threadIdx.x; i < n; i += 1024) { a += (double)p[2 * i]; b += (double)p[2 * i + 1]; }
   sa[threadIdx.x] = a; sb[threadIdx.x] = b;
@@ -88,8 +90,8 @@ int pattern_warp_forward(const float* disp, const float* pattern, float* proj, f
   return check_launch();
 }
 
-int reduce_pairs(const float* partials, int n, float* out3, cudaStream_t s) {
-  reduce_pairs_kernel<<<1, 1024, 0, s>>>(partials, n, out3);
+int reduce_pairs(const float* partials, int n, int count, float* out3, cudaStream_t s) {
+  reduce_pairs_kernel<<<count, 1024, 0, s>>>(partials, n, out3);
   return check_launch();
 }
 

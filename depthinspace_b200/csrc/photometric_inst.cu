@@ -1,6 +1,7 @@
 // One translation unit per window radius R = DIS_R (block_size = 2R+1): keeps every k x k loop fully
 // unrolled without a single multi-minute compile.  build.py compiles R = 0..7 in parallel.
 #include "photometric_kernels.cuh"
+#include "pattern_multi.cuh"
 
 #ifndef DIS_R
 #error "compile with -DDIS_R=<window radius>"
@@ -49,7 +50,29 @@ int pattern_loss_t(const PatternLossArgs& a, cudaStream_t s) {
   return check_launch();
 }
 
+template <int TYPE, int R, int NPAIR>
+int pattern_multi_t(const PatternMultiArgs& a, cudaStream_t s) {
+  const dim3 block(16, 16);
+  const dim3 grid((a.W + MTW - 1) / MTW, (a.H + MTH - 1) / MTH, a.N);
+  const size_t smem = pattern_multi_smem_bytes<R, NPAIR>();
+  if (a.grad_num[0]) {
+    if (int rc = prepare(pattern_multi_kernel<TYPE, R, NPAIR, true>, smem)) return rc;
+    pattern_multi_kernel<TYPE, R, NPAIR, true><<<grid, block, smem, s>>>(a);
+  } else {
+    if (int rc = prepare(pattern_multi_kernel<TYPE, R, NPAIR, false>, smem)) return rc;
+    pattern_multi_kernel<TYPE, R, NPAIR, false><<<grid, block, smem, s>>>(a);
+  }
+  return check_launch();
+}
+
 }  // namespace
+
+template <>
+int launch_pattern_multi<DIS_R>(const PatternMultiArgs& a, int S, int type, cudaStream_t s) {
+  if (type == CENSUS_SAD) return S == 4 ? pattern_multi_t<CENSUS_SAD, DIS_R, 2>(a, s) : pattern_multi_t<CENSUS_SAD, DIS_R, 1>(a, s);
+  if (type == CENSUS_MSE) return S == 4 ? pattern_multi_t<CENSUS_MSE, DIS_R, 2>(a, s) : pattern_multi_t<CENSUS_MSE, DIS_R, 1>(a, s);
+  return DIS_ERR_UNSUPPORTED_COMBINATION;
+}
 
 template <>
 int launch_photometric<DIS_R>(const PhotoArgs& a, int type, bool backward, cudaStream_t s) {

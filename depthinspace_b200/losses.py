@@ -36,10 +36,8 @@ class SingleFrameLoss(_HotPathLoss):
         if not isinstance(out, (tuple, list)):
             out = [out]
         im, std, amb = _merge(im_lcn)[:, 0:1], _merge(std), _merge(ambient)
-        vals = []
-        for s, o in enumerate(out):                                   # :108-115
-            val, _ = self.ph_loss(_merge(o), im, std)
-            vals.append(val / (2 ** s))
+        ph = self.ph_loss.forward_multi([_merge(o) for o in out], im, std)   # :108-115, all scales fused
+        vals = [v / (2 ** s) for s, v in enumerate(ph)]
         vals.append(self.disparity_loss(_merge(out[0]), amb) * 0.4)   # :118-124 (scale 0 only)
         if pseudo_gt is not None:                                     # :152-155 (DIS-FTSF)
             for s, o in enumerate(out):
@@ -52,10 +50,8 @@ class MultiFrameLoss(_HotPathLoss):
         if not isinstance(out, (tuple, list)):
             out = [out]
         im, std, amb = _merge(im_lcn)[:, 0:1], _merge(std), _merge(ambient)
-        vals = []
-        for s, o in enumerate(out):                                   # :110-117
-            val, _ = self.ph_loss(_merge(o), im, std)
-            vals.append(val / (2 ** s))
+        ph = self.ph_loss.forward_multi([_merge(o) for o in out], im, std)   # :110-117
+        vals = [v / (2 ** s) for s, v in enumerate(ph)]
         vals.append(self.disparity_loss(_merge(out[0]), amb) * 0.8)   # :120-126
         if primary_disp is not None:                                  # :160-165 (first two epochs)
             vals.append(torch.mean(torch.abs(out[0] - primary_disp)) * 0.1)

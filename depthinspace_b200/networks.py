@@ -85,6 +85,36 @@ class _PatternLossMean(torch.autograd.Function):
         return grad, None, None, None, None, None, None, None, None
 
 
+class _PatternLossMulti(torch.autograd.Function):
+    """S (2 or 4) scales of the same frames in one launch (census types): returns the S ratios."""
+
+    @staticmethod
+    def forward(ctx, im, std, pattern, block_size, type_id, eps, group, *disps):
+        ctx.set_materialize_grads(False)
+        S = len(disps)
+        need = [ctx.needs_input_grad[7 + i] for i in range(S)]
+        out3, grads = _ops.pattern_loss_multi_forward(list(disps), im, std, pattern, block_size, type_id, eps,
+                                                      want_grad=any(need))
+        if group is not None:
+            nd = out3[:, :2].contiguous()
+            all_reduce_sum_(nd, group)
+            out3 = torch.cat((nd, (nd[:, 0] / nd[:, 1]).unsqueeze(1)), dim=1)
+        ctx.S = S
+        ctx.save_for_backward(out3, *(grads if grads is not None else []))
+        return tuple(out3[i, 2].clone() for i in range(S))
+
+    @staticmethod
+    def backward(ctx, *g_vals):
+        out3, *grads = ctx.saved_tensors
+        res = []
+        for i in range(ctx.S):
+            if g_vals[i] is None or not grads or not ctx.needs_input_grad[7 + i]:
+                res.append(None)
+            else:
+                res.append(_ops.scale_by_device_scalar(grads[i], g_vals[i], out3[i, 1:2]))
+        return (None,) * 7 + tuple(res)
+
+
 class _PatternLossMap(torch.autograd.Function):
     """output_mean=False: per-pixel loss map (reference :375-376)."""
 
@@ -143,6 +173,28 @@ class RectifiedPatternSimilarityLoss(torch.nn.Module):
         return _PatternLossMap.apply(disp0, im, std, self.pattern, self.block_size, type_id, self.loss_eps)
 
     tforward = forward
+
+    def forward_multi(self, disps, im, std=None):
+        """The worker's photometric loop (model/single_frame_worker.py:108-115) in as few launches as possible:
+        groups of 4 / 2 scales go through the packed multi-scale kernel (census types), the rest one by one.
+        -> list of 0-dim ratios, one per disparity map (un-weighted)."""
+        self.pattern = self.pattern.to(device=im.device, dtype=torch.float32)
+        type_id = _ops.loss_type_id(self.loss_type)
+        im = im.contiguous()
+        vals, i = [], 0
+        while i < len(disps):
+            left = len(disps) - i
+            take = 4 if left >= 4 else (2 if left >= 2 else 1)
+            if take == 1 or type_id < 2:
+                v, _ = _PatternLossMean.apply(disps[i], im, std, self.pattern, self.block_size, type_id, self.loss_eps,
+                                              False, self.process_group)
+                vals.append(v)
+                take = 1
+            else:
+                vals.extend(_PatternLossMulti.apply(im, std, self.pattern, self.block_size, type_id, self.loss_eps,
+                                                    self.process_group, *disps[i:i + take]))
+            i += take
+        return vals
 
 
 class _SobelFunction(torch.autograd.Function):

@@ -45,7 +45,8 @@ typedef enum {
   DIS_ERR_NULL_POINTER = -4,
   DIS_ERR_CUDA_LAUNCH = -5,
   DIS_ERR_UNSUPPORTED_KSIZE = -6,
-  DIS_ERR_WORKSPACE_TOO_SMALL = -7
+  DIS_ERR_WORKSPACE_TOO_SMALL = -7,
+  DIS_ERR_UNSUPPORTED_COMBINATION = -8
 } dis_status;
 
 DIS_API int dis_abi_version(void);
@@ -91,6 +92,22 @@ DIS_API int dis_pattern_loss_forward(const float* disp, const float* im, const f
 
 /* Deterministic fixed-order reduction of n (a,b) pairs: out = {sum a, sum b, sum a / sum b}. */
 DIS_API int dis_reduce_pairs(const float* partials, int n, float* out3, void* stream);
+/* `count` independent segments of n pairs each (segment i at partials + 2*n*i) -> out3[3*i .. 3*i+2]. */
+DIS_API int dis_reduce_pairs_batched(const float* partials, int n, int count, float* out3, void* stream);
+
+/* ---- a8  photometric loop of the loss assembly, model/single_frame_worker.py:108-115 -------------
+ * S (2 or 4) disparity maps of the SAME frames against one (im, std): one launch evaluates the
+ * scale-independent half of the soft census (target term, sigma, tile loads) once and the estimate side
+ * with packed fp32x2 arithmetic, two scales per instruction.  census_mse / census_sad only
+ * (DIS_ERR_UNSUPPORTED_COMBINATION otherwise: use dis_pattern_loss_forward per scale).
+ *   disps, grad_nums   HOST arrays of S device pointers ([N,1,H,W] each); grad_nums may be NULL
+ *   partials           float[2 * S * dis_pattern_loss_multi_num_partials(N,H,W)], scale-major;
+ *                      reduce with dis_reduce_pairs_batched(partials, num_partials, S, out3). */
+DIS_API int dis_pattern_loss_multi_num_partials(int N, int H, int W);
+DIS_API int dis_pattern_loss_multi_forward(const float* const* disps, int S, const float* im,
+                                           const float* std_in, const float* pattern,
+                                           float* const* grad_nums, float* partials, int N, int H, int W,
+                                           int block_size, int type, float eps, void* stream);
 
 /* out[i] = in[i] * (*numer) / (*denom) (denom may be NULL = 1).  Scalars live on the device
  * so no host synchronisation is needed between forward and backward. */
