@@ -13,7 +13,7 @@
 // the MUFU pipe and the FP32 lanes are balanced at ~0.32 clk per tap (4 scales) per SM.
 //
 // Only the census types take this path (mse / sad have no scale-independent arithmetic worth sharing).
-// CTA = 256 threads = 16 (x) x 16 (y); tile 32 x 16 pixels; a thread owns 2 adjacent pixels of one row.
+// CTA = 256 threads = 32 (x) x 8 (y); tile 64 x 32 pixels; a thread owns 2 adjacent pixels of rows ty + 8g.
 #pragma once
 #include "window.cuh"
 
@@ -29,15 +29,15 @@ __device__ __forceinline__ u64 sub2(u64 a, u64 b) { u64 d; asm("sub.rn.f32x2 %0,
 __device__ __forceinline__ u64 mul2(u64 a, u64 b) { u64 d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
 __device__ __forceinline__ u64 bc2(float v) { return pk2(v, v); }  // ptxas folds this into a broadcast operand
 
-constexpr int MTW = 32, MTH = 16;             // tile
+constexpr int MTW = 64, MTH = 32;             // tile (halo re-computation 1.41x at R = 4)
+constexpr int MROWS_PER_PASS = 8;             // 256 threads = 32 (x, 2 px each) x 8 (y); 4 passes cover the tile
 constexpr int MFIX = 2 * MTH + 2 * MTW;       // border-line candidates per tile
 constexpr int MAX_SCALES = 4;
 
 template <int R>
 struct MultiGeom {
-  static constexpr int NW = 2 + 2 * R;                 // window values per thread-row
-  static constexpr int NWE = (NW + 1) & ~1;            // rounded to an even count (128-bit loads of float2 pairs)
-  static constexpr int PITCH = (MTW - 2) + NWE;        // >= MTW + 2R, even
+  static constexpr int NW = 2 + 2 * R;                 // window values per thread-row (always even)
+  static constexpr int PITCH = (MTW - 2) + NW;         // == MTW + 2R, even
   static constexpr int ROWS = MTH + 2 * R;
   static constexpr int COLS = MTW + 2 * R;
   static constexpr int PLANE = ROWS * PITCH;
@@ -99,12 +99,12 @@ __global__ void __launch_bounds__(256, 2) pattern_multi_kernel(PatternMultiArgs 
   float* sdd = sw + G::PLANE;                                // [S][MTH][MTW] d proj / d disp of own pixels
   float* fix = sdd + S * MTH * MTW;                          // [S][MFIX]
   float* red = fix + S * MFIX;                               // block-reduction scratch
-  const int tx = threadIdx.x, ty = threadIdx.y, tid = ty * 16 + tx;
+  const int tx = threadIdx.x, ty = threadIdx.y, tid = ty * 32 + tx;
   const int x0 = blockIdx.x * MTW, y0 = blockIdx.y * MTH, n = blockIdx.z;
   const size_t hw = (size_t)a.H * a.W;
   const size_t fo = (size_t)n * hw;
 
-  // ---- stage the tile: S pattern warps per position, image and sigma once ------------------------------
+  // ---- stage the tile: S pattern warps per position (shared y half), image and sigma once ---------------
   for (int idx = tid; idx < G::ROWS * G::COLS; idx += 256) {
     const int j = idx / G::COLS, i = idx - j * G::COLS;
     const int gy = y0 - R + j, gx = x0 - R + i;
@@ -116,115 +116,24 @@ __global__ void __launch_bounds__(256, 2) pattern_multi_kernel(PatternMultiArgs 
     for (int s = 0; s < S; ++s) dv[s] = __ldg(a.disp[s] + g);          // S independent loads in flight
     const float tv = __ldg(a.im + g);
     const float wv = inside ? (a.std_in ? __ldg(a.std_in + g) : 1.0f) : 0.0f;
-    const float gyn = normalize_coord((float)cy, a.inv_h);
-    Bilinear b[S];
-    Corners c[S];
-#pragma unroll
-    for (int s = 0; s < S; ++s) {
-      bilinear_setup<true>(normalize_coord(fsub((float)cx, dv[s]), a.inv_w), gyn, a.H, a.W, b[s]);
-      c[s] = fetch_corners(a.pattern, a.H, a.W, b[s]);                 // 4S gathers in flight
-    }
+    const WarpRow row = warp_row_setup(a.pattern, cy, a.H, a.W, a.inv_h);
     const bool own = GRAD && j >= R && j < R + MTH && i >= R && i < R + MTW;
+    float ev[S], dd[S];
 #pragma unroll
-    for (int p = 0; p < NPAIR; ++p)
-      se[p * G::PLANE + j * G::PITCH + i] = make_float2(blend(c[2 * p], b[2 * p]), blend(c[2 * p + 1], b[2 * p + 1]));
+    for (int s = 0; s < S; ++s) ev[s] = warp_col_sample(row, dv[s], cx, a.W, a.inv_w, own ? &dd[s] : nullptr);
+#pragma unroll
+    for (int p = 0; p < NPAIR; ++p) se[p * G::PLANE + j * G::PITCH + i] = make_float2(ev[2 * p], ev[2 * p + 1]);
     st[j * G::PITCH + i] = tv;
     sw[j * G::PITCH + i] = wv;
     if (own) {
 #pragma unroll
-      for (int s = 0; s < S; ++s)
-        sdd[(s * MTH + (j - R)) * MTW + (i - R)] = -(((b[s].gx_mult * blend_dx(c[s], b[s])) * 2.0f) * a.inv_w);
+      for (int s = 0; s < S; ++s) sdd[(s * MTH + (j - R)) * MTW + (i - R)] = dd[s];
     }
   }
   __syncthreads();
 
-  // ---- window loop: thread = pixels (2tx, 2tx+1) of row ty --------------------------------------------
-  u64 ec[NPAIR][2], acc_dummy;
-  (void)acc_dummy;
-  float acc[NPAIR][2][2];
-  u64 ga[NPAIR][2], gb[NPAIR][2];
-  float tc[2], wc[2];
-#pragma unroll
-  for (int i = 0; i < 2; ++i) {
-    const int o = (ty + R) * G::PITCH + 2 * tx + i + R;
-    tc[i] = st[o];
-    wc[i] = sw[o];
-#pragma unroll
-    for (int p = 0; p < NPAIR; ++p) {
-      const float2 v = se[p * G::PLANE + o];
-      ec[p][i] = pk2(v.x, v.y);
-      acc[p][i][0] = acc[p][i][1] = 0.0f;
-      ga[p][i] = gb[p][i] = pk2(0.0f, 0.0f);
-    }
-  }
-  const u64 eps2 = bc2(a.eps);
-#pragma unroll 1
-  for (int j = 0; j <= 2 * R; ++j) {
-    const int base = (ty + j) * G::PITCH + 2 * tx;
-    u64 er[NPAIR][G::NWE];
-    float tr[G::NWE], wr[G::NWE];
-#pragma unroll
-    for (int v = 0; v < G::NWE / 2; ++v) {
-#pragma unroll
-      for (int p = 0; p < NPAIR; ++p) {
-        const float4 q = *reinterpret_cast<const float4*>(se + p * G::PLANE + base + 2 * v);
-        er[p][2 * v] = pk2(q.x, q.y);
-        er[p][2 * v + 1] = pk2(q.z, q.w);
-      }
-      const float2 t2 = *reinterpret_cast<const float2*>(st + base + 2 * v);
-      tr[2 * v] = t2.x; tr[2 * v + 1] = t2.y;
-      const float2 w2 = *reinterpret_cast<const float2*>(sw + base + 2 * v);
-      wr[2 * v] = w2.x; wr[2 * v + 1] = w2.y;
-    }
-#pragma unroll
-    for (int i = 0; i < 2; ++i)
-#pragma unroll
-      for (int dx = 0; dx <= 2 * R; ++dx) {
-        const int k = i + dx;
-        // target side, shared by all scales: gt = dt * rt (rounded) and its exact rounding residual
-        const float dt = tr[k] - tc[i];
-        const float rt = rsqrt_fast(fmaf(dt, dt, a.eps));
-        const float gt = __fmul_rn(dt, rt);
-        const float rest = __fmaf_rn(dt, rt, -gt);
-#pragma unroll
-        for (int p = 0; p < NPAIR; ++p) {
-          const u64 de = sub2(er[p][k], ec[p][i]);
-          const u64 xe = fma2(de, de, eps2);
-          float x0f, x1f;
-          upk2(xe, x0f, x1f);
-          const float r0 = rsqrt_fast(x0f), r1 = rsqrt_fast(x1f);
-          const u64 re = pk2(r0, r1);
-          // diff2 = (de*re - gt) - (dt*rt - gt): both products enter through an exact FMA residual, so
-          // e == t gives exactly 0 (the reference's |.| has subgradient 0 there) and e != t costs one rounding
-          const u64 diff = sub2(fma2(de, re, bc2(-gt)), bc2(rest));
-          float d0, d1;
-          upk2(diff, d0, d1);
-          if (TYPE == CENSUS_SAD) {
-            acc[p][i][0] += fabsf(d0);
-            acc[p][i][1] += fabsf(d1);
-          } else {
-            acc[p][i][0] = fmaf(d0, d0, acc[p][i][0]);
-            acc[p][i][1] = fmaf(d1, d1, acc[p][i][1]);
-          }
-          if (GRAD) {
-            const u64 r3 = mul2(mul2(re, re), re);
-            u64 u;
-            if (TYPE == CENSUS_SAD) {
-              float q0, q1;
-              upk2(r3, q0, q1);
-              u = pk2(signed_mag(q0, d0), signed_mag(q1, d1));
-            } else {
-              u = mul2(diff, r3);
-            }
-            ga[p][i] = fma2(u, bc2(wr[k]), ga[p][i]);
-            gb[p][i] = add2(gb[p][i], u);
-          }
-        }
-      }
-  }
-
-  // ---- border-line pixels: exact clamp multiplicities (one pixel-scale per thread) ---------------------
   const bool edge_tile = (x0 == 0) || (y0 == 0) || (x0 + MTW >= a.W) || (y0 + MTH >= a.H);
+  // ---- border-line pixels: exact clamp multiplicities (one pixel-scale per thread) ---------------------
   if (GRAD && edge_tile) {
     for (int item = tid; item < S * MFIX; item += 256) {
       const int s = item / MFIX, c = item - s * MFIX;
@@ -240,57 +149,147 @@ __global__ void __launch_bounds__(256, 2) pattern_multi_kernel(PatternMultiArgs 
     __syncthreads();
   }
 
-  // ---- epilogue ----------------------------------------------------------------------------------------
   const float fs = fwd_scale<TYPE>() * a.inv_k2;
   const float gs = -0.5f * a.eps * a.inv_k2;
-  const int gy = y0 + ty;
+  const u64 eps2 = bc2(a.eps);
   float num[S], den = 0.0f;
 #pragma unroll
   for (int s = 0; s < S; ++s) num[s] = 0.0f;
-  float gout[S][2];
+
+  // ---- window loop: thread = pixels (2tx, 2tx+1) of rows ty, ty+8, ty+16, ty+24 ------------------------
+#pragma unroll 1
+  for (int pass = 0; pass < MTH / MROWS_PER_PASS; ++pass) {
+    const int ly = ty + pass * MROWS_PER_PASS;
+    u64 ec[NPAIR][2];
+    float acc[NPAIR][2][2];
+    u64 ga[NPAIR][2], gb[NPAIR][2];
+    float tc[2], wc[2];
 #pragma unroll
-  for (int i = 0; i < 2; ++i) {
-    const int gx = x0 + 2 * tx + i;
-    const bool valid = gy < a.H && gx < a.W;
-    if (valid) den += wc[i];
-    int slot = -1;
-    if (GRAD && edge_tile && valid) {
-      if (gx == 0) slot = ty;
-      else if (gx == a.W - 1) slot = MTH + ty;
-      else if (gy == 0) slot = 2 * MTH + 2 * tx + i;
-      else if (gy == a.H - 1) slot = 2 * MTH + MTW + 2 * tx + i;
+    for (int i = 0; i < 2; ++i) {
+      const int o = (ly + R) * G::PITCH + 2 * tx + i + R;
+      tc[i] = st[o];
+      wc[i] = sw[o];
+#pragma unroll
+      for (int p = 0; p < NPAIR; ++p) {
+        const float2 v = se[p * G::PLANE + o];
+        ec[p][i] = pk2(v.x, v.y);
+        acc[p][i][0] = acc[p][i][1] = 0.0f;
+        ga[p][i] = gb[p][i] = pk2(0.0f, 0.0f);
+      }
     }
+#pragma unroll 1
+    for (int j = 0; j <= 2 * R; ++j) {
+      const int base = (ly + j) * G::PITCH + 2 * tx;
+      u64 er[NPAIR][G::NW];
+      float tr[G::NW], wr[G::NW];
 #pragma unroll
-    for (int p = 0; p < NPAIR; ++p) {
-      float g0 = 0.f, g1 = 0.f;
-      if (GRAD) {
-        float a0, a1, b0, b1;
-        upk2(ga[p][i], a0, a1);
-        upk2(gb[p][i], b0, b1);
-        g0 = fmaf(wc[i], b0, a0);
-        g1 = fmaf(wc[i], b1, a1);
-        if (slot >= 0) { g0 = fix[(2 * p) * MFIX + slot]; g1 = fix[(2 * p + 1) * MFIX + slot]; }
+      for (int v = 0; v < G::NW / 2; ++v) {
+#pragma unroll
+        for (int p = 0; p < NPAIR; ++p) {
+          const float4 q = *reinterpret_cast<const float4*>(se + p * G::PLANE + base + 2 * v);
+          er[p][2 * v] = pk2(q.x, q.y);
+          er[p][2 * v + 1] = pk2(q.z, q.w);
+        }
+        const float2 t2 = *reinterpret_cast<const float2*>(st + base + 2 * v);
+        tr[2 * v] = t2.x; tr[2 * v + 1] = t2.y;
+        const float2 w2 = *reinterpret_cast<const float2*>(sw + base + 2 * v);
+        wr[2 * v] = w2.x; wr[2 * v + 1] = w2.y;
       }
 #pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        const int s = 2 * p + h;
-        if (valid) num[s] = fmaf(wc[i], acc[p][i][h] * fs, num[s]);
-        if (GRAD) gout[s][i] = (h ? g1 : g0) * gs * sdd[(s * MTH + ty) * MTW + 2 * tx + i];
+      for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int dx = 0; dx <= 2 * R; ++dx) {
+          const int k = i + dx;
+          // target side, shared by all scales: gt = dt * rt (rounded) and its exact rounding residual
+          const float dt = tr[k] - tc[i];
+          const float rt = rsqrt_fast(fmaf(dt, dt, a.eps));
+          const float gt = __fmul_rn(dt, rt);
+          const float rest = __fmaf_rn(dt, rt, -gt);
+#pragma unroll
+          for (int p = 0; p < NPAIR; ++p) {
+            const u64 de = sub2(er[p][k], ec[p][i]);
+            const u64 xe = fma2(de, de, eps2);
+            float x0f, x1f;
+            upk2(xe, x0f, x1f);
+            const float r0 = rsqrt_fast(x0f), r1 = rsqrt_fast(x1f);
+            const u64 re = pk2(r0, r1);
+            // diff2 = (de*re - gt) - (dt*rt - gt): both products enter through an exact FMA residual, so
+            // e == t gives exactly 0 (the reference's |.| has subgradient 0 there) and e != t costs one rounding
+            const u64 diff = sub2(fma2(de, re, bc2(-gt)), bc2(rest));
+            float d0, d1;
+            upk2(diff, d0, d1);
+            if (TYPE == CENSUS_SAD) {
+              acc[p][i][0] += fabsf(d0);
+              acc[p][i][1] += fabsf(d1);
+            } else {
+              acc[p][i][0] = fmaf(d0, d0, acc[p][i][0]);
+              acc[p][i][1] = fmaf(d1, d1, acc[p][i][1]);
+            }
+            if (GRAD) {
+              const u64 r3 = mul2(mul2(re, re), re);
+              u64 u;
+              if (TYPE == CENSUS_SAD) {
+                float q0, q1;
+                upk2(r3, q0, q1);
+                u = pk2(signed_mag(q0, d0), signed_mag(q1, d1));
+              } else {
+                u = mul2(diff, r3);
+              }
+              ga[p][i] = fma2(u, bc2(wr[k]), ga[p][i]);
+              gb[p][i] = add2(gb[p][i], u);
+            }
+          }
+        }
+    }
+
+    // ---- per-pass epilogue ---------------------------------------------------------------------------
+    const int gy = y0 + ly;
+    float gout[S][2];
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const int gx = x0 + 2 * tx + i;
+      const bool valid = gy < a.H && gx < a.W;
+      if (valid) den += wc[i];
+      int slot = -1;
+      if (GRAD && edge_tile && valid) {
+        if (gx == 0) slot = ly;
+        else if (gx == a.W - 1) slot = MTH + ly;
+        else if (gy == 0) slot = 2 * MTH + 2 * tx + i;
+        else if (gy == a.H - 1) slot = 2 * MTH + MTW + 2 * tx + i;
+      }
+#pragma unroll
+      for (int p = 0; p < NPAIR; ++p) {
+        float g0 = 0.f, g1 = 0.f;
+        if (GRAD) {
+          float a0, a1, b0, b1;
+          upk2(ga[p][i], a0, a1);
+          upk2(gb[p][i], b0, b1);
+          g0 = fmaf(wc[i], b0, a0);
+          g1 = fmaf(wc[i], b1, a1);
+          if (slot >= 0) { g0 = fix[(2 * p) * MFIX + slot]; g1 = fix[(2 * p + 1) * MFIX + slot]; }
+        }
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int s = 2 * p + h;
+          if (valid) num[s] = fmaf(wc[i], acc[p][i][h] * fs, num[s]);
+          if (GRAD) gout[s][i] = (h ? g1 : g0) * gs * sdd[(s * MTH + ly) * MTW + 2 * tx + i];
+        }
+      }
+    }
+    if (GRAD && gy < a.H) {
+      const int gx = x0 + 2 * tx;
+#pragma unroll
+      for (int s = 0; s < S; ++s) {
+        float* p = a.grad_num[s] + fo + (size_t)gy * a.W + gx;
+        if (a.vec_ok && gx + 1 < a.W) __stcs(reinterpret_cast<float2*>(p), make_float2(gout[s][0], gout[s][1]));
+        else {
+          if (gx < a.W) p[0] = gout[s][0];
+          if (gx + 1 < a.W) p[1] = gout[s][1];
+        }
       }
     }
   }
-  if (GRAD && gy < a.H) {
-    const int gx = x0 + 2 * tx;
-#pragma unroll
-    for (int s = 0; s < S; ++s) {
-      float* p = a.grad_num[s] + fo + (size_t)gy * a.W + gx;
-      if (a.vec_ok && gx + 1 < a.W) __stcs(reinterpret_cast<float2*>(p), make_float2(gout[s][0], gout[s][1]));
-      else {
-        if (gx < a.W) p[0] = gout[s][0];
-        if (gx + 1 < a.W) p[1] = gout[s][1];
-      }
-    }
-  }
+
   // block reduction of S numerators + 1 denominator (fixed order)
   const int lane = tid & 31, wid = tid >> 5;
 #pragma unroll

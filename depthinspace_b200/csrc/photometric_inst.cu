@@ -52,7 +52,7 @@ int pattern_loss_t(const PatternLossArgs& a, cudaStream_t s) {
 
 template <int TYPE, int R, int NPAIR>
 int pattern_multi_t(const PatternMultiArgs& a, cudaStream_t s) {
-  const dim3 block(16, 16);
+  const dim3 block(32, 8);
   const dim3 grid((a.W + MTW - 1) / MTW, (a.H + MTH - 1) / MTH, a.N);
   const size_t smem = pattern_multi_smem_bytes<R, NPAIR>();
   if (a.grad_num[0]) {

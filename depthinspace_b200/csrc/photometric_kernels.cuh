@@ -163,13 +163,14 @@ __global__ void __launch_bounds__(NTHREADS, 2) pattern_loss_kernel(PatternLossAr
     const bool inside = gy >= 0 && gy < a.H && gx >= 0 && gx < a.W;
     const int cy = clampi(gy, 0, a.H - 1), cx = clampi(gx, 0, a.W - 1);
     const size_t g = (size_t)cy * a.W + cx;
-    float dd;
-    const float e = pattern_warp_pixel(a.pattern, __ldg(disp + g), cy, cx, a.H, a.W, a.inv_w, a.inv_h,
-                                       GRAD ? &dd : nullptr);
+    const bool own = GRAD && j >= R && j < R + TH && i >= R && i < R + TW;
+    float dd = 0.0f;
+    const WarpRow row = warp_row_setup(a.pattern, cy, a.H, a.W, a.inv_h);
+    const float e = warp_col_sample(row, __ldg(disp + g), cx, a.W, a.inv_w, own ? &dd : nullptr);
     se[j * G::PITCH + i] = e;
     st[j * G::PITCH + i] = __ldg(im + g);
     sw[j * G::PITCH + i] = inside ? (sd ? __ldg(sd + g) : 1.0f) : 0.0f;
-    if (GRAD && j >= R && j < R + TH && i >= R && i < R + TW) sdd[(j - R) * TW + (i - R)] = dd;
+    if (own) sdd[(j - R) * TW + (i - R)] = dd;
   }
   __syncthreads();
 

@@ -434,14 +434,14 @@ def test_pattern_loss_multi_scale_kernel(mods, lt, S, hw, k):
         o64 = c_oracle.pattern_loss(disps[s], im_l, im_s, to_np(mod.pattern), k, tid, 0.5, True, "f64")
         o32 = c_oracle.pattern_loss(disps[s], im_l, im_s, to_np(mod.pattern), k, tid, 0.5, True, "f32")
         assert_scalar_close(vals[s].item(), o64["val"], name=f"val scale {s}")
-        assert_close(dd[s].grad, (0.5 ** s) * o32["grad_disp"], name=f"grad scale {s} vs fp32 oracle", outlier_frac=1e-4 if "sad" in lt else 0)
+        assert_close(dd[s].grad, (0.5 ** s) * o32["grad_disp"], name=f"grad scale {s} vs fp32 oracle", outlier_frac=5e-4 if "sad" in lt else 0)
         assert_close(dd[s].grad, (0.5 ** s) * o64["grad_disp"], 2e-5, name=f"grad scale {s} vs fp64 oracle", outlier_frac=2e-3)
         # single-scale kernel on the same inputs
         d1 = dev(disps[s]).requires_grad_(True)
         v1, _ = mod(d1, dev(im_l), dev(im_s))
         (v1 * (0.5 ** s)).backward()
         assert_scalar_close(vals[s].item(), v1.item(), 2e-6, name="multi vs single kernel")
-        assert_close(dd[s].grad, d1.grad, 2e-6, name="multi vs single kernel grad", outlier_frac=1e-4 if "sad" in lt else 0)
+        assert_close(dd[s].grad, d1.grad, 2e-6, name="multi vs single kernel grad", outlier_frac=5e-4 if "sad" in lt else 0)
 
 
 def test_pattern_loss_multi_exact_zero_when_estimate_equals_target(mods):
