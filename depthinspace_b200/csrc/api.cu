@@ -116,7 +116,7 @@ int dis_lcn_forward(const float* x, float* lcn, float* std_out, int N, int H, in
   if (!x || !lcn || !std_out) return DIS_ERR_NULL_POINTER;
   if (N < 0 || H < 1 || W < 1 || radius < 1 || radius > 8 || radius >= H || radius >= W) return DIS_ERR_BAD_SHAPE;
   if (N == 0) return DIS_OK;
-  const int vec_ok = (W % 4 == 0) && aligned16(lcn, std_out);
+  const int vec_ok = (W % 4 == 0) && aligned16(x, lcn, std_out);
   const size_t hw = (size_t)H * W;
   for (int n0 = 0; n0 < N; n0 += MAX_GRID_Z) {
     const int nb = N - n0 < MAX_GRID_Z ? N - n0 : MAX_GRID_Z;

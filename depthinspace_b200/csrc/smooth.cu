@@ -56,13 +56,49 @@ __device__ __forceinline__ float sobel5_adjoint(F u_at, int qy, int qx) {
   return acc;
 }
 
+// 4 horizontally adjacent Sobel responses from a 5 x 8 register window (rows r0..r4 of 8 floats each)
+__device__ __forceinline__ void sobel5_quad(const float (&win)[5][8], float (&gx)[4], float (&gy)[4]) {
+  constexpr float k[5][5] = {{SOB(-5.0), SOB(-4.0), 0.f, SOB(4.0), SOB(5.0)},
+                             {SOB(-8.0), SOB(-10.0), 0.f, SOB(10.0), SOB(8.0)},
+                             {SOB(-10.0), SOB(-20.0), 0.f, SOB(20.0), SOB(10.0)},
+                             {SOB(-8.0), SOB(-10.0), 0.f, SOB(10.0), SOB(8.0)},
+                             {SOB(-5.0), SOB(-4.0), 0.f, SOB(4.0), SOB(5.0)}};
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    float ax = 0.f, ay = 0.f;
+#pragma unroll
+    for (int i = 0; i < 5; ++i)
+#pragma unroll
+      for (int j = 0; j < 5; ++j) {
+        if (j != 2) ax = fmaf(k[i][j], win[i][q + j], ax);
+        if (i != 2) ay = fmaf(k[j][i], win[i][q + j], ay);
+      }
+    gx[q] = ax;
+    gy[q] = ay;
+  }
+}
+
+__device__ __forceinline__ void load_row8(const float* __restrict__ p, float (&r)[8]) {
+  const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
+  r[0] = a.x; r[1] = a.y; r[2] = a.z; r[3] = a.w; r[4] = b.x; r[5] = b.y; r[6] = b.z; r[7] = b.w;
+}
+
+// Tile 64 x 32.  Shared planes (all pitches multiples of 4 floats, every quad 16-byte aligned):
+//   sd, si  : inputs, replicate-clamped, origin (-4,-4): 40 rows x 72 cols
+//   sux, suy: u = sign(g a) a, zero outside the image, origin (-2,-2): 36 rows x 68 cols
+// Responses are produced in quads starting at tile-local column -2 + 4q, so their 8-wide input windows
+// (origin -4 + 4q) and their stores (origin -2 + 4q) are both aligned; the adjoint quads start at 4q and read
+// the u window starting at 4q - 2, aligned again.
 template <bool GRAD>
 __global__ void __launch_bounds__(SNT) smooth_loss_kernel(const float* __restrict__ disp, const float* __restrict__ im,
                                                           float* __restrict__ grad_sum, float* __restrict__ partials,
-                                                          int H, int W) {
-  __shared__ float sd[IN_H * IN_P];
-  __shared__ float si[IN_H * IN_P];
-  __shared__ float2 su[GRAD ? U_H * U_P : 1];
+                                                          int H, int W, int vec_ok) {
+  constexpr int P = IN_P;   // 72
+  constexpr int PU = U_P;   // 68
+  __shared__ __align__(16) float sd[IN_H * P];
+  __shared__ __align__(16) float si[IN_H * P];
+  __shared__ __align__(16) float sux[GRAD ? U_H * PU : 4];
+  __shared__ __align__(16) float suy[GRAD ? U_H * PU : 4];
   __shared__ float red[2 * (SNT / 32)];
   const int tid = threadIdx.x;
   const int x0 = blockIdx.x * STW, y0 = blockIdx.y * STH, n = blockIdx.z;
@@ -72,48 +108,100 @@ __global__ void __launch_bounds__(SNT) smooth_loss_kernel(const float* __restric
   for (int idx = tid; idx < IN_H * IN_W; idx += SNT) {
     const int j = idx / IN_W, i = idx - j * IN_W;
     const size_t g = (size_t)clampi(y0 - 4 + j, 0, H - 1) * W + clampi(x0 - 4 + i, 0, W - 1);
-    sd[j * IN_P + i] = __ldg(d + g);
-    si[j * IN_P + i] = __ldg(a + g);
+    sd[j * P + i] = __ldg(d + g);
+    si[j * P + i] = __ldg(a + g);
   }
   __syncthreads();
 
-  // u over the tile plus a halo of 2; the loss itself only over the tile's own pixels
   float lsum = 0.f, lcnt = 0.f;
-  for (int idx = tid; idx < U_H * U_W; idx += SNT) {
-    const int j = idx / U_W, i = idx - j * U_W;
-    const int gy = y0 - 2 + j, gx = x0 - 2 + i;
-    const bool own = j >= 2 && j < 2 + STH && i >= 2 && i < 2 + STW;
-    if (!GRAD && !own) continue;
-    float2 u = make_float2(0.f, 0.f);
-    if (gy >= 0 && gy < H && gx >= 0 && gx < W) {
-      float gdx, gdy, gix, giy;
-      sobel5_at(sd + j * IN_P + i, IN_P, gdx, gdy);  // input tile origin is (-4,-4): window top-left = (j, i)
-      sobel5_at(si + j * IN_P + i, IN_P, gix, giy);
-      const float ax = expf(-fabsf(255.0f * gix)), ay = expf(-fabsf(255.0f * giy));
-      const float vx = gdx * ax, vy = gdy * ay;
-      if (own) { lsum += fabsf(vx) + fabsf(vy); lcnt += 2.0f; }
-      u = make_float2(sign0(vx) * ax, sign0(vy) * ay);
+  constexpr int UROWS = GRAD ? U_H : STH;   // rows -2..33 with the gradient, 0..31 without
+  constexpr int UQ = U_W / 4;               // 17 quads: columns -2..65
+  for (int item = tid; item < UROWS * UQ; item += SNT) {
+    const int jr = item / UQ, q = item - jr * UQ;
+    const int ly = GRAD ? jr - 2 : jr;      // tile-local row of the responses
+    const int lx = 4 * q - 2;               // tile-local column of the first response
+    const int gy = y0 + ly;
+    float ux[4] = {0.f, 0.f, 0.f, 0.f}, uy[4] = {0.f, 0.f, 0.f, 0.f};
+    if (gy >= 0 && gy < H) {
+      // response (ly, lx+c) reads tile-local rows ly-2..ly+2, cols lx+c-2..lx+c+2 = smem rows ly+2.., cols 4q+c..
+      float wd[5][8], wi[5][8];
+#pragma unroll
+      for (int i = 0; i < 5; ++i) {
+        load_row8(sd + (ly + 2 + i) * P + 4 * q, wd[i]);
+        load_row8(si + (ly + 2 + i) * P + 4 * q, wi[i]);
+      }
+      float gdx[4], gdy[4], gix[4], giy[4];
+      sobel5_quad(wd, gdx, gdy);
+      sobel5_quad(wi, gix, giy);
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const int gx = x0 + lx + c;
+        if (gx >= 0 && gx < W) {
+          const float ax = expf(-fabsf(255.0f * gix[c])), ay = expf(-fabsf(255.0f * giy[c]));
+          const float vx = gdx[c] * ax, vy = gdy[c] * ay;
+          if (ly >= 0 && ly < STH && lx + c >= 0 && lx + c < STW) { lsum += fabsf(vx) + fabsf(vy); lcnt += 2.0f; }
+          ux[c] = sign0(vx) * ax;
+          uy[c] = sign0(vy) * ay;
+        }
+      }
     }
-    if (GRAD) su[j * U_P + i] = u;
+    if (GRAD) {  // response (ly, lx+c) lives at u-plane (ly+2, 4q+c)
+      *reinterpret_cast<float4*>(sux + (ly + 2) * PU + 4 * q) = make_float4(ux[0], ux[1], ux[2], ux[3]);
+      *reinterpret_cast<float4*>(suy + (ly + 2) * PU + 4 * q) = make_float4(uy[0], uy[1], uy[2], uy[3]);
+    }
   }
   if (GRAD) {
     __syncthreads();
     float* go = grad_sum + (size_t)n * hw;
-    auto u_at = [&](int ly, int lx) -> float2 {  // tile-local coords; zero beyond the stored halo (= outside image)
+    constexpr float k[5][5] = {{SOB(-5.0), SOB(-4.0), 0.f, SOB(4.0), SOB(5.0)},
+                               {SOB(-8.0), SOB(-10.0), 0.f, SOB(10.0), SOB(8.0)},
+                               {SOB(-10.0), SOB(-20.0), 0.f, SOB(20.0), SOB(10.0)},
+                               {SOB(-8.0), SOB(-10.0), 0.f, SOB(10.0), SOB(8.0)},
+                               {SOB(-5.0), SOB(-4.0), 0.f, SOB(4.0), SOB(5.0)}};
+    auto u_at = [&](int ly, int lx) -> float2 {  // tile-local; zero beyond the stored halo (= outside the image)
       if (ly < -2 || ly >= STH + 2 || lx < -2 || lx >= STW + 2) return make_float2(0.f, 0.f);
-      return su[(ly + 2) * U_P + lx + 2];
+      return make_float2(sux[(ly + 2) * PU + lx + 2], suy[(ly + 2) * PU + lx + 2]);
     };
-    for (int idx = tid; idx < STH * STW; idx += SNT) {
-      const int ly = idx / STW, lx = idx - ly * STW;
+    for (int item = tid; item < STH * (STW / 4); item += SNT) {
+      const int ly = item / (STW / 4), lx = 4 * (item - ly * (STW / 4));
       const int gy = y0 + ly, gx = x0 + lx;
       if (gy >= H || gx >= W) continue;
-      // pre-image of (gy,gx) under replicate clamping of the pad-2 domain
-      const int ylo = (gy == 0) ? -2 : 0, yhi = (gy == H - 1) ? 2 : 0;
-      const int xlo = (gx == 0) ? -2 : 0, xhi = (gx == W - 1) ? 2 : 0;
-      float acc = 0.f;
-      for (int py = ylo; py <= yhi; ++py)
-        for (int px = xlo; px <= xhi; ++px) acc += sobel5_adjoint(u_at, ly + py, lx + px);
-      go[(size_t)gy * W + gx] = acc;
+      // grad(q) = sum_{i,j} kx[i][j] ux(q - (i-2, j-2)) + ky[i][j] uy(q - (i-2, j-2))
+      // u window: tile-local rows ly-2..ly+2, cols lx-2..lx+5 = u-plane rows ly.., cols lx..lx+7
+      float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int r = 0; r < 5; ++r) {   // u row offset r-2  => i = 4 - r
+        float vx[8], vy[8];
+        load_row8(sux + (ly + r) * PU + lx, vx);
+        load_row8(suy + (ly + r) * PU + lx, vy);
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+#pragma unroll
+          for (int t = 0; t < 5; ++t) {  // u col offset t-2 => j = 4 - t
+            const int i = 4 - r, j = 4 - t;
+            if (j != 2) acc[c] = fmaf(k[i][j], vx[c + t], acc[c]);
+            if (i != 2) acc[c] = fmaf(k[j][i], vy[c + t], acc[c]);
+          }
+      }
+      // border-line pixels also collect the pad-2 positions that replicate-clamp onto them
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const int px_ = gx + c;
+        if (px_ < W && (gy == 0 || gy == H - 1 || px_ == 0 || px_ == W - 1)) {
+          const int ylo = (gy == 0) ? -2 : 0, yhi = (gy == H - 1) ? 2 : 0;
+          const int xlo = (px_ == 0) ? -2 : 0, xhi = (px_ == W - 1) ? 2 : 0;
+          float v = 0.f;
+          for (int py2 = ylo; py2 <= yhi; ++py2)
+            for (int px2 = xlo; px2 <= xhi; ++px2) v += sobel5_adjoint(u_at, ly + py2, lx + c + px2);
+          acc[c] = v;
+        }
+      }
+      float* o = go + (size_t)gy * W + gx;
+      if (vec_ok && gx + 3 < W) __stcs(reinterpret_cast<float4*>(o), make_float4(acc[0], acc[1], acc[2], acc[3]));
+      else {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) if (gx + c < W) o[c] = acc[c];
+      }
     }
   }
   block_sum2<SNT>(lsum, lcnt, red);
@@ -204,8 +292,9 @@ int smooth_loss_num_partials(int N, int H, int W) { return N * ((H + STH - 1) / 
 int smooth_loss_forward(const float* disp, const float* im, float* grad_sum, float* partials, int N, int H, int W,
                         cudaStream_t s) {
   dim3 grid((W + STW - 1) / STW, (H + STH - 1) / STH, N);
-  if (grad_sum) smooth_loss_kernel<true><<<grid, SNT, 0, s>>>(disp, im, grad_sum, partials, H, W);
-  else smooth_loss_kernel<false><<<grid, SNT, 0, s>>>(disp, im, nullptr, partials, H, W);
+  const int vec_ok = (W % 4 == 0) && ((reinterpret_cast<uintptr_t>(grad_sum) & 15) == 0);
+  if (grad_sum) smooth_loss_kernel<true><<<grid, SNT, 0, s>>>(disp, im, grad_sum, partials, H, W, vec_ok);
+  else smooth_loss_kernel<false><<<grid, SNT, 0, s>>>(disp, im, nullptr, partials, H, W, vec_ok);
   return check_launch();
 }
 
