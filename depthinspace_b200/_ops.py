@@ -260,3 +260,48 @@ def lcn_backward(data, lcn, std, g_lcn, g_std, radius, eps):
         _lib.check(lib.dis_lcn_backward(_ptr(data), _ptr(g_lcn), _ptr(g_std), _ptr(out), N * C, H, W, int(radius),
                                         float(eps), _stream(data)))
     return out
+
+
+def flow_consistency_dir(depth0, depth1, R0, t0, R1, t1, flow0, flow1, amb0, amb1, K, ray, clamp, primary_depth1,
+                         want_mask, want_orig_mask, want_grad0, want_grad1, fb_scale=0.02):
+    """One direction of the flow-consistency loss.
+    -> (out3 [sum(diff*mask), sum(mask), ratio], mask|None, orig_mask|None, grad_depth0|None, grad_depth1|None)"""
+    depth0, depth1 = _chk(depth0, "depth0"), _chk(depth1, "depth1")
+    flow0, flow1, amb0, amb1 = _chk(flow0, "flow0"), _chk(flow1, "flow1"), _chk(amb0, "amb0"), _chk(amb1, "amb1")
+    bs, C, H, W = depth0.shape
+    if C != 1 or depth1.shape != depth0.shape or tuple(flow0.shape) != (bs, 2, H, W) or flow1.shape != flow0.shape \
+            or amb0.shape != amb1.shape or amb0.shape[0] != bs or tuple(amb0.shape[-2:]) != (H, W):
+        raise ValueError("flow-consistency loss: inconsistent shapes")
+    R0, R1 = _chk(R0, "R0", 3), _chk(R1, "R1", 3)
+    t0, t1 = _chk(t0, "t0", None).reshape(bs, 3), _chk(t1, "t1", None).reshape(bs, 3)
+    K, ray = _chk(K, "K", None).reshape(3, 3), _chk(ray, "ray", None).reshape(H * W, 3)
+    if primary_depth1 is not None:
+        primary_depth1 = _chk(primary_depth1, "primary_depth1")
+    new = lambda: torch.empty_like(depth0)
+    mask = new() if want_mask else None
+    orig = new() if want_orig_mask else None
+    g0 = new() if want_grad0 else None
+    g1 = new() if want_grad1 else None
+    out3 = torch.empty(3, dtype=torch.float32, device=depth0.device)
+    with _on(depth0) as lib:
+        npart = lib.dis_flow_consistency_num_partials(bs, H, W)
+        partials = torch.empty(2 * max(npart, 1), dtype=torch.float32, device=depth0.device)
+        s = _stream(depth0)
+        _lib.check(lib.dis_flow_consistency_forward(_ptr(depth0), _ptr(depth1), _ptr(R0), _ptr(t0), _ptr(R1), _ptr(t1),
+                                                    _ptr(flow0), _ptr(flow1), _ptr(amb0), _ptr(amb1), int(amb0.shape[1]),
+                                                    _ptr(primary_depth1), _ptr(K), _ptr(ray), float(clamp), float(fb_scale),
+                                                    _ptr(mask), _ptr(orig), _ptr(g0), _ptr(g1), _ptr(partials), bs, H, W, s))
+        _lib.check(lib.dis_reduce_pairs(_ptr(partials), npart, _ptr(out3), s))
+    return out3, mask, orig, g0, g1
+
+
+def combine2(a, b, numer, den_a, den_b, eps):
+    """numer * (a / (den_a + eps) + b / (den_b + eps)) with one-element device tensors (no host sync)."""
+    a = a.contiguous()
+    b = b.contiguous() if b is not None else None
+    out = torch.empty_like(a)
+    numer = numer.reshape(1).to(torch.float32).contiguous()
+    with _on(a) as lib:
+        _lib.check(lib.dis_combine2(_ptr(a), _ptr(b), _ptr(out), a.numel(), _ptr(numer), _ptr(den_a), _ptr(den_b),
+                                    float(eps), _stream(a)))
+    return out

@@ -26,6 +26,13 @@ int sobel_backward(const float*, float*, int, int, int, int, cudaStream_t);
 int flow_warp_forward(const float*, const float*, float*, float*, int32_t*, int32_t*, int, int, int, int, cudaStream_t);
 int flow_warp_backward(const float*, const float*, const float*, float*, float*, int, int, int, int, cudaStream_t);
 
+int flow_consistency_blocks_per_frame(int, int);
+int flow_consistency_forward(const float*, const float*, const float*, const float*, const float*, const float*,
+                             const float*, const float*, const float*, const float*, int, const float*, const float*,
+                             const float*, float, float, float*, float*, float*, float*, float*, int, int, int,
+                             cudaStream_t);
+int combine2(const float*, const float*, float*, size_t, const float*, const float*, const float*, float, cudaStream_t);
+
 namespace {
 
 constexpr int MAX_GRID_Z = 65535;
@@ -324,6 +331,33 @@ int dis_flow_warp_backward(const float* x, const float* flow, const float* grad_
   if (N < 0 || C < 1 || H < 2 || W < 2) return DIS_ERR_BAD_SHAPE;
   if (N == 0) return DIS_OK;
   return flow_warp_backward(x, flow, grad_out, grad_x, grad_flow, N, C, H, W, as_stream(stream));
+}
+
+int dis_flow_consistency_num_partials(int bs, int H, int W) {
+  if (bs < 0 || H < 2 || W < 2) return DIS_ERR_BAD_SHAPE;
+  return bs * flow_consistency_blocks_per_frame(H, W);
+}
+
+int dis_flow_consistency_forward(const float* depth0, const float* depth1, const float* R0, const float* t0,
+                                 const float* R1, const float* t1, const float* flow0, const float* flow1,
+                                 const float* amb0, const float* amb1, int amb_channels, const float* primary_depth1,
+                                 const float* K, const float* ray, float clamp, float fb_scale, float* loss_mask,
+                                 float* orig_mask, float* grad_depth0, float* grad_depth1, float* partials, int bs,
+                                 int H, int W, void* stream) {
+  if (!depth0 || !depth1 || !R0 || !t0 || !R1 || !t1 || !flow0 || !flow1 || !amb0 || !amb1 || !K || !ray || !partials)
+    return DIS_ERR_NULL_POINTER;
+  if (bs < 0 || bs > MAX_GRID_Z || H < 2 || W < 2 || amb_channels < 1) return DIS_ERR_BAD_SHAPE;
+  if (bs == 0) return DIS_OK;
+  return flow_consistency_forward(depth0, depth1, R0, t0, R1, t1, flow0, flow1, amb0, amb1, amb_channels,
+                                  primary_depth1, K, ray, clamp, fb_scale, loss_mask, orig_mask, grad_depth0,
+                                  grad_depth1, partials, bs, H, W, as_stream(stream));
+}
+
+int dis_combine2(const float* a, const float* b, float* out, size_t n, const float* numer, const float* den_a,
+                 const float* den_b, float eps, void* stream) {
+  if (!a || !out || !numer || !den_a || (b && !den_b)) return DIS_ERR_NULL_POINTER;
+  if (n == 0) return DIS_OK;
+  return combine2(a, b, out, n, numer, den_a, den_b, eps, as_stream(stream));
 }
 
 }  // extern "C"

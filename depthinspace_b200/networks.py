@@ -258,3 +258,104 @@ class DisparitySmoothLoss(torch.nn.Module):
         return _SmoothLoss.apply(disp, im.contiguous(), self.process_group)
 
     tforward = forward
+
+
+# ----------------------------------------------------------------------------------------------------
+# Flow-consistency (geometric) losses, reference model/networks.py:433-661
+# ----------------------------------------------------------------------------------------------------
+class _FlowConsistency(torch.autograd.Function):
+    """Both directions (0->1 and 1->0) of the loss: two fused launches; gradients w.r.t. depth0 and depth1."""
+
+    @staticmethod
+    def forward(ctx, depth0, depth1, R0, t0, R1, t1, flow0, flow1, amb0, amb1, primary0, primary1, K, ray, clamp,
+                multi_frame):
+        ctx.set_materialize_grads(False)
+        need0, need1 = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        # direction A: frame 0 -> 1 (direct gradient to depth0, scatter to depth1); direction B: the mirror image
+        a3, mask0, orig, gA0, gA1 = _ops.flow_consistency_dir(depth0, depth1, R0, t0, R1, t1, flow0, flow1, amb0, amb1, K,
+                                                              ray, clamp, primary1 if multi_frame else None,
+                                                              True, not multi_frame, need0, need1)
+        b3, mask1, _, gB1, gB0 = _ops.flow_consistency_dir(depth1, depth0, R1, t1, R0, t0, flow1, flow0, amb1, amb0, K,
+                                                           ray, clamp, primary0 if multi_frame else None,
+                                                           True, False, need1, need0)
+        loss = a3[0] / (a3[1] + 1e-8) + b3[0] / (b3[1] + 1e-8)      # (diff*mask).sum() / (mask.sum() + 1e-8), :599, :653
+        ctx.save_for_backward(a3, b3, gA0, gA1, gB0, gB1)
+        if orig is None:
+            orig = depth0.new_empty(0)
+        ctx.mark_non_differentiable(mask0, mask1, orig)
+        return loss, mask0, mask1, orig
+
+    @staticmethod
+    def backward(ctx, g_loss, *_):
+        a3, b3, gA0, gA1, gB0, gB1 = ctx.saved_tensors
+        if g_loss is None:
+            return (None,) * 16
+        g0 = _ops.combine2(gA0, gB0, g_loss, a3[1:2], b3[1:2], 1e-8) if gA0 is not None else None
+        g1 = _ops.combine2(gB1, gA1, g_loss, b3[1:2], a3[1:2], 1e-8) if gB1 is not None else None
+        return (g0, g1) + (None,) * 14
+
+
+class ProjectionBaseLoss(torch.nn.Module):
+    """Holds K and the per-pixel rays [u, v, 1] @ Ki^T (computed in float64, stored float32 like the reference,
+    model/networks.py:437-453)."""
+
+    def __init__(self, K, Ki, im_height, im_width):
+        super().__init__()
+        import numpy as np
+        self.K = K.reshape(3, 3).to(torch.float32)
+        self.im_height, self.im_width = im_height, im_width
+        u, v = np.meshgrid(range(im_width), range(im_height))
+        uv = np.stack((u, v, np.ones_like(u)), axis=2).reshape(-1, 3)
+        self.ray = torch.from_numpy((uv @ Ki.detach().cpu().numpy().T).astype(np.float32))
+
+    def _consts(self, ref):
+        self.K = self.K.to(ref.device)
+        self.ray = self.ray.to(ref.device)
+        return self.K, self.ray
+
+
+class Single_Frame_Flow_Consistency_Loss(ProjectionBaseLoss):
+    """reference model/networks.py:609-661.  Returns (loss, mask0, mask1, orig_mask) like the reference, except that
+    orig_mask ([H,W], first sample) stays a device tensor: the reference's blocking `.to('cpu').numpy()` (:640)
+    stalls the stream for a value the worker never uses (single_frame_worker.py:148)."""
+
+    def __init__(self, *args, clamp=-1):
+        super().__init__(*args)
+        self.clamp = clamp
+
+    def forward(self, depth0, depth1, R0, t0, R1, t1, flow0, flow1, amb0, amb1):
+        K, ray = self._consts(depth0)
+        loss, m0, m1, orig = _FlowConsistency.apply(depth0, depth1, R0, t0, R1, t1, flow0, flow1, amb0, amb1, None, None,
+                                                    K, ray, self.clamp, False)
+        return loss, m0, m1, orig[0, 0]
+
+    tforward = forward
+
+
+class Multi_Frame_Flow_Consistency_Loss(ProjectionBaseLoss):
+    """reference model/networks.py:554-607 (adds the < 1 px reprojection mask from the primary depths)."""
+
+    def __init__(self, *args, clamp=-1):
+        super().__init__(*args)
+        self.clamp = clamp   # stored but unused, as in the reference's fwd (:564-601)
+
+    def forward(self, depth0, depth1, R0, t0, R1, t1, flow0, flow1, amb0, amb1, primary_depth0, primary_depth1):
+        K, ray = self._consts(depth0)
+        loss, _, _, _ = _FlowConsistency.apply(depth0, depth1, R0, t0, R1, t1, flow0, flow1, amb0, amb1,
+                                               primary_depth0.detach(), primary_depth1.detach(), K, ray, -1.0, True)
+        return loss
+
+    tforward = forward
+
+
+class DispToDepth(torch.nn.Module):
+    """reference model/networks.py:311-319 (plain torch: two elementwise ops feeding the fused geometric loss)."""
+
+    def __init__(self, focal_length, baseline):
+        super().__init__()
+        self.baseline_focal_length = baseline * focal_length
+
+    def forward(self, disp):
+        return self.baseline_focal_length / (torch.nn.functional.relu(disp) + 1e-12)
+
+    tforward = forward

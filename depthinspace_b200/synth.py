@@ -114,3 +114,72 @@ def make_flows(n, hw, max_mag=8.0, seed=42, inconsistent=0.05):
     bad = rng.random((n, 1, H, W)) < inconsistent
     f10 = np.where(bad, f10 + rng.normal(0, 3.0, f01.shape).astype(np.float32), f10).astype(np.float32)
     return f01, f10
+
+
+def _rot(rx, ry, rz):
+    cx, sx, cy, sy, cz, sz = np.cos(rx), np.sin(rx), np.cos(ry), np.sin(ry), np.cos(rz), np.sin(rz)
+    Rx = np.array([[1, 0, 0], [0, cx, -sx], [0, sx, cx]])
+    Ry = np.array([[cy, 0, sy], [0, 1, 0], [-sy, 0, cy]])
+    Rz = np.array([[cz, -sz, 0], [sz, cz, 0], [0, 0, 1]])
+    return Rz @ Ry @ Rx
+
+
+def _bilinear_zero(img, x, y):
+    H, W = img.shape
+    x0, y0 = np.floor(x).astype(int), np.floor(y).astype(int)
+    out = np.zeros_like(x, dtype=np.float64)
+    for dy in (0, 1):
+        for dx in (0, 1):
+            xi, yi = x0 + dx, y0 + dy
+            w = (1 - np.abs(x - xi)) * (1 - np.abs(y - yi))
+            ok = (xi >= 0) & (xi < W) & (yi >= 0) & (yi < H)
+            out += np.where(ok, img[np.clip(yi, 0, H - 1), np.clip(xi, 0, W - 1)] * w, 0.0)
+    return out
+
+
+def make_geometry(bs, hw, seed=42, flow_noise=0.15, bump=0.02):
+    """Two views of a slanted plane with small bumps: intrinsics, poses (row-vector convention of the
+    reference: X_world = (X_cam - t) R), per-view depth, optical flow both ways (from the geometry plus
+    noise, a few percent grossly wrong), ambient images related by the flow.  float32 arrays:
+    K [3,3], R0,R1 [bs,3,3], t0,t1 [bs,3], depth0,depth1,amb0,amb1 [bs,1,H,W], flow01,flow10 [bs,2,H,W]."""
+    rng = np.random.default_rng(seed + 101)
+    H, W = hw
+    f = 1.3 * W
+    K = np.array([[f, 0, (W - 1) / 2.0], [0, f, (H - 1) / 2.0], [0, 0, 1]], np.float64)
+    Ki = np.linalg.inv(K)
+    v, u = np.meshgrid(np.arange(H, dtype=np.float64), np.arange(W, dtype=np.float64), indexing="ij")
+    ray = np.stack((u, v, np.ones_like(u)), -1).reshape(-1, 3) @ Ki.T
+    out = {k: [] for k in ("R0", "t0", "R1", "t1", "depth0", "depth1", "flow01", "flow10", "amb0", "amb1")}
+
+    def plane_depth(R, t, n, d):   # n . ((depth ray - t) R) = d
+        return (d + (t @ R) @ n) / ((ray @ R) @ n)
+
+    def project(depth, Ra, ta, Rb, tb):
+        X = ((depth[:, None] * ray - ta) @ Ra) @ Rb.T + tb
+        p = X @ K.T
+        return p[:, 0] / p[:, 2], p[:, 1] / p[:, 2]
+
+    for _ in range(bs):
+        n = np.array([rng.uniform(-0.25, 0.25), rng.uniform(-0.25, 0.25), 1.0])
+        d = rng.uniform(1.2, 2.0)
+        R0, R1 = _rot(*rng.uniform(-0.03, 0.03, 3)), _rot(*rng.uniform(-0.03, 0.03, 3))
+        t0, t1 = rng.uniform(-0.03, 0.03, 3), rng.uniform(-0.03, 0.03, 3)
+        dep0, dep1 = plane_depth(R0, t0, n, d), plane_depth(R1, t1, n, d)
+        u1, v1 = project(dep0, R0, t0, R1, t1)
+        u0, v0 = project(dep1, R1, t1, R0, t0)
+        f01 = np.stack((u1 - u.ravel(), v1 - v.ravel())).reshape(2, H, W)
+        f10 = np.stack((u0 - u.ravel(), v0 - v.ravel())).reshape(2, H, W)
+        f01 += rng.normal(0, flow_noise, f01.shape)
+        f10 += rng.normal(0, flow_noise, f10.shape)
+        bad = rng.random((1, H, W)) < 0.04
+        f01 = np.where(bad, f01 + rng.normal(0, 4.0, f01.shape), f01)
+        a0 = 0.1 + 0.6 * _smooth_field(rng, hw).astype(np.float64)
+        a1 = _bilinear_zero(a0, u + f10[0], v + f10[1]) + rng.normal(0, 0.003, hw)
+        dep0 = dep0.reshape(H, W) + bump * _smooth_field(rng, hw, cells=10)
+        dep1 = dep1.reshape(H, W) + bump * _smooth_field(rng, hw, cells=10)
+        for k, val in (("R0", R0), ("t0", t0), ("R1", R1), ("t1", t1), ("depth0", dep0[None]), ("depth1", dep1[None]),
+                       ("flow01", f01), ("flow10", f10), ("amb0", a0[None]), ("amb1", a1[None])):
+            out[k].append(val)
+    res = {k: np.stack(v).astype(np.float32) for k, v in out.items()}
+    res["K"] = K.astype(np.float32)
+    return res

@@ -141,6 +141,30 @@ DIS_API int dis_flow_warp_backward(const float* x, const float* flow, const floa
                                    float* grad_x, float* grad_flow, int N, int C, int H, int W,
                                    void* stream);
 
+/* ---- a9  flow-consistency (geometric) loss, ONE direction (frame 0 -> frame 1) -------------------------
+ * Single_Frame_Flow_Consistency_Loss.fwd / Multi_Frame_Flow_Consistency_Loss.fwd, model/networks.py:619-655,
+ * 564-601 (+ ProjectionBaseLoss :455-488).  depth*, amb* [bs,C,H,W] (depth C=1), flow* [bs,2,H,W],
+ * R* [bs,3,3], t* [bs,3], K [3,3], ray [H*W,3] (= uv1 @ Ki^T, :446-449), all device fp32.
+ *   primary_depth1  NULL for the single-frame variant; else adds the < 1 px reprojection mask (:591-595)
+ *   clamp           > 0: diff clamped to [0, clamp] (:637-638);  fb_scale 0.02 (:645)
+ *   loss_mask, orig_mask  optional [bs,1,H,W] float 0/1 outputs (:646-651, :640)
+ *   grad_depth0     optional: d sum(diff*mask) / d depth0 (per pixel)
+ *   grad_depth1     optional: d sum(diff*mask) / d depth1 (zero-filled here, then RED.ADD scatter)
+ *   partials        float[2 * dis_flow_consistency_num_partials(bs,H,W)] (sum(diff*mask), sum(mask)) pairs
+ * loss = sum(diff*mask) / (sum(mask) + 1e-8): reduce with dis_reduce_pairs, scale gradients with dis_combine2. */
+DIS_API int dis_flow_consistency_num_partials(int bs, int H, int W);
+DIS_API int dis_flow_consistency_forward(const float* depth0, const float* depth1, const float* R0,
+                                         const float* t0, const float* R1, const float* t1,
+                                         const float* flow0, const float* flow1, const float* amb0,
+                                         const float* amb1, int amb_channels, const float* primary_depth1,
+                                         const float* K, const float* ray, float clamp, float fb_scale,
+                                         float* loss_mask, float* orig_mask, float* grad_depth0,
+                                         float* grad_depth1, float* partials, int bs, int H, int W,
+                                         void* stream);
+/* out = (*numer) * (a / (*den_a + eps) + b / (*den_b + eps)); b, den_b may be NULL. */
+DIS_API int dis_combine2(const float* a, const float* b, float* out, size_t n, const float* numer,
+                         const float* den_a, const float* den_b, float eps, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -192,3 +192,31 @@ def pattern_loss(disp, im, std, pattern, block_size=9, type=3, eps=0.5, want_gra
         # per-frame call normalised by the frame's own den; rescale to the batch-wide den
         g *= (dens / den).reshape(N, 1, 1, 1).astype(g.dtype)
     return dict(val=num / den, num=num, den=den, diff=diff, proj=proj, grad_disp=g)
+
+
+def flow_consistency_dir(depth0, depth1, R0, t0, R1, t1, flow0, flow1, amb0, amb1, K, ray, clamp=-1.0,
+                         primary_depth1=None, fb_scale=0.02, want_grad=True, prec="f32"):
+    """One direction of the flow-consistency loss (model/networks.py:619-655 / 564-601).
+    -> dict(loss, num, den, mask, orig_mask, grad_depth0, grad_depth1)  (gradients of loss = num/(den+1e-8))"""
+    c = lambda a: _c(a, prec)
+    depth0, depth1, R0, t0, R1, t1 = c(depth0), c(depth1), c(R0), c(t0), c(R1), c(t1)
+    flow0, flow1, amb0, amb1, K, ray = c(flow0), c(flow1), c(amb0), c(amb1), c(K), c(ray)
+    pd1 = c(primary_depth1)
+    bs, _, H, W = depth0.shape
+    mask, om = np.empty_like(depth0), np.empty_like(depth0)
+    g0 = np.empty_like(depth0) if want_grad else None
+    g1 = np.empty_like(depth0) if want_grad else None
+    num, den = ctypes.c_double(), ctypes.c_double()
+    _lib(prec).orc_flow_consistency(_p(depth0), _p(depth1), _p(R0), _p(t0), _p(R1), _p(t1), _p(flow0), _p(flow1),
+                                    _p(amb0), _p(amb1), int(amb0.shape[1]), _p(pd1), _p(K), _p(ray),
+                                    _real(prec, clamp), _real(prec, fb_scale), _p(mask), _p(om), _p(g0), _p(g1),
+                                    ctypes.byref(num), ctypes.byref(den), bs, H, W)
+    return dict(loss=num.value / (den.value + 1e-8), num=num.value, den=den.value, mask=mask, orig_mask=om,
+                grad_depth0=g0, grad_depth1=g1)
+
+
+def make_rays(K, H, W):
+    """ray = [u, v, 1] @ Ki^T computed in float64 and rounded to float32 (model/networks.py:443-449)."""
+    u, v = np.meshgrid(range(W), range(H))
+    uv = np.stack((u, v, np.ones_like(u)), axis=2).reshape(-1, 3)
+    return (uv @ np.linalg.inv(np.asarray(K, np.float64)).T).astype(np.float32)

@@ -472,3 +472,105 @@ ORC_API int orc_pattern_loss(const real* disp, const real* im, const real* std_i
   free(dpd);
   return rc;
 }
+
+/* ------------------------------------------------------------------------
+ * Flow-consistency (geometric) loss, one direction.  model/networks.py:619-655 (single frame),
+ * :564-601 (multi frame, adds the reprojection mask), ProjectionBaseLoss :455-488.
+ * Row-vector conventions of the reference: bmm(xyz, R0), bmm(xyz, R1^T), bmm(xyz, K^T).
+ * Outputs: *num = sum(diff*mask), *den = sum(mask); optional mask, orig_mask, and the gradients of
+ * num/(den+1e-8) w.r.t. depth0 (direct) and depth1 (scatter through the bilinear sampling).
+ * ---------------------------------------------------------------------- */
+static void project_view(const real* R0, const real* t0, const real* R1, const real* t1, const real* K,
+                         real depth, const real* ray, real out[3]) {
+  real c0[3], w[3], c1[3];
+  for (int j = 0; j < 3; ++j) c0[j] = depth * ray[j] - t0[j];
+  for (int j = 0; j < 3; ++j) w[j] = c0[0] * R0[j] + c0[1] * R0[3 + j] + c0[2] * R0[6 + j];
+  for (int j = 0; j < 3; ++j) c1[j] = w[0] * R1[3 * j] + w[1] * R1[3 * j + 1] + w[2] * R1[3 * j + 2] + t1[j];
+  for (int j = 0; j < 3; ++j) out[j] = c1[0] * K[3 * j] + c1[1] * K[3 * j + 1] + c1[2] * K[3 * j + 2];
+}
+
+ORC_API void orc_flow_consistency(const real* depth0, const real* depth1, const real* R0, const real* t0,
+                                  const real* R1, const real* t1, const real* flow0, const real* flow1,
+                                  const real* amb0, const real* amb1, int amb_c, const real* primary_depth1,
+                                  const real* K, const real* ray, real clamp, real fb_scale, real* mask_out,
+                                  real* orig_mask, real* grad_depth0, real* grad_depth1, double* num, double* den,
+                                  int bs, int H, int W) {
+  const real invw = sizeof(real) == 4 ? (real)((float)1.0f / (float)(W - 1)) : (real)1 / (real)(W - 1);
+  const real invh = sizeof(real) == 4 ? (real)((float)1.0f / (float)(H - 1)) : (real)1 / (real)(H - 1);
+  const size_t hw = (size_t)H * W;
+  double sn = 0, sd = 0;
+  real* g = (real*)malloc(sizeof(real) * bs * hw);   /* d(diff*mask)/d d1 */
+  for (int n = 0; n < bs; ++n)
+    for (int h = 0; h < H; ++h)
+      for (int w = 0; w < W; ++w) {
+        const size_t pix = (size_t)h * W + w, o = n * hw + pix;
+        bilin_t b;
+        flow_setup(flow0, n, h, w, H, W, invw, invh, &b);
+        real uvd[3];
+        project_view(R0 + 9 * n, t0 + 3 * n, R1 + 9 * n, t1 + 3 * n, K, depth0[o], ray + 3 * pix, uvd);
+        const real depth10 = bilin_sample(depth1 + n * hw, H, W, &b);
+        const real raw = uvd[2] - depth10;
+        real diff = r_abs(raw);
+        const int clamped = clamp > 0 && diff > clamp;
+        if (clamp > 0 && diff > clamp) diff = clamp;
+        if (orig_mask) orig_mask[o] = diff < clamp ? 1 : 0;
+        const real fx = flow0[(n * 2 + 0) * hw + pix], fy = flow0[(n * 2 + 1) * hw + pix];
+        const real f10x = bilin_sample(flow1 + (n * 2 + 0) * hw, H, W, &b);
+        const real f10y = bilin_sample(flow1 + (n * 2 + 1) * hw, H, W, &b);
+        const real sx = fx + f10x, sy = fy + f10y;
+        real m = (sx * sx + sy * sy) < (real)0.5 + fb_scale * ((fx * fx + fy * fy) + (f10x * f10x + f10y * f10y)) ? 1 : 0;
+        real vc = 0;
+        for (int c = 0; c < amb_c; ++c)
+          vc += r_abs(amb0[((size_t)n * amb_c + c) * hw + pix] - bilin_sample(amb1 + ((size_t)n * amb_c + c) * hw, H, W, &b));
+        if (amb_c > 1) vc = vc / (real)amb_c;
+        m *= vc < (real)0.01 ? 1 : 0;
+        if (primary_depth1) {
+          real wu = 0, wv = 0;
+          const int cx[4] = {b.x0, b.x0 + 1, b.x0, b.x0 + 1}, cy[4] = {b.y0, b.y0, b.y0 + 1, b.y0 + 1};
+          const real wg[4] = {b.wnw, b.wne, b.wsw, b.wse};
+          for (int k = 0; k < 4; ++k) {
+            if (!inb(cy[k], cx[k], H, W)) continue;
+            const size_t q = (size_t)cy[k] * W + cx[k];
+            real p3[3];
+            project_view(R1 + 9 * n, t1 + 3 * n, R0 + 9 * n, t0 + 3 * n, K, primary_depth1[n * hw + q], ray + 3 * q, p3);
+            const real dz = (p3[2] > 0 ? p3[2] : 0) + (real)1e-12;
+            wu = r_fma(p3[0] / dz, wg[k], wu);
+            wv = r_fma(p3[1] / dz, wg[k], wv);
+          }
+          const real du = wu - (real)w, dv = wv - (real)h;
+          m *= (du * du + dv * dv) < (real)1 ? 1 : 0;
+        }
+        if (mask_out) mask_out[o] = m;
+        sn += (double)(diff * m);
+        sd += (double)m;
+        g[o] = (clamped ? 0 : sgn(raw)) * m;
+      }
+  *num = sn;
+  *den = sd;
+  if (grad_depth0 || grad_depth1) {
+    const real scale = (real)(1.0 / (sd + 1e-8));
+    if (grad_depth1) memset(grad_depth1, 0, sizeof(real) * bs * hw);
+    for (int n = 0; n < bs; ++n)
+      for (int h = 0; h < H; ++h)
+        for (int w = 0; w < W; ++w) {
+          const size_t pix = (size_t)h * W + w, o = n * hw + pix;
+          if (grad_depth0) {
+            real a[3], z[3] = {0, 0, 0}, b3[3];
+            project_view(R0 + 9 * n, z, R1 + 9 * n, z, K, (real)1, ray + 3 * pix, a);   /* linear part: d d1/d depth0 */
+            (void)b3;
+            grad_depth0[o] = g[o] * a[2] * scale;
+          }
+          if (grad_depth1 && g[o] != 0) {
+            bilin_t b;
+            flow_setup(flow0, n, h, w, H, W, invw, invh, &b);
+            real* gd = grad_depth1 + n * hw;
+            const real v = -g[o] * scale;
+            if (inb(b.y0, b.x0, H, W))         gd[(size_t)b.y0 * W + b.x0] += b.wnw * v;
+            if (inb(b.y0, b.x0 + 1, H, W))     gd[(size_t)b.y0 * W + b.x0 + 1] += b.wne * v;
+            if (inb(b.y0 + 1, b.x0, H, W))     gd[(size_t)(b.y0 + 1) * W + b.x0] += b.wsw * v;
+            if (inb(b.y0 + 1, b.x0 + 1, H, W)) gd[(size_t)(b.y0 + 1) * W + b.x0 + 1] += b.wse * v;
+          }
+        }
+  }
+  free(g);
+}

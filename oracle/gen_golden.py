@@ -135,12 +135,39 @@ def case_flow_warp(ref, rng):
     np.savez_compressed(os.path.join(OUT, "flow_warp.npz"), **out)
 
 
+def case_flow_consistency(ref, rng):
+    hw = (32, 44)
+    g = synth.make_geometry(2, hw, seed=3)
+    out = {k: v for k, v in g.items()}
+    pd0, pd1 = (g["depth0"] + 0.002).astype(np.float32), (g["depth1"] - 0.002).astype(np.float32)
+    out.update(primary_depth0=pd0, primary_depth1=pd1)
+    for dt, suf in ((torch.float32, ""), (torch.float64, "_f64")):
+        K = torch.from_numpy(g["K"].astype(np.float64)).to(dt)
+        Ki = torch.from_numpy(np.linalg.inv(g["K"].astype(np.float64))).to(dt)
+        T = lambda k: torch.from_numpy(g[k]).to(dt)
+        for mf in (False, True):
+            cls = ref.networks.Multi_Frame_Flow_Consistency_Loss if mf else ref.networks.Single_Frame_Flow_Consistency_Loss
+            mod = cls(K, Ki, hw[0], hw[1], clamp=0.1)
+            mod.ray, mod.u, mod.v = mod.ray.to(dt), mod.u.to(dt), mod.v.to(dt)
+            d0, d1 = T("depth0").requires_grad_(True), T("depth1").requires_grad_(True)
+            args = [d0, d1, T("R0"), T("t0"), T("R1"), T("t1"), T("flow01"), T("flow10"), T("amb0"), T("amb1")]
+            key = "mf" if mf else "sf"
+            if mf:
+                loss = mod(*args, torch.from_numpy(pd0).to(dt), torch.from_numpy(pd1).to(dt))
+            else:
+                loss, m0, m1, om = mod(*args)
+                out.update({f"sf_mask0{suf}": _np(m0), f"sf_mask1{suf}": _np(m1), f"sf_orig_mask{suf}": np.asarray(om)})
+            loss.backward()
+            out.update({f"{key}_loss{suf}": _np(loss), f"{key}_grad0{suf}": _np(d0.grad), f"{key}_grad1{suf}": _np(d1.grad)})
+    np.savez_compressed(os.path.join(OUT, "flow_consistency.npz"), **out)
+
+
 def main():
     ref = ref_shim.load()
     os.makedirs(OUT, exist_ok=True)
     torch.manual_seed(42)
     rng = np.random.default_rng(42)
-    for fn in (case_lcn, case_photometric, case_pattern_loss, case_smooth, case_flow_warp):
+    for fn in (case_lcn, case_photometric, case_pattern_loss, case_smooth, case_flow_warp, case_flow_consistency):
         fn(ref, rng)
         print("wrote", fn.__name__)
 

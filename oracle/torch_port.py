@@ -167,3 +167,71 @@ def multi_frame_loss(disp, im_lcn, std, ambient, pattern, chunk=None, primary_di
     if primary_disp is not None:
         vals.append((disp - primary_disp).abs().mean() * 0.1)
     return vals
+
+
+class FlowConsistency:
+    """Restatement of ProjectionBaseLoss + Single/Multi_Frame_Flow_Consistency_Loss
+    (model/networks.py:433-493, 554-661); K, Ki: [3,3] tensors as the workers pass them."""
+
+    def __init__(self, K, Ki, im_height, im_width, clamp=-1, multi_frame=False):
+        import numpy as np
+        self.K = K.view(-1, 3, 3)
+        self.h, self.w, self.clamp, self.multi_frame = im_height, im_width, clamp, multi_frame
+        u, v = np.meshgrid(range(im_width), range(im_height))
+        uv = np.stack((u, v, np.ones_like(u)), axis=2).reshape(-1, 3)
+        self.ray = torch.from_numpy((uv @ Ki.numpy().T).reshape(1, -1, 3).astype(np.float32))
+        self.u = torch.from_numpy(u.astype("float32"))
+        self.v = torch.from_numpy(v.astype("float32"))
+
+    def _to(self, ref):
+        self.ray, self.K = self.ray.to(ref.device, ref.dtype), self.K.to(ref.device, ref.dtype)
+        self.u, self.v = self.u.to(ref.device, ref.dtype), self.v.to(ref.device, ref.dtype)
+
+    def project(self, depth, Ra, ta, Rb, tb):
+        bs = depth.shape[0]
+        xyz = depth.reshape(bs, -1, 1) * self.ray
+        xyz = torch.bmm(xyz - ta.reshape(bs, 1, 3), Ra)
+        xyz = torch.bmm(xyz, Rb.transpose(1, 2)) + tb.reshape(bs, 1, 3)
+        uv = torch.bmm(xyz, self.K.transpose(1, 2).expand(bs, -1, -1))
+        d = uv[:, :, 2:3]
+        return uv[:, :, :2] / (F.relu(d) + 1e-12), d
+
+    def direction(self, depth0, depth1, R0, t0, R1, t1, flow0, flow1, amb0, amb1, primary_depth1=None):
+        self._to(depth0)
+        _, d1 = self.project(depth0, R0, t0, R1, t1)
+        d1 = d1.view(-1, 1, self.h, self.w)
+        grid = flow0.permute(0, 2, 3, 1).clone()
+        grid[..., 0] += self.u
+        grid[..., 1] += self.v
+        grid[..., 0] = 2 * (grid[..., 0] / (self.w - 1) - 0.5)
+        grid[..., 1] = 2 * (grid[..., 1] / (self.h - 1) - 0.5)
+        sample = lambda t: F.grid_sample(t, grid.detach() if not t.requires_grad else grid, padding_mode="zeros", align_corners=True)
+        diff = (d1 - sample(depth1)).abs()
+        orig = None
+        if not self.multi_frame:
+            if self.clamp > 0:
+                diff = torch.clamp(diff, 0, self.clamp)
+            orig = (diff.detach() < self.clamp).float()
+        with torch.no_grad():
+            f10 = sample(flow1.detach())
+            fb = ((flow0 + f10) ** 2).sum(dim=1) < 0.5 + 0.02 * ((flow0 ** 2).sum(dim=1) + (f10 ** 2).sum(dim=1))
+            mask = fb.to(depth0.dtype).unsqueeze(1)
+            mask = mask * ((amb0 - sample(amb1.detach())).abs().mean(dim=1, keepdim=True) < 0.01).to(depth0.dtype)
+            if self.multi_frame:
+                uv0, _ = self.project(primary_depth1.detach(), R1, t1, R0, t0)
+                uv0 = uv0.view(-1, self.h, self.w, 2).permute(0, 3, 1, 2)
+                self_uv = torch.stack([self.u, self.v], dim=0).unsqueeze(0)
+                mask = mask * (((sample(uv0) - self_uv) ** 2).sum(dim=1, keepdim=True) < 1).to(depth0.dtype)
+        return (diff * mask).sum() / (mask.sum() + 1e-8), mask, orig
+
+    def __call__(self, depth0, depth1, R0, t0, R1, t1, flow0, flow1, amb0, amb1, primary_depth0=None, primary_depth1=None):
+        l0, m0, orig = self.direction(depth0, depth1, R0, t0, R1, t1, flow0, flow1, amb0, amb1, primary_depth1)
+        l1, m1, _ = self.direction(depth1, depth0, R1, t1, R0, t0, flow1, flow0, amb1, amb0, primary_depth0)
+        if self.multi_frame:
+            return l0 + l1
+        return l0 + l1, m0, m1, orig[0][0]
+
+
+def disp_to_depth(disp, focal_length, baseline):
+    """DispToDepth, model/networks.py:311-319."""
+    return (baseline * focal_length) / (F.relu(disp) + 1e-12)

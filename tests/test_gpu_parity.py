@@ -516,3 +516,98 @@ def test_multi_frame_loss_assembly_vs_torch_port(mods):
     for a, b in zip(vals, rvals):
         assert_scalar_close(a.item(), b.item(), name="term")
     assert_close(o.grad, r.grad, 5e-5, name="grad", outlier_frac=2e-3)
+
+
+# ----------------------------------------------------------------------------- flow-consistency loss (a9)
+def _geom(bs, hw, seed):
+    g = synth.make_geometry(bs, hw, seed=seed)
+    g["primary_depth0"] = (g["depth0"] + 0.002).astype(np.float32)
+    g["primary_depth1"] = (g["depth1"] - 0.002).astype(np.float32)
+    return g
+
+
+def _fc_oracle(g, mf, prec):
+    ray = c_oracle.make_rays(g["K"], *g["depth0"].shape[-2:])
+    kw = dict(clamp=-1.0 if mf else 0.1, prec=prec)
+    A = c_oracle.flow_consistency_dir(g["depth0"], g["depth1"], g["R0"], g["t0"], g["R1"], g["t1"], g["flow01"], g["flow10"],
+                                      g["amb0"], g["amb1"], g["K"], ray, primary_depth1=g["primary_depth1"] if mf else None, **kw)
+    B = c_oracle.flow_consistency_dir(g["depth1"], g["depth0"], g["R1"], g["t1"], g["R0"], g["t0"], g["flow10"], g["flow01"],
+                                      g["amb1"], g["amb0"], g["K"], ray, primary_depth1=g["primary_depth0"] if mf else None, **kw)
+    return A, B
+
+
+def _fc_module(net, g, mf, hw):
+    K = torch.from_numpy(g["K"].astype(np.float64))
+    Ki = torch.from_numpy(np.linalg.inv(g["K"].astype(np.float64)))
+    cls = net.Multi_Frame_Flow_Consistency_Loss if mf else net.Single_Frame_Flow_Consistency_Loss
+    mod = cls(K, Ki, hw[0], hw[1], clamp=0.1)
+    d0, d1 = dev(g["depth0"]).requires_grad_(True), dev(g["depth1"]).requires_grad_(True)
+    args = [d0, d1] + [dev(g[k]) for k in ("R0", "t0", "R1", "t1", "flow01", "flow10", "amb0", "amb1")]
+    if mf:
+        args += [dev(g["primary_depth0"]), dev(g["primary_depth1"])]
+    return mod, d0, d1, args
+
+
+@pytest.mark.parametrize("mf", [False, True])
+@pytest.mark.parametrize("hw,bs", [((64, 80), 3), ((37, 51), 2), ((256, 216), 2)])
+def test_flow_consistency_vs_oracle(mods, mf, hw, bs):
+    net, _, _ = mods
+    g = _geom(bs, hw, seed=hw[0] + bs)
+    mod, d0, d1, args = _fc_module(net, g, mf, hw)
+    out = mod(*args)
+    loss = out if mf else out[0]
+    (loss * 0.2).backward()
+    A, B = _fc_oracle(g, mf, "f32")
+    assert_scalar_close(loss.item(), A["loss"] + B["loss"], 2e-5, "loss vs fp32 oracle")
+    if not mf:
+        assert np.array_equal(to_np(out[1]), A["mask"]) and np.array_equal(to_np(out[2]), B["mask"]), "masks must be bit-exact"
+        assert np.array_equal(to_np(out[3]), A["orig_mask"][0, 0])
+    assert 0.3 < A["mask"].mean() < 0.98
+    assert_close(d0.grad, 0.2 * (A["grad_depth0"] + B["grad_depth1"]), 2e-5, "grad depth0", outlier_frac=1e-3)
+    assert_close(d1.grad, 0.2 * (A["grad_depth1"] + B["grad_depth0"]), 2e-5, "grad depth1", outlier_frac=1e-3)
+    A64, B64 = _fc_oracle(g, mf, "f64")
+    # fp64 coordinates flip a handful of thresholded mask pixels; the loss moves by their share
+    assert_scalar_close(loss.item(), A64["loss"] + B64["loss"], 2e-3, "loss vs fp64 oracle")
+
+
+@pytest.mark.parametrize("mf", [False, True])
+def test_flow_consistency_vs_torch_cuda_port(mods, mf):
+    """The reference's op sequence run by torch on the GPU (ATen grid_sample; cuDNN's sampler disabled so that the
+    arithmetic is the public one): masks bit-exact, loss and gradients to tolerance."""
+    net, _, _ = mods
+    hw, bs = (128, 108), 3
+    g = _geom(bs, hw, seed=77)
+    mod, d0, d1, args = _fc_module(net, g, mf, hw)
+    out = mod(*args)
+    loss = out if mf else out[0]
+    loss.backward()
+    K = torch.from_numpy(g["K"].astype(np.float64)).float()
+    Ki = torch.from_numpy(np.linalg.inv(g["K"].astype(np.float64))).float()
+    port = torch_port.FlowConsistency(K, Ki, hw[0], hw[1], clamp=0.1, multi_frame=mf)
+    e0, e1 = dev(g["depth0"]).requires_grad_(True), dev(g["depth1"]).requires_grad_(True)
+    with torch.backends.cudnn.flags(enabled=False):
+        rout = port(e0, e1, *args[2:])
+        rloss = rout if mf else rout[0]
+        rloss.backward()
+    assert_scalar_close(loss.item(), rloss.item(), 2e-5, "loss")
+    if not mf:
+        assert float((out[1] != rout[1]).float().mean()) < 2e-4 and float((out[2] != rout[2]).float().mean()) < 2e-4
+        assert float((out[3] != rout[3]).float().mean()) < 2e-4
+    assert_close(d0.grad, e0.grad, 5e-5, "grad depth0", outlier_frac=2e-3)
+    assert_close(d1.grad, e1.grad, 5e-5, "grad depth1", outlier_frac=2e-3)
+
+
+def test_flow_consistency_golden(mods, golden):
+    net, _, _ = mods
+    g = dict(golden("flow_consistency"))
+    hw = g["depth0"].shape[-2:]
+    for mf in (False, True):
+        key = "mf" if mf else "sf"
+        mod, d0, d1, args = _fc_module(net, g, mf, hw)
+        out = mod(*args)
+        loss = out if mf else out[0]
+        loss.backward()
+        assert_scalar_close(loss.item(), float(g[f"{key}_loss"]), 2e-3, key)     # CPU-torch coordinates: a few mask flips
+        if not mf:
+            assert float((to_np(out[1]) != g["sf_mask0"]).mean()) < 5e-3
+        assert_close(d0.grad, g[f"{key}_grad0"], 1e-2, "grad0", outlier_frac=2e-2)

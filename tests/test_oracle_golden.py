@@ -106,3 +106,31 @@ def test_flow_warp(golden):
     f10w = torch_port.flow_warp(torch.from_numpy(g["flow_back"]), torch.from_numpy(g["flow"]))
     m = torch_port.fb_mask(torch.from_numpy(g["flow"]), f10w)
     assert (m.numpy() != g["fb_mask"]).mean() < 1e-3
+
+
+def _fc_dirs(g, mf, prec):
+    ray = c_oracle.make_rays(g["K"], *g["depth0"].shape[-2:])
+    kw = dict(clamp=-1.0 if mf else 0.1, prec=prec)
+    A = c_oracle.flow_consistency_dir(g["depth0"], g["depth1"], g["R0"], g["t0"], g["R1"], g["t1"], g["flow01"], g["flow10"],
+                                      g["amb0"], g["amb1"], g["K"], ray, primary_depth1=g["primary_depth1"] if mf else None, **kw)
+    B = c_oracle.flow_consistency_dir(g["depth1"], g["depth0"], g["R1"], g["t1"], g["R0"], g["t0"], g["flow10"], g["flow01"],
+                                      g["amb1"], g["amb0"], g["K"], ray, primary_depth1=g["primary_depth0"] if mf else None, **kw)
+    return A, B
+
+
+@pytest.mark.parametrize("mf", [False, True])
+def test_flow_consistency(golden, mf):
+    g = golden("flow_consistency")
+    key = "mf" if mf else "sf"
+    A, B = _fc_dirs(g, mf, "f64")
+    assert_scalar_close(A["loss"] + B["loss"], float(g[f"{key}_loss_f64"]), 1e-10)
+    assert_close(A["grad_depth0"] + B["grad_depth1"], g[f"{key}_grad0_f64"], 1e-9, "grad depth0")
+    assert_close(A["grad_depth1"] + B["grad_depth0"], g[f"{key}_grad1_f64"], 1e-9, "grad depth1")
+    if not mf:
+        assert np.array_equal(A["mask"], g["sf_mask0_f64"]) and np.array_equal(B["mask"], g["sf_mask1_f64"])
+        assert np.array_equal(A["orig_mask"][0, 0], g["sf_orig_mask_f64"])
+    A32, B32 = _fc_dirs(g, mf, "f32")
+    # fp32: thresholded masks may flip on a few pixels between the CPU-torch and the CUDA-order arithmetic
+    assert_scalar_close(A32["loss"] + B32["loss"], float(g[f"{key}_loss"]), 1e-3)
+    if not mf:
+        assert (A32["mask"] != g["sf_mask0"]).mean() < 5e-3

@@ -116,3 +116,45 @@ def test_lcn_c_oracle_equals_reference(ref):
         ol, os_ = c_oracle.lcn_forward(x.numpy(), radius, 0.05, "f64")
         assert_close(ol, l, 1e-13)
         assert_close(os_, s, 1e-13)
+
+
+@pytest.mark.parametrize("mf", [False, True])
+def test_flow_consistency_c_oracle_f64_equals_reference_f64(ref, mf):
+    hw = (36, 48)
+    g = synth.make_geometry(2, hw, seed=5)
+    dt = torch.float64
+    K = torch.from_numpy(g["K"].astype(np.float64))
+    Ki = torch.from_numpy(np.linalg.inv(g["K"].astype(np.float64)))
+    cls = ref.networks.Multi_Frame_Flow_Consistency_Loss if mf else ref.networks.Single_Frame_Flow_Consistency_Loss
+    mod = cls(K, Ki, hw[0], hw[1], clamp=0.1)
+    mod.ray, mod.u, mod.v = mod.ray.to(dt), mod.u.to(dt), mod.v.to(dt)
+    T = lambda k: torch.from_numpy(g[k]).to(dt)
+    d0, d1 = T("depth0").requires_grad_(True), T("depth1").requires_grad_(True)
+    args = [d0, d1, T("R0"), T("t0"), T("R1"), T("t1"), T("flow01"), T("flow10"), T("amb0"), T("amb1")]
+    pd0, pd1 = g["depth0"] + 0.001, g["depth1"] - 0.001
+    if mf:
+        loss = mod(*args, torch.from_numpy(pd0).to(dt), torch.from_numpy(pd1).to(dt))
+    else:
+        loss, m0, m1, om = mod(*args)
+    loss.backward()
+    ray = c_oracle.make_rays(g["K"], *hw)
+    kw = dict(clamp=-1.0 if mf else 0.1, prec="f64")
+    A = c_oracle.flow_consistency_dir(g["depth0"], g["depth1"], g["R0"], g["t0"], g["R1"], g["t1"], g["flow01"], g["flow10"],
+                                      g["amb0"], g["amb1"], g["K"], ray, primary_depth1=pd1 if mf else None, **kw)
+    B = c_oracle.flow_consistency_dir(g["depth1"], g["depth0"], g["R1"], g["t1"], g["R0"], g["t0"], g["flow10"], g["flow01"],
+                                      g["amb1"], g["amb0"], g["K"], ray, primary_depth1=pd0 if mf else None, **kw)
+    assert_scalar_close(A["loss"] + B["loss"], loss.item(), 1e-10)
+    assert_close(A["grad_depth0"] + B["grad_depth1"], d0.grad, 1e-9)
+    assert_close(A["grad_depth1"] + B["grad_depth0"], d1.grad, 1e-9)
+    if not mf:
+        assert np.array_equal(A["mask"], m0.numpy()) and np.array_equal(B["mask"], m1.numpy())
+        assert np.array_equal(A["orig_mask"][0, 0], om)
+    # and the torch port is the same op sequence (fp32, CPU): bit-identical
+    f = torch.float32
+    modf = cls(K.float(), Ki.float(), hw[0], hw[1], clamp=0.1)
+    port = torch_port.FlowConsistency(K.float(), Ki.float(), hw[0], hw[1], clamp=0.1, multi_frame=mf)
+    Tf = lambda k: torch.from_numpy(g[k])
+    a32 = [Tf("depth0"), Tf("depth1"), Tf("R0"), Tf("t0"), Tf("R1"), Tf("t1"), Tf("flow01"), Tf("flow10"), Tf("amb0"), Tf("amb1")]
+    extra = [torch.from_numpy(pd0.astype(np.float32)), torch.from_numpy(pd1.astype(np.float32))] if mf else []
+    r, p = modf(*a32, *extra), port(*a32, *extra)
+    assert torch.equal(r if mf else r[0], p if mf else p[0])
