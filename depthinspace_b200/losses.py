@@ -9,7 +9,8 @@ model/worker.py:522).  The geometric (flow-consistency) terms are appended by th
 """
 import torch
 
-from .networks import DisparitySmoothLoss, RectifiedPatternSimilarityLoss
+from .networks import (DisparitySmoothLoss, DispToDepth, Multi_Frame_Flow_Consistency_Loss,
+                       RectifiedPatternSimilarityLoss, Single_Frame_Flow_Consistency_Loss)
 
 
 def _merge(x):
@@ -20,25 +21,54 @@ def _merge(x):
 class _HotPathLoss(torch.nn.Module):
     smooth_weight = None
 
+    ge_class = None
+
     def __init__(self, im_height, im_width, pattern, loss_type='census_sad', loss_eps=0.5, block_size=9,
-                 process_group=None):
+                 process_group=None, K=None, Ki=None, focal_length=None, baseline=None, ge_clamp=0.1):
         super().__init__()
         self.ph_loss = RectifiedPatternSimilarityLoss(im_height, im_width, pattern, loss_type, loss_eps,
                                                       block_size=block_size, return_pattern_proj=False,
                                                       process_group=process_group)
         self.disparity_loss = DisparitySmoothLoss(process_group=process_group)
+        # geometric (flow-consistency) terms are optional: they need the intrinsics and the stereo baseline
+        self.ge_loss = self.ge_class(K, Ki, im_height, im_width, clamp=ge_clamp) if K is not None else None
+        self.d2d = DispToDepth(float(focal_length), float(baseline)) if focal_length is not None else None
+
+    def _geometric_terms(self, disp_tl, R, t, amb, flow_out, primary_disp=None):
+        """The pair loop of the workers (single_frame_worker.py:127-149, multi_frame_worker.py:128-157):
+        every unordered frame pair of a track, weight 0.2 / (tl (tl-1) / 2)."""
+        tl = disp_tl.shape[0]
+        depth = self.d2d(disp_tl)
+        primary = self.d2d(primary_disp) if primary_disp is not None else None
+        ge_num = tl * (tl - 1) / 2
+        vals = []
+        for i in range(tl):
+            for j in range(i + 1, tl):
+                args = (depth[i], depth[j], R[i], t[i], R[j], t[j], flow_out[f'flow_{i}{j}'], flow_out[f'flow_{j}{i}'],
+                        amb[i], amb[j])
+                if primary is not None:
+                    val = self.ge_loss(*args, primary[i], primary[j])
+                else:
+                    val = self.ge_loss(*args)[0]
+                vals.append(val * 0.2 / ge_num)
+        return vals
 
 
 class SingleFrameLoss(_HotPathLoss):
-    """out: list of per-scale disparities (all full resolution, model/networks.py:290-295)."""
+    """out: list of per-scale disparities (all full resolution, model/networks.py:290-295).
+    With R, t ([tl,bs,3,3], [tl,bs,3]) and flow_out ({'flow_ij': [bs,2,H,W]}) the 6 x 2 geometric terms are added
+    in the reference's position (after smoothness, before the pseudo-GT terms); `out` must then be [tl,bs,1,H,W]."""
+    ge_class = Single_Frame_Flow_Consistency_Loss
 
-    def forward(self, out, im_lcn, std, ambient, pseudo_gt=None):
+    def forward(self, out, im_lcn, std, ambient, pseudo_gt=None, R=None, t=None, flow_out=None):
         if not isinstance(out, (tuple, list)):
             out = [out]
         im, std, amb = _merge(im_lcn)[:, 0:1], _merge(std), _merge(ambient)
         ph = self.ph_loss.forward_multi([_merge(o) for o in out], im, std)   # :108-115, all scales fused
         vals = [v / (2 ** s) for s, v in enumerate(ph)]
         vals.append(self.disparity_loss(_merge(out[0]), amb) * 0.4)   # :118-124 (scale 0 only)
+        if flow_out is not None:                                      # :127-149
+            vals += self._geometric_terms(out[0], R, t, ambient, flow_out)
         if pseudo_gt is not None:                                     # :152-155 (DIS-FTSF)
             for s, o in enumerate(out):
                 vals.append(torch.mean(torch.abs(o - pseudo_gt)) * 0.1 / (2 ** s))
@@ -46,13 +76,17 @@ class SingleFrameLoss(_HotPathLoss):
 
 
 class MultiFrameLoss(_HotPathLoss):
-    def forward(self, out, im_lcn, std, ambient, primary_disp=None):
+    ge_class = Multi_Frame_Flow_Consistency_Loss
+
+    def forward(self, out, im_lcn, std, ambient, primary_disp=None, R=None, t=None, flow_out=None, warmup=True):
         if not isinstance(out, (tuple, list)):
             out = [out]
         im, std, amb = _merge(im_lcn)[:, 0:1], _merge(std), _merge(ambient)
         ph = self.ph_loss.forward_multi([_merge(o) for o in out], im, std)   # :110-117
         vals = [v / (2 ** s) for s, v in enumerate(ph)]
         vals.append(self.disparity_loss(_merge(out[0]), amb) * 0.8)   # :120-126
-        if primary_disp is not None:                                  # :160-165 (first two epochs)
+        if flow_out is not None:                                      # :128-157 (needs primary_disp)
+            vals += self._geometric_terms(out[0], R, t, ambient, flow_out, primary_disp=primary_disp)
+        if primary_disp is not None and warmup:                       # :160-165 (first two epochs)
             vals.append(torch.mean(torch.abs(out[0] - primary_disp)) * 0.1)
         return vals

@@ -39,3 +39,24 @@ def warp_with_fb_mask(flow_back, flow_fwd):
     with torch.no_grad():
         out, mask, _, _ = _ops.flow_warp_forward(flow_back, flow_fwd, want_fb_mask=True)
     return out, mask
+
+
+def gather_warped(x, flow, tidx, with_fb_mask=False):
+    """Stack [x[tidx], warp(x[j], flow_{tidx,j}) for j != tidx] -> [tl, bs, C, h, w]: the gather step of
+    FuseNet.gather_warped_xyz (reference :187-214) and Block2D3D.gather_warped_feat (:347-360).
+    x: [tl, bs, C, h, w]; flow: {'flow_ij': [bs, 2, h, w]} at the resolution of x.
+    with_fb_mask additionally returns the float masks [tl, bs, 1, h, w] (ones for the own frame, the
+    forward-backward consistency mask of :202-209 for the others)."""
+    tl = x.shape[0]
+    warped, masks = [x[tidx]], []
+    if with_fb_mask:
+        masks.append(torch.ones_like(x[tidx][:, :1]))
+    for j in range(tl):
+        if j == tidx:
+            continue
+        f = flow[f'flow_{tidx}{j}']
+        warped.append(warp(x[j].contiguous(), f))
+        if with_fb_mask:
+            masks.append(warp_with_fb_mask(flow[f'flow_{j}{tidx}'], f)[1])
+    out = torch.stack(warped, dim=0)
+    return (out, torch.stack(masks, dim=0)) if with_fb_mask else out

@@ -611,3 +611,65 @@ def test_flow_consistency_golden(mods, golden):
         if not mf:
             assert float((to_np(out[1]) != g["sf_mask0"]).mean()) < 5e-3
         assert_close(d0.grad, g[f"{key}_grad0"], 1e-2, "grad0", outlier_frac=2e-2)
+
+
+def test_full_single_frame_assembly_with_geometric_terms(mods):
+    """Whole loss_forward of the single-frame worker (photometric x4, smoothness, 6 geometric pairs) on a 4-frame
+    track, against the torch port run in fp32 on the GPU."""
+    from depthinspace_b200 import losses
+    hw, tl, bs = (64, 80), 4, 2
+    d, im_l, im_s, pat = _frames(tl * bs, hw, "default", seed=21, scales=4)
+    rng = np.random.default_rng(3)
+    disps = [(p + 0.2 * rng.standard_normal(p.shape)).astype(np.float32) for p in d["disp_pred"]]
+    view = lambda a: dev(a).view(tl, bs, *a.shape[1:])
+    geo = [[None] * tl for _ in range(tl)]
+    g0 = synth.make_geometry(tl * bs, hw, seed=9)
+    K, Ki = torch.from_numpy(g0["K"].astype(np.float64)), torch.from_numpy(np.linalg.inv(g0["K"].astype(np.float64)))
+    R, t = view(g0["R0"]), view(g0["t0"])
+    flow_out = {}
+    for i in range(tl):
+        for j in range(tl):
+            if i != j:
+                f01, _ = synth.make_flows(bs, hw, max_mag=1.5, seed=10 * i + j)
+                flow_out[f"flow_{i}{j}"] = dev(f01)
+    loss = losses.SingleFrameLoss(hw[0], hw[1], dev(np.repeat(pat, 3, axis=1)), K=K, Ki=Ki, focal_length=float(g0["K"][0, 0]), baseline=0.075)
+    outs = [view(p).requires_grad_(True) for p in disps]
+    amb = view(d["ambient"])
+    vals = loss(outs, view(im_l), view(im_s), amb, R=R, t=t, flow_out=flow_out)
+    assert len(vals) == 4 + 1 + 6
+    sum(vals).backward()
+    # reference composition with the torch port
+    refs = [view(p).clone().requires_grad_(True) for p in disps]
+    port = torch_port.FlowConsistency(K.float(), Ki.float(), hw[0], hw[1], clamp=0.1)
+    with torch.backends.cudnn.flags(enabled=False):
+        rv = torch_port.single_frame_loss([r.view(-1, 1, *hw) for r in refs], dev(im_l), dev(im_s), dev(d["ambient"]), loss.ph_loss.pattern, chunk=2)
+        depth = torch_port.disp_to_depth(refs[0], float(g0["K"][0, 0]), 0.075)
+        for i in range(tl):
+            for j in range(i + 1, tl):
+                v = port(depth[i], depth[j], R[i], t[i], R[j], t[j], flow_out[f"flow_{i}{j}"], flow_out[f"flow_{j}{i}"], amb[i], amb[j])[0]
+                rv.append(v * 0.2 / 6)
+        sum(rv).backward()
+    for k, (a, b) in enumerate(zip(vals, rv)):
+        assert_scalar_close(a.item(), b.item(), 5e-5, f"term {k}")
+    for s in range(4):
+        assert_close(outs[s].grad, refs[s].grad, 1e-4, f"grad scale {s}", outlier_frac=5e-3)
+
+
+def test_gather_warped_matches_reference_composition(mods):
+    _, _, mf = mods
+    tl, bs, C, hw = 4, 2, 5, (64, 54)
+    x = torch.randn(tl, bs, C, *hw, device="cuda", requires_grad=True)
+    flow = {f"flow_{i}{j}": dev(synth.make_flows(bs, hw, max_mag=4.0, seed=7 * i + j)[0]) for i in range(tl) for j in range(tl) if i != j}
+    out, masks = mf.gather_warped(x, flow, 1, with_fb_mask=True)
+    assert out.shape == (tl, bs, C, *hw) and masks.shape == (tl, bs, 1, *hw)
+    w = torch.randn_like(out)
+    (out * w).sum().backward()
+    xr = x.detach().clone().requires_grad_(True)
+    with torch.backends.cudnn.flags(enabled=False):
+        ref = [xr[1]] + [torch_port.flow_warp(xr[j], flow[f"flow_1{j}"]) for j in (0, 2, 3)]
+        rmask = [torch.ones(bs, 1, *hw, device="cuda")] + [
+            torch_port.fb_mask(flow[f"flow_1{j}"], torch_port.flow_warp(flow[f"flow_{j}1"], flow[f"flow_1{j}"])) for j in (0, 2, 3)]
+        ref = torch.stack(ref)
+        (ref * w).sum().backward()
+    assert torch.equal(out, ref) and torch.equal(masks, torch.stack(rmask))
+    assert_close(x.grad, xr.grad, 2e-6, "grad through the gather")
