@@ -22,7 +22,7 @@ SIGNATURES = {
     "dis_status_string": [_i],
     "dis_last_cuda_error": [],
     "dis_lcn_forward": [_f, _f, _f, _i, _i, _i, _i, _fl, _st],
-    "dis_lcn_backward": [_f, _f, _f, _f, _i, _i, _i, _i, _fl, _st],
+    "dis_lcn_backward": [_f, _f, _f, _f, _f, _f, _f, _i, _i, _i, _i, _fl, _st],
     "dis_photometric_loss_forward": [_f, _f, _f, _i, _i, _i, _i, _i, _i, _fl, _st],
     "dis_photometric_loss_backward": [_f, _f, _f, _f, _i, _i, _i, _i, _i, _i, _fl, _st],
     "dis_pattern_warp_forward": [_f, _f, _f, _f, _f, _f, _i, _i, _i, _st],
@@ -45,7 +45,7 @@ SIGNATURES = {
     "dis_combine2": [_f, _f, _f, _sz, _f, _f, _f, _fl, _st],
 }
 _RESTYPE = {"dis_status_string": _c.c_char_p, "dis_last_cuda_error": _c.c_char_p}
-OPTIONAL = {"dis_lcn_backward"}  # declared in later ABI revisions
+OPTIONAL = set()
 
 _lib = None
 

@@ -246,19 +246,17 @@ def flow_warp_backward(x, flow, grad_out, want_x=True, want_flow=False):
 
 
 def lcn_backward(data, lcn, std, g_lcn, g_std, radius, eps):
-    lib = _lib.load()
-    if not hasattr(lib, "dis_lcn_backward"):
-        raise NotImplementedError(
-            "LCN backward: the reference never differentiates through LCN (its inputs are data, "
-            "model/worker.py:430-445); this ABI revision ships the forward only")
-    data = _chk(data, "data")
+    data, lcn, std = _chk(data, "data"), _chk(lcn, "lcn"), _chk(std, "std")
     N, C, H, W = data.shape
-    g_lcn = torch.zeros_like(data) if g_lcn is None else _chk(g_lcn, "g_lcn")
-    g_std = torch.zeros_like(data) if g_std is None else _chk(g_std, "g_std")
+    g_lcn = _chk(g_lcn, "g_lcn") if g_lcn is not None else None
+    g_std = _chk(g_std, "g_std") if g_std is not None else None
+    if g_lcn is None and g_std is None:
+        return torch.zeros_like(data)
     out = torch.empty_like(data)
+    work = torch.empty(2 * data.numel(), dtype=torch.float32, device=data.device)
     with _on(data) as lib:
-        _lib.check(lib.dis_lcn_backward(_ptr(data), _ptr(g_lcn), _ptr(g_std), _ptr(out), N * C, H, W, int(radius),
-                                        float(eps), _stream(data)))
+        _lib.check(lib.dis_lcn_backward(_ptr(data), _ptr(lcn), _ptr(std), _ptr(g_lcn), _ptr(g_std), _ptr(out), _ptr(work),
+                                        N * C, H, W, int(radius), float(eps), _stream(data)), launches=2)
     return out
 
 

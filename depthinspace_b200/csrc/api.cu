@@ -15,6 +15,8 @@ void set_last_cuda_error(cudaError_t e) {
 
 // defined in lcn.cu / misc.cu / smooth.cu / flow_warp.cu
 int lcn_forward(const float*, float*, float*, int, int, int, int, float, int, cudaStream_t);
+int lcn_backward(const float*, const float*, const float*, const float*, const float*, float*, float*, int, int, int,
+                 int, float, cudaStream_t);
 int pattern_warp_forward(const float*, const float*, float*, float*, int32_t*, int32_t*, int, int, int, cudaStream_t);
 int reduce_pairs(const float*, int, int, float*, cudaStream_t);
 int scale_by_device_scalar(const float*, float*, size_t, const float*, const float*, cudaStream_t);
@@ -132,6 +134,14 @@ int dis_lcn_forward(const float* x, float* lcn, float* std_out, int N, int H, in
       return rc;
   }
   return DIS_OK;
+}
+
+int dis_lcn_backward(const float* x, const float* lcn, const float* std_in, const float* g_lcn, const float* g_std,
+                     float* grad_x, float* workspace, int N, int H, int W, int radius, float eps, void* stream) {
+  if (!x || !lcn || !std_in || !grad_x || !workspace || (!g_lcn && !g_std)) return DIS_ERR_NULL_POINTER;
+  if (N < 0 || H < 1 || W < 1 || radius < 1 || radius > 8 || radius >= H || radius >= W) return DIS_ERR_BAD_SHAPE;
+  if (N == 0) return DIS_OK;
+  return lcn_backward(x, lcn, std_in, g_lcn, g_std, grad_x, workspace, N, H, W, radius, eps, as_stream(stream));
 }
 
 int dis_photometric_loss_forward(const float* es, const float* ta, float* out, int N, int C, int H, int W,

@@ -42,6 +42,7 @@ class LCN(torch.nn.Module):
 class _LCNFunction(torch.autograd.Function):
     @staticmethod
     def forward(ctx, data, radius, eps):
+        ctx.set_materialize_grads(False)
         lcn, std = _ops.lcn_forward(data, radius, eps)
         ctx.save_for_backward(data, lcn, std)
         ctx.radius, ctx.eps = radius, eps

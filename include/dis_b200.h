@@ -59,6 +59,13 @@ DIS_API const char* dis_last_cuda_error(void);
 DIS_API int dis_lcn_forward(const float* x, float* lcn, float* std_out, int N, int H, int W,
                             int radius, float eps, void* stream);
 
+/* Backward of LCN for API completeness (the reference never needs it: LCN inputs are data,
+ * model/worker.py:430-445).  x, lcn, std: forward input/outputs; g_lcn, g_std: upstream gradients (either may
+ * be NULL); workspace: 2*N*H*W floats of scratch. */
+DIS_API int dis_lcn_backward(const float* x, const float* lcn, const float* std_in, const float* g_lcn,
+                             const float* g_std, float* grad_x, float* workspace, int N, int H, int W,
+                             int radius, float eps, void* stream);
+
 /* ---- a4  ext_cuda.photometric_loss_forward / _backward, model/ext_functions.py:124,137 --
  * es, ta [N,C,H,W] -> out [N,1,H,W];  grad_out [N,1,H,W] -> grad_es [N,C,H,W]
  * (gradient w.r.t. es only, model/ext_functions.py:140). */

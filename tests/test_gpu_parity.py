@@ -673,3 +673,26 @@ def test_gather_warped_matches_reference_composition(mods):
         (ref * w).sum().backward()
     assert torch.equal(out, ref) and torch.equal(masks, torch.stack(rmask))
     assert_close(x.grad, xr.grad, 2e-6, "grad through the gather")
+
+
+def test_lcn_backward_vs_reference_autograd(mods):
+    """API completeness: gradient through LCN (both outputs) against autograd of the reference formula in fp64."""
+    net, _, _ = mods
+    for hw, radius in (((40, 52), 5), ((17, 23), 3), ((64, 64), 2)):
+        x = synth.make_frames(2, hw, "kinect", seed=radius)["im"]
+        xt = dev(x).requires_grad_(True)
+        lcn, std = net.LCN(radius, 0.05)(xt)
+        wl, ws = torch.randn_like(lcn), torch.randn_like(std)
+        ((lcn * wl).sum() + (std * ws).sum()).backward()
+        xr = dev(x).double().requires_grad_(True)
+        rl, rs = torch_port.lcn(xr, radius, 0.05)
+        ((rl * wl.double()).sum() + (rs * ws.double()).sum()).backward()
+        assert_close(xt.grad, xr.grad, 2e-4, f"lcn backward r={radius}")   # mu, sqrt(var) are recovered from fp32 outputs
+        # only one of the two outputs used
+        xt.grad = None
+        lcn, std = net.LCN(radius, 0.05)(xt)
+        (lcn * wl).sum().backward()
+        xr.grad = None
+        rl, _ = torch_port.lcn(xr, radius, 0.05)
+        (rl * wl.double()).sum().backward()
+        assert_close(xt.grad, xr.grad, 2e-4, "lcn backward, lcn output only")
