@@ -65,7 +65,7 @@ class ClockSampler:
     def __enter__(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "--query-gpu=" + ",".join(self.FIELDS),
-                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -203,20 +203,26 @@ def run_ours(args):
             dist.barrier()
             torch.cuda.synchronize()
 
-    for _ in range(args.warmup):
-        step(im, amb, disps)
-    sync_all()
-
-    # ---- device-resident timing (value) ----
-    l0 = _lib.LAUNCHES
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    # the clock sampler covers warm-up + timed region (the GPU is under the same load throughout), so that
+    # even a short timed region gets several 100 ms samples
     with ClockSampler(local_rank) as clocks:
+        for _ in range(args.warmup):
+            step(im, amb, disps)
         sync_all()
+
+        # ---- device-resident timing (value) ----
+        l0 = _lib.LAUNCHES
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ev0.record()
         for _ in range(args.steps):
             total = step(im, amb, disps)
         ev1.record()
         sync_all()
+        if ev0.elapsed_time(ev1) < 400.0:      # keep the load on until nvidia-smi has reported at least a few samples
+            t_end = time.perf_counter() + 0.5
+            while time.perf_counter() < t_end:
+                step(im, amb, disps)
+            torch.cuda.synchronize()
     ms = ev0.elapsed_time(ev1)
     launches = _lib.LAUNCHES - l0
     loss_value = float(total.detach())

@@ -696,3 +696,42 @@ def test_lcn_backward_vs_reference_autograd(mods):
         rl, _ = torch_port.lcn(xr, radius, 0.05)
         (rl * wl.double()).sum().backward()
         assert_close(xt.grad, xr.grad, 2e-4, "lcn backward, lcn output only")
+
+
+# ----------------------------------------------------------------------------- BASELINE.json configs as parity cases
+@pytest.mark.parametrize("kind,k", [("real", 5), ("real", 7), ("real", 11), ("real", 13), ("kinect", 9)])
+def test_config_sweep_dataset_shape_real_and_kinect_patterns(mods, kind, k):
+    """configs[3]/[4]: kinect / real dot patterns at the dataset's 512x432 frame shape, window sweep, against the
+    reference's op sequence run by torch on the GPU (fp32)."""
+    net, _, _ = mods
+    hw = synth.DATASET_HW
+    d, im_l, im_s, pat = _frames(2, hw, kind, seed=k, scales=1, max_disp=128 if k < 13 else 64)
+    mod = net.RectifiedPatternSimilarityLoss(hw[0], hw[1], dev(np.repeat(pat, 3, axis=1)), block_size=k, return_pattern_proj=False)
+    dd = dev(d["disp_pred"][0]).requires_grad_(True)
+    val, _ = mod(dd, dev(im_l), dev(im_s))
+    val.backward()
+    dt = dev(d["disp_pred"][0]).requires_grad_(True)
+    rval, _ = torch_port.pattern_loss(dt, dev(im_l), dev(im_s), mod.pattern, block_size=k, chunk=1)
+    rval.backward()
+    assert_scalar_close(val.item(), rval.item(), name=f"{kind} k={k}")
+    assert_close(dd.grad, dt.grad, 2e-5, name="grad", outlier_frac=2e-4)
+
+
+def test_config_dis_ftsf_pseudo_gt_kinect(mods):
+    """configs[3]: DIS-FTSF = single-frame loss + pseudo-GT L1 terms (single_frame_worker.py:152-155), kinect pattern."""
+    from depthinspace_b200 import losses
+    hw = (128, 108)
+    d, im_l, im_s, pat = _frames(4, hw, "kinect", seed=31, scales=4)
+    loss = losses.SingleFrameLoss(hw[0], hw[1], dev(np.repeat(pat, 3, axis=1)))
+    outs = [dev(p).requires_grad_(True) for p in d["disp_pred"]]
+    pgt = dev((d["disp_gt"] + 0.25).astype(np.float32))
+    vals = loss(outs, dev(im_l), dev(im_s), dev(d["ambient"]), pseudo_gt=pgt)
+    sum(vals).backward()
+    refs = [dev(p).requires_grad_(True) for p in d["disp_pred"]]
+    rvals = torch_port.single_frame_loss(refs, dev(im_l), dev(im_s), dev(d["ambient"]), loss.ph_loss.pattern, pseudo_gt=pgt)
+    sum(rvals).backward()
+    assert len(vals) == len(rvals) == 9
+    for a, b in zip(vals, rvals):
+        assert_scalar_close(a.item(), b.item(), 2e-5)
+    for a, b in zip(outs, refs):
+        assert_close(a.grad, b.grad, 5e-5, outlier_frac=2e-3)
