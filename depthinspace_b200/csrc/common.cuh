@@ -157,45 +157,47 @@ __device__ __forceinline__ float pattern_warp_pixel(const float* __restrict__ pa
 // disparity map sampled at the same pixel, corner fetches are branch-free (clamped address, value
 // forced to 0 when ATen's within_bounds_2d() fails: fma(0, w, acc) == acc, i.e. "corner skipped").
 struct WarpRow {
-  const float* row0;   // pattern row y0 (clamped so that the address is always valid)
-  const float* row1;   // pattern row y0 + 1 (clamped)
+  int off0, off1;      // element offsets of pattern rows y0 and y0+1 (clamped so that the address is always valid)
   float wy0, wy1;      // (y0 + 1) - iy, iy - y0
-  bool by0, by1;       // rows inside the image
+  int by;              // bit 0: row y0 inside the image, bit 1: row y0+1 inside
 };
 
+// Branch-free border clip.  Forward semantics of ATen's clip_coordinates (min/max, so NaN clips to 0) and the
+// gradient mask of clip_coordinates_set_grad (zero on and outside the border).
 __device__ __forceinline__ float border_source_index(float g, int size, float& mult) {
-  float c = unnormalize_coord(g, size);
-  mult = (float)(size - 1) * 0.5f;
-  if (c <= 0.0f) { c = 0.0f; mult = 0.0f; }
-  else if (c >= (float)(size - 1)) { c = (float)(size - 1); mult = 0.0f; }
-  return (c != c) ? -100.0f : c;  // after clipping only NaN can fail safe_downgrade_to_int_range
+  const float c = unnormalize_coord(g, size);
+  const float hi = (float)(size - 1);
+  mult = (c > 0.0f && c < hi) ? hi * 0.5f : 0.0f;
+  return fminf(fmaxf(c, 0.0f), hi);
 }
 
-__device__ __forceinline__ WarpRow warp_row_setup(const float* __restrict__ pattern, int h, int H, int W, float inv_h) {
+__device__ __forceinline__ WarpRow warp_row_setup(int h, int H, int W, float inv_h) {
   float unused;
   const float iy = border_source_index(normalize_coord((float)h, inv_h), H, unused);
   const int y0 = (int)floorf(iy);
   WarpRow r;
   r.wy0 = fsub((float)(y0 + 1), iy);
   r.wy1 = fsub(iy, (float)y0);
-  r.by0 = (unsigned)y0 < (unsigned)H;
-  r.by1 = (unsigned)(y0 + 1) < (unsigned)H;
-  r.row0 = pattern + (size_t)clampi(y0, 0, H - 1) * W;
-  r.row1 = pattern + (size_t)clampi(y0 + 1, 0, H - 1) * W;
+  r.by = ((unsigned)y0 < (unsigned)H ? 1 : 0) | ((unsigned)(y0 + 1) < (unsigned)H ? 2 : 0);
+  r.off0 = clampi(y0, 0, H - 1) * W;
+  r.off1 = clampi(y0 + 1, 0, H - 1) * W;
   return r;
 }
 
 // value of the warped pattern; *dproj (optional) = d value / d disp
-__device__ __forceinline__ float warp_col_sample(const WarpRow& r, float disp, int w, int W, float inv_w, float* dproj) {
+__device__ __forceinline__ float warp_col_sample(const float* __restrict__ pattern, const WarpRow& r, float disp, int w,
+                                                 int W, float inv_w, float* dproj) {
   float mult;
   const float ix = border_source_index(normalize_coord(fsub((float)w, disp), inv_w), W, mult);
   const int x0 = (int)floorf(ix);
   const float wx0 = fsub((float)(x0 + 1), ix), wx1 = fsub(ix, (float)x0);
   const bool bx0 = (unsigned)x0 < (unsigned)W, bx1 = (unsigned)(x0 + 1) < (unsigned)W;
   const int c0 = clampi(x0, 0, W - 1), c1 = clampi(x0 + 1, 0, W - 1);
-  const float l00 = __ldg(r.row0 + c0), l01 = __ldg(r.row0 + c1), l10 = __ldg(r.row1 + c0), l11 = __ldg(r.row1 + c1);
-  const float vnw = (r.by0 && bx0) ? l00 : 0.0f, vne = (r.by0 && bx1) ? l01 : 0.0f;
-  const float vsw = (r.by1 && bx0) ? l10 : 0.0f, vse = (r.by1 && bx1) ? l11 : 0.0f;
+  const float l00 = __ldg(pattern + r.off0 + c0), l01 = __ldg(pattern + r.off0 + c1);
+  const float l10 = __ldg(pattern + r.off1 + c0), l11 = __ldg(pattern + r.off1 + c1);
+  const bool by0 = r.by & 1, by1 = r.by & 2;
+  const float vnw = (by0 && bx0) ? l00 : 0.0f, vne = (by0 && bx1) ? l01 : 0.0f;
+  const float vsw = (by1 && bx0) ? l10 : 0.0f, vse = (by1 && bx1) ? l11 : 0.0f;
   float acc = __fmaf_rn(vnw, fmul(wx0, r.wy0), 0.0f);
   acc = __fmaf_rn(vne, fmul(wx1, r.wy0), acc);
   acc = __fmaf_rn(vsw, fmul(wx0, r.wy1), acc);

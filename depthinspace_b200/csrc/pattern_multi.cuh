@@ -60,7 +60,8 @@ struct PatternMultiArgs {
 template <int R, int NPAIR>
 constexpr size_t pattern_multi_smem_bytes() {
   using G = MultiGeom<R>;
-  return sizeof(float) * ((size_t)2 * NPAIR * G::PLANE + 2 * G::PLANE + 2 * NPAIR * MTH * MTW + 2 * NPAIR * MFIX + 64);
+  return sizeof(float) * ((size_t)2 * NPAIR * G::PLANE + 2 * G::PLANE + 2 * NPAIR * MTH * MTW + 2 * NPAIR * MFIX + 64) +
+         sizeof(WarpRow) * G::ROWS;
 }
 
 // exact backward accumulator of one border-line pixel for scale s (same maths as window.cuh border_pixel_gacc)
@@ -99,10 +100,18 @@ __global__ void __launch_bounds__(256, 2) pattern_multi_kernel(PatternMultiArgs 
   float* sdd = sw + G::PLANE;                                // [S][MTH][MTW] d proj / d disp of own pixels
   float* fix = sdd + S * MTH * MTW;                          // [S][MFIX]
   float* red = fix + S * MFIX;                               // block-reduction scratch
+  WarpRow* srow = reinterpret_cast<WarpRow*>(red + 64);      // y half of the pattern warp, one entry per tile row
   const int tx = threadIdx.x, ty = threadIdx.y, tid = ty * 32 + tx;
   const int x0 = blockIdx.x * MTW, y0 = blockIdx.y * MTH, n = blockIdx.z;
   const size_t hw = (size_t)a.H * a.W;
   const size_t fo = (size_t)n * hw;
+  if (tid < G::ROWS) srow[tid] = warp_row_setup(clampi(y0 - R + tid, 0, a.H - 1), a.H, a.W, a.inv_h);
+  __syncthreads();
+  const float* dptr[S];
+#pragma unroll
+  for (int s = 0; s < S; ++s) dptr[s] = a.disp[s] + fo;
+  const float* imp = a.im + fo;
+  const float* sdp = a.std_in ? a.std_in + fo : nullptr;
 
   // ---- stage the tile: S pattern warps per position (shared y half), image and sigma once ---------------
   for (int idx = tid; idx < G::ROWS * G::COLS; idx += 256) {
@@ -110,17 +119,17 @@ __global__ void __launch_bounds__(256, 2) pattern_multi_kernel(PatternMultiArgs 
     const int gy = y0 - R + j, gx = x0 - R + i;
     const bool inside = gy >= 0 && gy < a.H && gx >= 0 && gx < a.W;
     const int cy = clampi(gy, 0, a.H - 1), cx = clampi(gx, 0, a.W - 1);
-    const size_t g = fo + (size_t)cy * a.W + cx;
+    const int g = cy * a.W + cx;
     float dv[S];
 #pragma unroll
-    for (int s = 0; s < S; ++s) dv[s] = __ldg(a.disp[s] + g);          // S independent loads in flight
-    const float tv = __ldg(a.im + g);
-    const float wv = inside ? (a.std_in ? __ldg(a.std_in + g) : 1.0f) : 0.0f;
-    const WarpRow row = warp_row_setup(a.pattern, cy, a.H, a.W, a.inv_h);
+    for (int s = 0; s < S; ++s) dv[s] = __ldg(dptr[s] + g);            // S independent loads in flight
+    const float tv = __ldg(imp + g);
+    const float wv = inside ? (sdp ? __ldg(sdp + g) : 1.0f) : 0.0f;
+    const WarpRow row = srow[j];
     const bool own = GRAD && j >= R && j < R + MTH && i >= R && i < R + MTW;
     float ev[S], dd[S];
 #pragma unroll
-    for (int s = 0; s < S; ++s) ev[s] = warp_col_sample(row, dv[s], cx, a.W, a.inv_w, own ? &dd[s] : nullptr);
+    for (int s = 0; s < S; ++s) ev[s] = warp_col_sample(a.pattern, row, dv[s], cx, a.W, a.inv_w, own ? &dd[s] : nullptr);
 #pragma unroll
     for (int p = 0; p < NPAIR; ++p) se[p * G::PLANE + j * G::PITCH + i] = make_float2(ev[2 * p], ev[2 * p + 1]);
     st[j * G::PITCH + i] = tv;

@@ -165,8 +165,8 @@ __global__ void __launch_bounds__(NTHREADS, 2) pattern_loss_kernel(PatternLossAr
     const size_t g = (size_t)cy * a.W + cx;
     const bool own = GRAD && j >= R && j < R + TH && i >= R && i < R + TW;
     float dd = 0.0f;
-    const WarpRow row = warp_row_setup(a.pattern, cy, a.H, a.W, a.inv_h);
-    const float e = warp_col_sample(row, __ldg(disp + g), cx, a.W, a.inv_w, own ? &dd : nullptr);
+    const WarpRow row = warp_row_setup(cy, a.H, a.W, a.inv_h);
+    const float e = warp_col_sample(a.pattern, row, __ldg(disp + g), cx, a.W, a.inv_w, own ? &dd : nullptr);
     se[j * G::PITCH + i] = e;
     st[j * G::PITCH + i] = __ldg(im + g);
     sw[j * G::PITCH + i] = inside ? (sd ? __ldg(sd + g) : 1.0f) : 0.0f;
