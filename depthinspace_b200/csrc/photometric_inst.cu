@@ -2,6 +2,7 @@
 // unrolled without a single multi-minute compile.  build.py compiles R = 0..7 in parallel.
 #include "photometric_kernels.cuh"
 #include "pattern_multi.cuh"
+#include "box_kernels.cuh"
 
 #ifndef DIS_R
 #error "compile with -DDIS_R=<window radius>"
@@ -20,6 +21,36 @@ int prepare(K kernel, size_t smem) {
 }
 
 dim3 tile_grid(int H, int W, int z) { return dim3((W + TW - 1) / TW, (H + TH - 1) / TH, z); }
+
+// mse / sad: separable box filters (HBM-bound)
+template <int TYPE, int R>
+int box_photometric_t(const PhotoArgs& a, bool backward, cudaStream_t s) {
+  const dim3 block(16, 16);
+  if (!backward) {
+    const size_t smem = box_smem_bytes<R>(1, 1, 0);
+    if (int rc = prepare(box_photometric_fwd_kernel<TYPE, R>, smem)) return rc;
+    box_photometric_fwd_kernel<TYPE, R><<<tile_grid(a.H, a.W, a.N), block, smem, s>>>(a);
+  } else {
+    const size_t smem = box_smem_bytes<R>(1, 1, 0);
+    if (int rc = prepare(box_photometric_bwd_kernel<TYPE, R>, smem)) return rc;
+    box_photometric_bwd_kernel<TYPE, R><<<tile_grid(a.H, a.W, a.N), block, smem, s>>>(a);
+  }
+  return check_launch();
+}
+
+template <int TYPE, int R>
+int box_pattern_loss_t(const PatternLossArgs& a, cudaStream_t s) {
+  const dim3 block(16, 16);
+  const size_t smem = box_smem_bytes<R>(2, 2, 2);
+  if (a.grad_num) {
+    if (int rc = prepare(box_pattern_loss_kernel<TYPE, R, true>, smem)) return rc;
+    box_pattern_loss_kernel<TYPE, R, true><<<tile_grid(a.H, a.W, a.N), block, smem, s>>>(a);
+  } else {
+    if (int rc = prepare(box_pattern_loss_kernel<TYPE, R, false>, smem)) return rc;
+    box_pattern_loss_kernel<TYPE, R, false><<<tile_grid(a.H, a.W, a.N), block, smem, s>>>(a);
+  }
+  return check_launch();
+}
 
 template <int TYPE, int R>
 int photometric_t(const PhotoArgs& a, bool backward, cudaStream_t s) {
@@ -77,8 +108,8 @@ int launch_pattern_multi<DIS_R>(const PatternMultiArgs& a, int S, int type, cuda
 template <>
 int launch_photometric<DIS_R>(const PhotoArgs& a, int type, bool backward, cudaStream_t s) {
   switch (type) {
-    case MSE: return photometric_t<MSE, DIS_R>(a, backward, s);
-    case SAD: return photometric_t<SAD, DIS_R>(a, backward, s);
+    case MSE: return box_photometric_t<MSE, DIS_R>(a, backward, s);
+    case SAD: return box_photometric_t<SAD, DIS_R>(a, backward, s);
     case CENSUS_MSE: return photometric_t<CENSUS_MSE, DIS_R>(a, backward, s);
     case CENSUS_SAD: return photometric_t<CENSUS_SAD, DIS_R>(a, backward, s);
   }
@@ -88,8 +119,8 @@ int launch_photometric<DIS_R>(const PhotoArgs& a, int type, bool backward, cudaS
 template <>
 int launch_pattern_loss<DIS_R>(const PatternLossArgs& a, int type, cudaStream_t s) {
   switch (type) {
-    case MSE: return pattern_loss_t<MSE, DIS_R>(a, s);
-    case SAD: return pattern_loss_t<SAD, DIS_R>(a, s);
+    case MSE: return box_pattern_loss_t<MSE, DIS_R>(a, s);
+    case SAD: return box_pattern_loss_t<SAD, DIS_R>(a, s);
     case CENSUS_MSE: return pattern_loss_t<CENSUS_MSE, DIS_R>(a, s);
     case CENSUS_SAD: return pattern_loss_t<CENSUS_SAD, DIS_R>(a, s);
   }
