@@ -22,6 +22,7 @@ SIGNATURES = {
     "dis_status_string": [_i],
     "dis_last_cuda_error": [],
     "dis_lcn_forward": [_f, _f, _f, _i, _i, _i, _i, _fl, _st],
+    "dis_lcn_prepare_input": [_f, _f, _f, _i, _i, _i, _i, _i, _fl, _st],
     "dis_lcn_backward": [_f, _f, _f, _f, _f, _f, _f, _i, _i, _i, _i, _fl, _st],
     "dis_photometric_loss_forward": [_f, _f, _f, _i, _i, _i, _i, _i, _i, _fl, _st],
     "dis_photometric_loss_backward": [_f, _f, _f, _f, _i, _i, _i, _i, _i, _i, _fl, _st],

@@ -64,6 +64,19 @@ def lcn_forward(x, radius, eps):
     return lcn, std
 
 
+def lcn_prepare_input(x, radius, eps):
+    """x [bs,tl,1,H,W] -> (im_cat [tl,bs,2,H,W] = cat(LCN(x), x), std [tl,bs,1,H,W]); Worker.copy_data fused."""
+    x = _chk(x, "im", 5)
+    bs, tl, C, H, W = x.shape
+    if C != 1:
+        raise ValueError("expected [bs, tl, 1, H, W]")
+    im_cat = torch.empty((tl, bs, 2, H, W), dtype=x.dtype, device=x.device)
+    std = torch.empty((tl, bs, 1, H, W), dtype=x.dtype, device=x.device)
+    with _on(x) as lib:
+        _lib.check(lib.dis_lcn_prepare_input(_ptr(x), _ptr(im_cat), _ptr(std), bs, tl, H, W, int(radius), float(eps), _stream(x)))
+    return im_cat, std
+
+
 def photometric_loss_forward(es, ta, block_size, type, eps):
     es, ta = _chk(es, "es"), _chk(ta, "ta")
     if es.shape != ta.shape:

@@ -17,6 +17,7 @@ void set_last_cuda_error(cudaError_t e) {
 int lcn_forward(const float*, float*, float*, int, int, int, int, float, int, cudaStream_t);
 int lcn_backward(const float*, const float*, const float*, const float*, const float*, float*, float*, int, int, int,
                  int, float, cudaStream_t);
+int lcn_forward_ex(const float*, float*, float*, float*, int, int, int, int, float, int, int, int, size_t, cudaStream_t);
 int pattern_warp_forward(const float*, const float*, float*, float*, int32_t*, int32_t*, int, int, int, cudaStream_t);
 int reduce_pairs(const float*, int, int, float*, cudaStream_t);
 int scale_by_device_scalar(const float*, float*, size_t, const float*, const float*, cudaStream_t);
@@ -134,6 +135,19 @@ int dis_lcn_forward(const float* x, float* lcn, float* std_out, int N, int H, in
       return rc;
   }
   return DIS_OK;
+}
+
+int dis_lcn_prepare_input(const float* x, float* im_cat, float* std_out, int bs, int tl, int H, int W, int radius,
+                          float eps, void* stream) {
+  if (!x || !im_cat || !std_out) return DIS_ERR_NULL_POINTER;
+  if (bs < 0 || tl < 1 || H < 1 || W < 1 || radius < 1 || radius > 8 || radius >= H || radius >= W ||
+      (long)bs * tl > MAX_GRID_Z)
+    return DIS_ERR_BAD_SHAPE;
+  if (bs == 0) return DIS_OK;
+  const size_t hw = (size_t)H * W;
+  const int vec_ok = (W % 4 == 0) && aligned16(x, im_cat, std_out);
+  return lcn_forward_ex(x, im_cat, std_out, im_cat + hw, bs * tl, H, W, radius, eps, vec_ok, tl, bs, 2 * hw,
+                        as_stream(stream));
 }
 
 int dis_lcn_backward(const float* x, const float* lcn, const float* std_in, const float* g_lcn, const float* g_std,

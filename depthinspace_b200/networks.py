@@ -38,6 +38,11 @@ class LCN(torch.nn.Module):
 
     tforward = forward
 
+    def prepare_input(self, im):
+        """Worker.copy_data for an image key (reference model/worker.py:418-438), fused into one launch:
+        im [bs,tl,1,H,W] as delivered by the DataLoader -> (im_cat [tl,bs,2,H,W] = cat(LCN(im), im), std [tl,bs,1,H,W])."""
+        return _ops.lcn_prepare_input(im, self.radius, self.epsilon)
+
 
 class _LCNFunction(torch.autograd.Function):
     @staticmethod

@@ -59,6 +59,12 @@ DIS_API const char* dis_last_cuda_error(void);
 DIS_API int dis_lcn_forward(const float* x, float* lcn, float* std_out, int N, int H, int W,
                             int radius, float eps, void* stream);
 
+/* Worker pre-processing step, Worker.copy_data (model/worker.py:418-438), fused: x [bs,tl,1,H,W] as the
+ * DataLoader delivers it -> im_cat [tl,bs,2,H,W] (channel 0 = LCN(x), channel 1 = x) and std [tl,bs,1,H,W];
+ * replaces transpose + contiguous + LCN + torch.cat. */
+DIS_API int dis_lcn_prepare_input(const float* x, float* im_cat, float* std_out, int bs, int tl, int H, int W,
+                                  int radius, float eps, void* stream);
+
 /* Backward of LCN for API completeness (the reference never needs it: LCN inputs are data,
  * model/worker.py:430-445).  x, lcn, std: forward input/outputs; g_lcn, g_std: upstream gradients (either may
  * be NULL); workspace: 2*N*H*W floats of scratch. */

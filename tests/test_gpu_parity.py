@@ -735,3 +735,17 @@ def test_config_dis_ftsf_pseudo_gt_kinect(mods):
         assert_scalar_close(a.item(), b.item(), 2e-5)
     for a, b in zip(outs, refs):
         assert_close(a.grad, b.grad, 5e-5, outlier_frac=2e-3)
+
+
+def test_lcn_prepare_input_matches_copy_data(mods):
+    """§8(f2): transpose bs x tl -> tl x bs, LCN, cat((lcn, raw), dim=2) of Worker.copy_data (model/worker.py:418-438)."""
+    net, _, _ = mods
+    bs, tl, hw = 3, 4, (64, 56)
+    x = synth.make_frames(bs * tl, hw, "default", seed=17)["im"].reshape(bs, tl, 1, *hw)
+    lcn = net.LCN(5, 0.05)
+    im_cat, std = lcn.prepare_input(dev(x))
+    xt = dev(x).transpose(0, 1).contiguous()                      # reference order of operations
+    r_l, r_s = lcn(xt.view(-1, 1, *hw))
+    ref_cat = torch.cat((r_l.view(tl, bs, 1, *hw), xt), dim=2)
+    assert im_cat.shape == (tl, bs, 2, *hw) and std.shape == (tl, bs, 1, *hw)
+    assert torch.equal(im_cat, ref_cat) and torch.equal(std, r_s.view(tl, bs, 1, *hw))
