@@ -43,6 +43,15 @@ ALGO_BYTES_PER_FRAME = 144    # x P, SURVEY.md section 8(d): 12P LCN + 4 x 28P p
 KERNEL_ALGO_BYTES_PER_FRAME = 40  # x P, 4-scale fused pattern-loss kernel: reads 4 disp + im + sigma (24P), writes 4 x d/d disp (16P)
 
 
+def measured_traffic(kernel, frames):
+    """DRAM bytes per launch of the dominant kernel from the committed ncu capture (profiles/traffic.json), or None."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            return int(json.load(f)[kernel]["bytes_per_frame"] * frames)
+    except Exception:
+        return None
+
+
 def measured_peak():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -324,7 +333,9 @@ def run_ours(args):
                     "h2d_bytes_per_step": int((2 + N_SCALES) * 4 * P * n), "d2h_bytes_per_step": 4},
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "kernel": "pattern_multi_kernel<census_sad, R=4, 4 scales, grad>",
+                         "traffic": measured_traffic("pattern_multi_kernel<census_sad, R=4, 4 scales, grad>", n),
+                         "algorithmic_bytes": KERNEL_ALGO_BYTES_PER_FRAME * P * n,
+                         "kernel": "pattern_multi_kernel<census_sad, R=4, 4 scales, grad>",
                          "kernel_ms": kernel_ms, "peak_source": peak_src,
                          "limiter": "XU (rsqrt) + FP32 issue, not HBM: ~100 rsqrt per pixel-scale (see DESIGN.md)",
                          "step_algorithmic_gbs": step_gbs, "step_frac": step_gbs / peak},
