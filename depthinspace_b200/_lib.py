@@ -7,7 +7,7 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libdis_b200.so")
+LIB_PATH = os.environ.get("DIS_B200_LIB") or os.path.join(_HERE, "lib", "libdis_b200.so")  # env override: A/B builds
 
 _c = ctypes
 _f = _c.c_void_p          # device pointer (float* / int32_t*), nullable

@@ -33,6 +33,10 @@ constexpr int MTW = 64, MTH = 32;             // tile (halo re-computation 1.41x
 constexpr int MROWS_PER_PASS = 8;             // 256 threads = 32 (x, 2 px each) x 8 (y); 4 passes cover the tile
 constexpr int MFIX = 2 * MTH + 2 * MTW;       // border-line candidates per tile
 constexpr int MAX_SCALES = 4;
+#ifndef DIS_FILL_UNROLL
+#define DIS_FILL_UNROLL 3
+#endif
+constexpr int kFillUnroll = DIS_FILL_UNROLL;
 
 template <int R>
 struct MultiGeom {
@@ -114,6 +118,8 @@ __global__ void __launch_bounds__(256, 2) pattern_multi_kernel(PatternMultiArgs 
   const float* sdp = a.std_in ? a.std_in + fo : nullptr;
 
   // ---- stage the tile: S pattern warps per position (shared y half), image and sigma once ---------------
+  // (unrolled so that the loads of several positions are in flight together: the phase is latency-bound)
+#pragma unroll kFillUnroll
   for (int idx = tid; idx < G::ROWS * G::COLS; idx += 256) {
     const int j = idx / G::COLS, i = idx - j * G::COLS;
     const int gy = y0 - R + j, gx = x0 - R + i;

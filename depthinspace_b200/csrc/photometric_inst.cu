@@ -1,5 +1,7 @@
 // One translation unit per window radius R = DIS_R (block_size = 2R+1): keeps every k x k loop fully
 // unrolled without a single multi-minute compile.  build.py compiles R = 0..7 in parallel.
+#include <map>
+#include <mutex>
 #include "photometric_kernels.cuh"
 #include "pattern_multi.cuh"
 #include "box_kernels.cuh"
@@ -11,12 +13,24 @@
 namespace dis {
 namespace {
 
+// Opt a kernel in to > 48 KB of dynamic shared memory.  Done once per kernel and process (thread-safe static
+// initialisation), never on the launch path: keeps launches capturable into CUDA graphs.
 template <typename K>
 int prepare(K kernel, size_t smem) {
-  if (smem > 48 * 1024) {
-    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) { set_last_cuda_error(e); return DIS_ERR_CUDA_LAUNCH; }
-  }
+  if (smem <= 48 * 1024) return DIS_OK;
+  struct Once {
+    cudaError_t err;
+    Once(K k, size_t bytes) : err(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes)) {}
+  };
+  static std::map<std::pair<const void*, int>, cudaError_t> done;   // (kernel, device) pairs already opted in
+  static std::mutex mu;
+  int device = 0;
+  cudaGetDevice(&device);
+  std::lock_guard<std::mutex> lock(mu);
+  const std::pair<const void*, int> key(reinterpret_cast<const void*>(kernel), device);
+  auto it = done.find(key);
+  if (it == done.end()) it = done.emplace(key, Once(kernel, smem).err).first;
+  if (it->second != cudaSuccess) { set_last_cuda_error(it->second); return DIS_ERR_CUDA_LAUNCH; }
   return DIS_OK;
 }
 

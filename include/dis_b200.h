@@ -11,8 +11,9 @@
  *
  * Conventions
  *   - every pointer is a DEVICE pointer to contiguous fp32 NCHW data owned by the caller;
- *     nothing is retained across calls, no global mutable state, re-entrant (the backward
- *     half runs on autograd's worker thread, model/ext_functions.py:130-140);
+ *     nothing is retained across calls, re-entrant and thread-safe (the backward half runs on
+ *     autograd's worker thread, model/ext_functions.py:130-140); the only process-wide state is a
+ *     mutex-guarded record of which kernels have been opted in to > 48 KB shared memory;
  *   - `stream` is a cudaStream_t (CUstream) passed as void*; work is enqueued, never
  *     synchronised;
  *   - return value: DIS_OK (0) or a negative dis_status; dis_status_string() names it.
