@@ -22,6 +22,8 @@ int pattern_warp_forward(const float*, const float*, float*, float*, int32_t*, i
 int reduce_pairs(const float*, int, int, float*, cudaStream_t);
 int scale_by_device_scalar(const float*, float*, size_t, const float*, const float*, cudaStream_t);
 int mul(const float*, const float*, float*, size_t, cudaStream_t);
+int l1_num_partials(size_t);
+int l1_forward(const float*, const float*, float*, float*, size_t, cudaStream_t);
 int smooth_loss_num_partials(int, int, int);
 int smooth_loss_forward(const float*, const float*, float*, float*, int, int, int, cudaStream_t);
 int sobel_forward(const float*, float*, int, int, int, int, cudaStream_t);
@@ -296,6 +298,14 @@ int dis_scale_by_device_scalar(const float* in, float* out, size_t n, const floa
   if (!in || !out || !numer) return DIS_ERR_NULL_POINTER;
   if (n == 0) return DIS_OK;
   return scale_by_device_scalar(in, out, n, numer, denom, as_stream(stream));
+}
+
+int dis_l1_num_partials(size_t n) { return l1_num_partials(n); }
+
+int dis_l1_forward(const float* a, const float* b, float* sign_out, float* partials, size_t n, void* stream) {
+  if (!a || !b || !partials) return DIS_ERR_NULL_POINTER;
+  if (n == 0) return DIS_ERR_BAD_SHAPE;
+  return l1_forward(a, b, sign_out, partials, n, as_stream(stream));
 }
 
 int dis_mul(const float* a, const float* b, float* out, size_t n, void* stream) {

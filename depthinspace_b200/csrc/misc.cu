@@ -73,6 +73,33 @@ __global__ void __launch_bounds__(256) mul_kernel(const float* __restrict__ a, c
   for (size_t i = 4 * n4 + t; i < n; i += stride) out[i] = a[i] * b[i];
 }
 
+// mean |a - b| in one pass: per-CTA partial sums (sum |a-b|, count) and, optionally, sign(a - b) (the gradient of
+// the sum w.r.t. a).  Auxiliary L1 terms of the workers: pseudo-GT (single_frame_worker.py:152-155), primary
+// disparity (multi_frame_worker.py:160-165).
+__global__ void __launch_bounds__(256) l1_kernel(const float* __restrict__ a, const float* __restrict__ b,
+                                                 float* __restrict__ sgn, float* __restrict__ partials, size_t n4, size_t n) {
+  __shared__ float red[16];
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  float s = 0.f, c = 0.f;
+  for (size_t i = t; i < n4; i += stride) {
+    const float4 u = __ldcs(reinterpret_cast<const float4*>(a) + i);
+    const float4 v = __ldcs(reinterpret_cast<const float4*>(b) + i);
+    const float d0 = u.x - v.x, d1 = u.y - v.y, d2 = u.z - v.z, d3 = u.w - v.w;
+    s += (fabsf(d0) + fabsf(d1)) + (fabsf(d2) + fabsf(d3));
+    c += 4.0f;
+    if (sgn) __stcs(reinterpret_cast<float4*>(sgn) + i, make_float4(sign0(d0), sign0(d1), sign0(d2), sign0(d3)));
+  }
+  for (size_t i = 4 * n4 + t; i < n; i += stride) {
+    const float d = a[i] - b[i];
+    s += fabsf(d);
+    c += 1.0f;
+    if (sgn) sgn[i] = sign0(d);
+  }
+  block_sum2<256>(s, c, red);
+  if (threadIdx.x == 0) { partials[2 * blockIdx.x] = s; partials[2 * blockIdx.x + 1] = c; }
+}
+
 inline int stream_grid(size_t work_items, int threads) {
   const size_t want = (work_items + threads - 1) / threads;
   const size_t cap = 148 * 16;  // 16 resident 256-thread CTAs x 148 SMs is plenty for a streaming loop
@@ -100,6 +127,15 @@ int scale_by_device_scalar(const float* in, float* out, size_t n, const float* n
   const bool vec = ((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out)) & 15) == 0;
   const size_t n4 = vec ? n / 4 : 0;
   scale_kernel<<<stream_grid(n4 ? n4 : n, 256), 256, 0, s>>>(in, out, n4, n, numer, denom);
+  return check_launch();
+}
+
+int l1_num_partials(size_t n) { return stream_grid((n + 3) / 4, 256); }
+
+int l1_forward(const float* a, const float* b, float* sgn, float* partials, size_t n, cudaStream_t s) {
+  const bool vec = ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b) | reinterpret_cast<uintptr_t>(sgn)) & 15) == 0;
+  // the grid must match l1_num_partials(n) whatever the alignment: scalar fallback keeps the same grid
+  l1_kernel<<<l1_num_partials(n), 256, 0, s>>>(a, b, sgn, partials, vec ? n / 4 : 0, n);
   return check_launch();
 }
 

@@ -9,8 +9,29 @@ model/worker.py:522).  The geometric (flow-consistency) terms are appended by th
 """
 import torch
 
+from . import _ops
 from .networks import (DisparitySmoothLoss, DispToDepth, Multi_Frame_Flow_Consistency_Loss,
                        RectifiedPatternSimilarityLoss, Single_Frame_Flow_Consistency_Loss)
+
+
+class _L1Mean(torch.autograd.Function):
+    """torch.mean(torch.abs(o - target)) with the gradient w.r.t. o produced by the same pass."""
+
+    @staticmethod
+    def forward(ctx, o, target):
+        out3, sgn = _ops.l1_forward(o, target, want_grad=ctx.needs_input_grad[0])
+        ctx.save_for_backward(sgn, out3)
+        return out3[2].clone()
+
+    @staticmethod
+    def backward(ctx, g):
+        sgn, out3 = ctx.saved_tensors
+        return _ops.scale_by_device_scalar(sgn, g, out3[1:2]).view_as(sgn), None
+
+
+def l1_mean(o, target):
+    """mean |o - target| (gradient to o only: the targets are data)."""
+    return _L1Mean.apply(o.contiguous(), target.detach())
 
 
 def _merge(x):
@@ -71,7 +92,7 @@ class SingleFrameLoss(_HotPathLoss):
             vals += self._geometric_terms(out[0], R, t, ambient, flow_out)
         if pseudo_gt is not None:                                     # :152-155 (DIS-FTSF)
             for s, o in enumerate(out):
-                vals.append(torch.mean(torch.abs(o - pseudo_gt)) * 0.1 / (2 ** s))
+                vals.append(l1_mean(o, pseudo_gt) * 0.1 / (2 ** s))
         return vals
 
 
@@ -88,5 +109,5 @@ class MultiFrameLoss(_HotPathLoss):
         if flow_out is not None:                                      # :128-157 (needs primary_disp)
             vals += self._geometric_terms(out[0], R, t, ambient, flow_out, primary_disp=primary_disp)
         if primary_disp is not None and warmup:                       # :160-165 (first two epochs)
-            vals.append(torch.mean(torch.abs(out[0] - primary_disp)) * 0.1)
+            vals.append(l1_mean(out[0], primary_disp) * 0.1)
         return vals

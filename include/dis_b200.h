@@ -127,6 +127,11 @@ DIS_API int dis_pattern_loss_multi_forward(const float* const* disps, int S, con
  * so no host synchronisation is needed between forward and backward. */
 DIS_API int dis_scale_by_device_scalar(const float* in, float* out, size_t n, const float* numer,
                                        const float* denom, void* stream);
+/* Auxiliary L1 terms of the loss assembly, mean|a - b| (single_frame_worker.py:152-155, multi_frame_worker.py:
+ * 160-165) in one pass: partials = float[2 * dis_l1_num_partials(n)] of (sum|a-b|, count) pairs (reduce with
+ * dis_reduce_pairs -> mean in out3[2]); sign_out (optional) = sign(a - b), the gradient of the sum w.r.t. a. */
+DIS_API int dis_l1_num_partials(size_t n);
+DIS_API int dis_l1_forward(const float* a, const float* b, float* sign_out, float* partials, size_t n, void* stream);
 /* out[i] = a[i] * b[i] */
 DIS_API int dis_mul(const float* a, const float* b, float* out, size_t n, void* stream);
 

@@ -749,3 +749,18 @@ def test_lcn_prepare_input_matches_copy_data(mods):
     ref_cat = torch.cat((r_l.view(tl, bs, 1, *hw), xt), dim=2)
     assert im_cat.shape == (tl, bs, 2, *hw) and std.shape == (tl, bs, 1, *hw)
     assert torch.equal(im_cat, ref_cat) and torch.equal(std, r_s.view(tl, bs, 1, *hw))
+
+
+def test_l1_mean_matches_torch(mods):
+    from depthinspace_b200 import losses
+    for shape in ((4, 2, 1, 64, 80), (3, 1, 37, 53), (5,)):
+        a = torch.randn(*shape, device="cuda", requires_grad=True)
+        b = torch.randn(*shape, device="cuda")
+        b.view(-1)[:2] = a.detach().view(-1)[:2]          # exact ties: sign(0) = 0 like torch.abs
+        v = losses.l1_mean(a, b)
+        (v * 0.3).backward()
+        ar = a.detach().double().requires_grad_(True)
+        vr = (ar - b.double()).abs().mean()
+        (vr * 0.3).backward()
+        assert_scalar_close(v.item(), vr.item(), 2e-6)
+        assert_close(a.grad, ar.grad, 1e-6, "l1 grad")
