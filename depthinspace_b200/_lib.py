@@ -45,6 +45,9 @@ SIGNATURES = {
     "dis_flow_warp_backward": [_f, _f, _f, _f, _f, _i, _i, _i, _i, _st],
     "dis_flow_consistency_num_partials": [_i, _i, _i],
     "dis_flow_consistency_forward": [_f] * 10 + [_i, _f, _f, _f, _fl, _fl, _f, _f, _f, _f, _f, _i, _i, _i, _st],
+    "dis_conv3d_out_size": [_i, _i, _i],
+    "dis_conv3d_gather_forward": [_f, _f, _f, _f, _f, _f, _f, _i, _i, _i, _i, _i, _i, _i, _i, _st],
+    "dis_conv3d_gather_backward": [_f, _f, _f, _f, _f, _i, _i, _i, _i, _i, _i, _i, _i, _st],
     "dis_combine2": [_f, _f, _f, _sz, _f, _f, _f, _fl, _st],
 }
 _RESTYPE = {"dis_status_string": _c.c_char_p, "dis_last_cuda_error": _c.c_char_p}

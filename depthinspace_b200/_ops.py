@@ -332,3 +332,34 @@ def combine2(a, b, numer, den_a, den_b, eps):
         _lib.check(lib.dis_combine2(_ptr(a), _ptr(b), _ptr(out), a.numel(), _ptr(numer), _ptr(den_a), _ptr(den_b),
                                     float(eps), _stream(a)))
     return out
+
+
+def conv3d_gather_forward(xyz, feat, mask, ksize, stride, neighbors):
+    """-> (xyz_nb [M,nb,3], feat_nb [M,nb,C], idx uint8 [M,nb], (oh, ow))"""
+    xyz, feat, mask = _chk(xyz, "xyz", 5), _chk(feat, "feat", 5), _chk(mask, "mask", 5)
+    tl, bs, C, h, w = feat.shape
+    if tuple(xyz.shape) != (tl, bs, 3, h, w) or tuple(mask.shape) != (tl, bs, 1, h, w):
+        raise ValueError("expected xyz [tl,bs,3,h,w], feat [tl,bs,C,h,w], mask [tl,bs,1,h,w]")
+    with _on(xyz) as lib:
+        oh, ow = lib.dis_conv3d_out_size(h, ksize, stride), lib.dis_conv3d_out_size(w, ksize, stride)
+        M = bs * oh * ow
+        xyz_nb = torch.empty((M, neighbors, 3), dtype=torch.float32, device=xyz.device)
+        feat_nb = torch.empty((M, neighbors, C), dtype=torch.float32, device=xyz.device)
+        idx = torch.empty((M, neighbors), dtype=torch.uint8, device=xyz.device)
+        scratch = torch.empty(1, dtype=torch.float32, device=xyz.device)
+        _lib.check(lib.dis_conv3d_gather_forward(_ptr(xyz), _ptr(feat), _ptr(mask), _ptr(xyz_nb), _ptr(feat_nb), _ptr(idx),
+                                                 _ptr(scratch), tl, bs, C, h, w, int(ksize), int(stride), int(neighbors),
+                                                 _stream(xyz)), launches=3)
+    return xyz_nb, feat_nb, idx, (oh, ow)
+
+
+def conv3d_gather_backward(g_xyz_nb, g_feat_nb, idx, shape, ksize, stride, neighbors, want_xyz, want_feat):
+    tl, bs, C, h, w = shape
+    g_xyz = torch.empty((tl, bs, 3, h, w), dtype=torch.float32, device=idx.device) if want_xyz else None
+    g_feat = torch.empty((tl, bs, C, h, w), dtype=torch.float32, device=idx.device) if want_feat else None
+    g_xyz_nb = g_xyz_nb.contiguous() if g_xyz_nb is not None else None
+    g_feat_nb = g_feat_nb.contiguous() if g_feat_nb is not None else None
+    with _on(idx) as lib:
+        _lib.check(lib.dis_conv3d_gather_backward(_ptr(g_xyz_nb), _ptr(g_feat_nb), _ptr(idx), _ptr(g_xyz), _ptr(g_feat),
+                                                  tl, bs, C, h, w, int(ksize), int(stride), int(neighbors), _stream(idx)))
+    return g_xyz, g_feat

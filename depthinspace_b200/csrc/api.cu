@@ -38,6 +38,12 @@ int flow_consistency_forward(const float*, const float*, const float*, const flo
                              cudaStream_t);
 int combine2(const float*, const float*, float*, size_t, const float*, const float*, const float*, float, cudaStream_t);
 
+int conv3d_out_size(int, int, int);
+int conv3d_gather_forward(const float*, const float*, const float*, float*, float*, uint8_t*, float*, int, int, int, int,
+                          int, int, int, int, cudaStream_t);
+int conv3d_gather_backward(const float*, const float*, const uint8_t*, float*, float*, int, int, int, int, int, int, int,
+                           int, cudaStream_t);
+
 namespace {
 
 constexpr int MAX_GRID_Z = 65535;
@@ -392,6 +398,39 @@ int dis_combine2(const float* a, const float* b, float* out, size_t n, const flo
   if (!a || !out || !numer || !den_a || (b && !den_b)) return DIS_ERR_NULL_POINTER;
   if (n == 0) return DIS_OK;
   return combine2(a, b, out, n, numer, den_a, den_b, eps, as_stream(stream));
+}
+
+int dis_conv3d_out_size(int n, int ksize, int stride) {
+  if (n < 1 || ksize < 1 || (ksize & 1) == 0 || stride < 1) return DIS_ERR_BAD_SHAPE;
+  return conv3d_out_size(n, ksize, stride);
+}
+
+static int check_conv3d(int tl, int bs, int C, int h, int w, int ksize, int stride, int neighbors) {
+  if (tl < 1 || bs < 0 || C < 1 || h < 1 || w < 1 || stride < 1) return DIS_ERR_BAD_SHAPE;
+  if (ksize < 1 || (ksize & 1) == 0 || ksize * ksize * tl > 64 || neighbors < 1 || neighbors > ksize * ksize * tl ||
+      neighbors > 16)
+    return DIS_ERR_UNSUPPORTED_COMBINATION;
+  return DIS_OK;
+}
+
+int dis_conv3d_gather_forward(const float* xyz, const float* feat, const float* mask, float* xyz_nb, float* feat_nb,
+                              uint8_t* idx, float* scratch, int tl, int bs, int C, int h, int w, int ksize, int stride,
+                              int neighbors, void* stream) {
+  if (int rc = check_conv3d(tl, bs, C, h, w, ksize, stride, neighbors)) return rc;
+  if (!xyz || !feat || !mask || !xyz_nb || !feat_nb || !idx || !scratch) return DIS_ERR_NULL_POINTER;
+  if (bs == 0) return DIS_OK;
+  return conv3d_gather_forward(xyz, feat, mask, xyz_nb, feat_nb, idx, scratch, tl, bs, C, h, w, ksize, stride,
+                               neighbors, as_stream(stream));
+}
+
+int dis_conv3d_gather_backward(const float* g_xyz_nb, const float* g_feat_nb, const uint8_t* idx, float* g_xyz,
+                               float* g_feat, int tl, int bs, int C, int h, int w, int ksize, int stride,
+                               int neighbors, void* stream) {
+  if (int rc = check_conv3d(tl, bs, C, h, w, ksize, stride, neighbors)) return rc;
+  if (!idx || (!g_xyz && !g_feat) || (g_xyz && !g_xyz_nb) || (g_feat && !g_feat_nb)) return DIS_ERR_NULL_POINTER;
+  if (bs == 0) return DIS_OK;
+  return conv3d_gather_backward(g_xyz_nb, g_feat_nb, idx, g_xyz, g_feat, tl, bs, C, h, w, ksize, stride, neighbors,
+                                as_stream(stream));
 }
 
 }  // extern "C"

@@ -1,0 +1,206 @@
+// Neighbour selection + gather of FuseNet's Conv3D (the step right after the flow warps in DIS-MF).
+// reference: Conv3D.tforward, model/multi_frame_networks.py:469-501
+//   unfold xyz / feat / mask [tl,bs,C,h,w] into k x k x tl candidates per output pixel (zero padding, stride s),
+//   rank the candidates by squared distance to the centre ray in the normalised image plane
+//   (masked-out candidates get global_max + 1), keep the `neighbors` smallest, gather xyz_local and feat.
+// The reference materialises three unfolded tensors of k*k*tl (=36) times the input and runs topk + two gathers;
+// here one thread ranks the 36 candidates of its output pixel in registers and only the 9 winners are written.
+// Ties (equal keys) are broken by the lowest candidate index; torch.topk(sorted=False) leaves them unspecified.
+// Backward is a deterministic gather (no atomics): every source element looks up the <= k*k output pixels whose
+// window contains it and adds the gradients of the slots that selected it.
+#include "common.cuh"
+
+namespace dis {
+namespace {
+
+constexpr int MAX_CAND = 64;
+
+struct C3Args {
+  const float* xyz; const float* feat; const float* mask;
+  float* xyz_nb; float* feat_nb; uint8_t* idx; float* gmax;
+  int tl, bs, C, h, w, k, stride, nb, oh, ow;
+};
+
+// squared plane distance of candidate (t, ky, kx) of output pixel (b, oy, ox) to the centre candidate, and its mask
+__device__ __forceinline__ void cand_pos(const C3Args& a, int oy, int ox, int ky, int kx, int& y, int& x, bool& inside) {
+  const int pad = (a.k - 1) / 2;
+  y = oy * a.stride + ky - pad;
+  x = ox * a.stride + kx - pad;
+  inside = y >= 0 && y < a.h && x >= 0 && x < a.w;
+}
+
+__device__ __forceinline__ void load_xyz(const C3Args& a, int t, int b, int y, int x, bool inside, float v[3]) {
+  if (!inside) { v[0] = v[1] = v[2] = 0.f; return; }   // F.pad(constant 0), :472
+  const size_t hw = (size_t)a.h * a.w;
+  const float* p = a.xyz + ((size_t)(t * a.bs + b) * 3) * hw + (size_t)y * a.w + x;
+  v[0] = __ldg(p); v[1] = __ldg(p + hw); v[2] = __ldg(p + 2 * hw);
+}
+
+// plane = xyz / (z + 1e-12)  (:489);  returns sum_c (plane_c - centre_plane_c)^2  (:493-495)
+__device__ __forceinline__ float plane_sq(const float v[3], const float cpl[3]) {
+  const float den = v[2] + 1e-12f;
+  const float d0 = __fdiv_rn(v[0], den) - cpl[0], d1 = __fdiv_rn(v[1], den) - cpl[1], d2 = __fdiv_rn(v[2], den) - cpl[2];
+  return __fmaf_rn(d2, d2, __fmaf_rn(d1, d1, __fmul_rn(d0, d0)));
+}
+
+template <bool SELECT>
+__global__ void __launch_bounds__(128) conv3d_rank_kernel(C3Args a) {
+  const int m = blockIdx.x * blockDim.x + threadIdx.x;
+  const int M = a.bs * a.oh * a.ow;
+  float local_max = 0.f;
+  if (m < M) {
+    const int b = m / (a.oh * a.ow), r = m - b * a.oh * a.ow, oy = r / a.ow, ox = r - oy * a.ow;
+    const int ncand = a.k * a.k * a.tl;
+    const int pad = (a.k - 1) / 2;
+    // centre candidate: (ky, kx) = (pad, pad), t = 0   (tidx = (k*k // 2) * tl, :491)
+    int cy, cx; bool cin;
+    cand_pos(a, oy, ox, pad, pad, cy, cx, cin);
+    float cxyz[3];
+    load_xyz(a, 0, b, cy, cx, cin, cxyz);
+    const float cden = cxyz[2] + 1e-12f;
+    const float cpl[3] = {__fdiv_rn(cxyz[0], cden), __fdiv_rn(cxyz[1], cden), __fdiv_rn(cxyz[2], cden)};
+    float key[MAX_CAND];
+    const float big = SELECT ? __ldg(a.gmax) + 1.0f : 0.f;
+    const size_t hw = (size_t)a.h * a.w;
+#pragma unroll 1
+    for (int c = 0; c < ncand; ++c) {
+      const int t = c % a.tl, kk = c / a.tl, ky = kk / a.k, kx = kk - ky * a.k;   // index = (ky*k + kx)*tl + t, :485
+      int y, x; bool in;
+      cand_pos(a, oy, ox, ky, kx, y, x, in);
+      float v[3];
+      load_xyz(a, t, b, y, x, in, v);
+      const float sq = plane_sq(v, cpl);
+      if (SELECT) {
+        const float mk = in ? __ldg(a.mask + (size_t)(t * a.bs + b) * hw + (size_t)y * a.w + x) : 0.f;
+        key[c] = __fmaf_rn(mk, sq, __fmul_rn(1.0f - mk, big));     // mask*sq + (1-mask)*(max+1), :497
+      } else {
+        local_max = fmaxf(local_max, sq);
+      }
+    }
+    if (SELECT) {
+      uint64_t taken = 0;
+      for (int j = 0; j < a.nb; ++j) {
+        int best = -1; float bk = 0.f;
+        for (int c = 0; c < ncand; ++c) {
+          if ((taken >> c) & 1) continue;
+          if (best < 0 || key[c] < bk) { best = c; bk = key[c]; }
+        }
+        taken |= (uint64_t)1 << best;
+        a.idx[(size_t)m * a.nb + j] = (uint8_t)best;
+        const int t = best % a.tl, kk = best / a.tl, ky = kk / a.k, kx = kk - ky * a.k;
+        int y, x; bool in;
+        cand_pos(a, oy, ox, ky, kx, y, x, in);
+        float v[3];
+        load_xyz(a, t, b, y, x, in, v);
+        float* o = a.xyz_nb + ((size_t)m * a.nb + j) * 3;
+        o[0] = v[0] - cxyz[0]; o[1] = v[1] - cxyz[1]; o[2] = v[2] - cxyz[2];     // xyz_local, :492
+      }
+    }
+  }
+  if (!SELECT) {
+    // global max of the squared distances (:497 xyz_sq.max()): order-independent, so an integer atomicMax on the
+    // bit pattern of the non-negative floats is deterministic
+    local_max = fmaxf(local_max, 0.f);
+    for (int o = 16; o > 0; o >>= 1) local_max = fmaxf(local_max, __shfl_xor_sync(0xffffffffu, local_max, o));
+    if ((threadIdx.x & 31) == 0) atomicMax(reinterpret_cast<int*>(a.gmax), __float_as_int(local_max));
+  }
+}
+
+// feat_nb[m, j, :] = feat[t, b, :, y, x] of the selected candidate (zeros when it lies in the padding)
+__global__ void __launch_bounds__(256) conv3d_feat_gather_kernel(C3Args a) {
+  const size_t total = (size_t)a.bs * a.oh * a.ow * a.nb;
+  const size_t hw = (size_t)a.h * a.w;
+  for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < total; i += (size_t)gridDim.x * 256) {
+    const int m = (int)(i / a.nb);
+    const int b = m / (a.oh * a.ow), r = m - b * a.oh * a.ow, oy = r / a.ow, ox = r - oy * a.ow;
+    const int c = a.idx[i];
+    const int t = c % a.tl, kk = c / a.tl, ky = kk / a.k, kx = kk - ky * a.k;
+    int y, x; bool in;
+    cand_pos(a, oy, ox, ky, kx, y, x, in);
+    float* o = a.feat_nb + i * a.C;
+    const float* src = a.feat + ((size_t)(t * a.bs + b) * a.C) * hw + (size_t)y * a.w + x;
+    for (int ch = 0; ch < a.C; ++ch) o[ch] = in ? __ldg(src + ch * hw) : 0.f;
+  }
+}
+
+struct C3BwdArgs {
+  const float* g_xyz_nb; const float* g_feat_nb; const uint8_t* idx;
+  float* g_xyz; float* g_feat;
+  int tl, bs, C, h, w, k, stride, nb, oh, ow;
+};
+
+// one thread per source element (t, b, y, x): deterministic gather of the gradients of every slot that selected it
+__global__ void __launch_bounds__(256) conv3d_gather_bwd_kernel(C3BwdArgs a) {
+  const size_t hw = (size_t)a.h * a.w;
+  const size_t total = (size_t)a.tl * a.bs * hw;
+  const int pad = (a.k - 1) / 2;
+  for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < total; i += (size_t)gridDim.x * 256) {
+    const int tb = (int)(i / hw), pix = (int)(i - (size_t)tb * hw), y = pix / a.w, x = pix - y * a.w;
+    const int t = tb / a.bs, b = tb - t * a.bs;
+    float gx[3] = {0.f, 0.f, 0.f};
+    int match[16];      // (m * nb + j) of the slots that picked this element; <= k*k of them
+    int nmatch = 0;
+    for (int ky = 0; ky < a.k; ++ky)
+      for (int kx = 0; kx < a.k; ++kx) {
+        // output pixel (oy, ox) sees (y, x) as candidate (ky, kx) iff oy*stride + ky - pad == y
+        const int ny = y - ky + pad, nx = x - kx + pad;
+        if (ny < 0 || nx < 0 || ny % a.stride || nx % a.stride) continue;
+        const int oy = ny / a.stride, ox = nx / a.stride;
+        if (oy >= a.oh || ox >= a.ow) continue;
+        const int m = (b * a.oh + oy) * a.ow + ox;
+        const int cand = (ky * a.k + kx) * a.tl + t;
+        for (int j = 0; j < a.nb; ++j)
+          if (a.idx[(size_t)m * a.nb + j] == cand) { if (nmatch < 16) match[nmatch++] = m * a.nb + j; break; }
+      }
+    if (a.g_xyz) {
+      for (int q = 0; q < nmatch; ++q)
+        for (int c = 0; c < 3; ++c) gx[c] += __ldg(a.g_xyz_nb + (size_t)match[q] * 3 + c);
+      if (t == 0 && y % a.stride == 0 && x % a.stride == 0 && y / a.stride < a.oh && x / a.stride < a.ow) {
+        const int m = (b * a.oh + y / a.stride) * a.ow + x / a.stride;      // this element is the centre of pixel m
+        for (int j = 0; j < a.nb; ++j)
+          for (int c = 0; c < 3; ++c) gx[c] -= __ldg(a.g_xyz_nb + ((size_t)m * a.nb + j) * 3 + c);
+      }
+      for (int c = 0; c < 3; ++c) a.g_xyz[((size_t)tb * 3 + c) * hw + pix] = gx[c];
+    }
+    if (a.g_feat) {
+      for (int ch = 0; ch < a.C; ++ch) {
+        float s = 0.f;
+        for (int q = 0; q < nmatch; ++q) s += __ldg(a.g_feat_nb + (size_t)match[q] * a.C + ch);
+        a.g_feat[((size_t)tb * a.C + ch) * hw + pix] = s;
+      }
+    }
+  }
+}
+
+inline int flat_grid(size_t total, int threads) {
+  const size_t want = (total + threads - 1) / threads, cap = 148 * 32;
+  return (int)(want < cap ? (want ? want : 1) : cap);
+}
+
+}  // namespace
+
+int conv3d_out_size(int n, int k, int stride) { return (n + 2 * ((k - 1) / 2) - k) / stride + 1; }
+
+int conv3d_gather_forward(const float* xyz, const float* feat, const float* mask, float* xyz_nb, float* feat_nb,
+                          uint8_t* idx, float* gmax, int tl, int bs, int C, int h, int w, int k, int stride, int nb,
+                          cudaStream_t s) {
+  C3Args a{xyz, feat, mask, xyz_nb, feat_nb, idx, gmax, tl, bs, C, h, w, k, stride, nb,
+           conv3d_out_size(h, k, stride), conv3d_out_size(w, k, stride)};
+  const int M = bs * a.oh * a.ow;
+  cudaError_t e = cudaMemsetAsync(gmax, 0, sizeof(float), s);
+  if (e != cudaSuccess) { set_last_cuda_error(e); return DIS_ERR_CUDA_LAUNCH; }
+  conv3d_rank_kernel<false><<<(M + 127) / 128, 128, 0, s>>>(a);
+  conv3d_rank_kernel<true><<<(M + 127) / 128, 128, 0, s>>>(a);
+  conv3d_feat_gather_kernel<<<flat_grid((size_t)M * nb, 256), 256, 0, s>>>(a);
+  return check_launch();
+}
+
+int conv3d_gather_backward(const float* g_xyz_nb, const float* g_feat_nb, const uint8_t* idx, float* g_xyz, float* g_feat,
+                           int tl, int bs, int C, int h, int w, int k, int stride, int nb, cudaStream_t s) {
+  C3BwdArgs a{g_xyz_nb, g_feat_nb, idx, g_xyz, g_feat, tl, bs, C, h, w, k, stride, nb,
+              conv3d_out_size(h, k, stride), conv3d_out_size(w, k, stride)};
+  conv3d_gather_bwd_kernel<<<flat_grid((size_t)tl * bs * h * w, 256), 256, 0, s>>>(a);
+  return check_launch();
+}
+
+}  // namespace dis

@@ -60,3 +60,36 @@ def gather_warped(x, flow, tidx, with_fb_mask=False):
             masks.append(warp_with_fb_mask(flow[f'flow_{j}{tidx}'], f)[1])
     out = torch.stack(warped, dim=0)
     return (out, torch.stack(masks, dim=0)) if with_fb_mask else out
+
+
+class _Conv3DGather(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, xyz, feat, mask, ksize, stride, neighbors):
+        ctx.set_materialize_grads(False)
+        xyz_nb, feat_nb, idx, _ = _ops.conv3d_gather_forward(xyz, feat, mask, ksize, stride, neighbors)
+        ctx.save_for_backward(idx)
+        ctx.cfg = (tuple(feat.shape), ksize, stride, neighbors)
+        ctx.mark_non_differentiable(idx)
+        return xyz_nb, feat_nb, idx
+
+    @staticmethod
+    def backward(ctx, g_xyz_nb, g_feat_nb, _):
+        (idx,) = ctx.saved_tensors
+        shape, ksize, stride, neighbors = ctx.cfg
+        want_xyz = ctx.needs_input_grad[0] and g_xyz_nb is not None
+        want_feat = ctx.needs_input_grad[1] and g_feat_nb is not None
+        if not (want_xyz or want_feat):
+            return None, None, None, None, None, None
+        g_xyz, g_feat = _ops.conv3d_gather_backward(g_xyz_nb, g_feat_nb, idx, shape, ksize, stride, neighbors,
+                                                    want_xyz, want_feat)
+        return g_xyz, g_feat, None, None, None, None
+
+
+def conv3d_gather(xyz, feat, mask, ksize=3, stride=1, neighbors=9):
+    """Neighbour selection + gather of Conv3D.tforward (reference :469-501), everything up to the MLP:
+    xyz [tl,bs,3,h,w], feat [tl,bs,C,h,w], mask [tl,bs,1,h,w] ->
+      xyz_neighbors [M,neighbors,3] (local coordinates), feat_neighbors [M,neighbors,C],
+      neighbors_ind [M,neighbors] (uint8 candidate index (ky*k+kx)*tl + t), M = bs*oh*ow.
+    Neighbours come in ascending distance with ties broken by the lowest index (torch.topk(sorted=False) leaves both
+    unspecified; the reference only sums over them).  Gradients flow to xyz and feat."""
+    return _Conv3DGather.apply(xyz, feat, mask, ksize, stride, neighbors)

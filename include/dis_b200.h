@@ -184,6 +184,21 @@ DIS_API int dis_flow_consistency_forward(const float* depth0, const float* depth
 DIS_API int dis_combine2(const float* a, const float* b, float* out, size_t n, const float* numer,
                          const float* den_a, const float* den_b, float eps, void* stream);
 
+/* ---- (next) neighbour selection + gather of FuseNet's Conv3D, model/multi_frame_networks.py:469-501 -------
+ * xyz [tl,bs,3,h,w], feat [tl,bs,C,h,w], mask [tl,bs,1,h,w] -> for each of the M = bs*oh*ow output pixels
+ * (ksize x ksize window, zero padding (ksize-1)/2, given stride) the `neighbors` candidates (of ksize^2*tl <= 64)
+ * closest to the centre ray in the normalised image plane:
+ *   xyz_nb [M,neighbors,3] = xyz_local, feat_nb [M,neighbors,C], idx [M,neighbors] uint8 candidate index
+ *   ((ky*ksize + kx)*tl + t, ascending key, ties -> lowest index); scratch: 1 float on the device.
+ * backward: deterministic gather; g_xyz / g_feat may be NULL. */
+DIS_API int dis_conv3d_out_size(int n, int ksize, int stride);
+DIS_API int dis_conv3d_gather_forward(const float* xyz, const float* feat, const float* mask, float* xyz_nb,
+                                      float* feat_nb, uint8_t* idx, float* scratch, int tl, int bs, int C, int h,
+                                      int w, int ksize, int stride, int neighbors, void* stream);
+DIS_API int dis_conv3d_gather_backward(const float* g_xyz_nb, const float* g_feat_nb, const uint8_t* idx,
+                                       float* g_xyz, float* g_feat, int tl, int bs, int C, int h, int w,
+                                       int ksize, int stride, int neighbors, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -235,3 +235,25 @@ class FlowConsistency:
 def disp_to_depth(disp, focal_length, baseline):
     """DispToDepth, model/networks.py:311-319."""
     return (baseline * focal_length) / (F.relu(disp) + 1e-12)
+
+
+def conv3d_gather(xyz, feat, mask, ksize=3, stride=1, neighbors=9):
+    """Conv3D.tforward up to the gathers, model/multi_frame_networks.py:469-501.
+    -> (xyz_neighbors [M,nb,3], feat_neighbors [M,nb,C], neighbors_ind [M,nb,1])"""
+    tl = xyz.shape[0]
+    p = (ksize - 1) // 2
+    pad = lambda t: F.pad(t, (p, p, p, p), mode="constant", value=0)
+    unf = lambda t: pad(t).unfold(3, ksize, stride).unfold(4, ksize, stride).permute(1, 3, 4, 5, 6, 0, 2)
+    xyz_u, feat_u, mask_u = unf(xyz), unf(feat), unf(mask)
+    flat = lambda t: t.reshape(-1, ksize * ksize * tl, t.shape[-1])
+    xyz_u, feat_u, mask_u = flat(xyz_u), flat(feat_u), flat(mask_u)
+    plane = xyz_u / (xyz_u[..., 2:] + 1e-12)
+    tidx = ((ksize ** 2) // 2) * tl
+    xyz_local = xyz_u - xyz_u[:, tidx:tidx + 1, :]
+    plane_local = plane - plane[:, tidx:tidx + 1, :]
+    sq = (plane_local ** 2).sum(dim=-1, keepdim=True)
+    key = (mask_u * sq) + (1 - mask_u) * (sq.max() + 1)
+    _, ind = torch.topk(key, neighbors, dim=1, largest=False, sorted=False)
+    xyz_nb = torch.gather(xyz_local, dim=1, index=ind.expand(-1, -1, xyz_local.shape[-1]))
+    feat_nb = torch.gather(feat_u, dim=1, index=ind.expand(-1, -1, feat_u.shape[-1]))
+    return xyz_nb, feat_nb, ind

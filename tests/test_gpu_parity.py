@@ -764,3 +764,47 @@ def test_l1_mean_matches_torch(mods):
         (vr * 0.3).backward()
         assert_scalar_close(v.item(), vr.item(), 2e-6)
         assert_close(a.grad, ar.grad, 1e-6, "l1 grad")
+
+
+# ----------------------------------------------------------------------------- Conv3D neighbour gather (§8 f3)
+def _sort_by_index(nb, ind):
+    order = torch.argsort(ind.long(), dim=1)
+    return torch.gather(nb, 1, order.unsqueeze(-1).expand(-1, -1, nb.shape[-1])), torch.gather(ind.long(), 1, order)
+
+
+@pytest.mark.parametrize("stride,tl,C,hw", [(1, 4, 32, (32, 27)), (2, 4, 8, (33, 28)), (1, 2, 3, (9, 7))])
+def test_conv3d_gather_vs_torch_port(mods, stride, tl, C, hw):
+    _, _, mf = mods
+    torch.manual_seed(C)
+    bs = 2
+    xyz = torch.randn(tl, bs, 3, *hw, device="cuda") * 0.1
+    xyz[:, :, 2] += 1.5
+    feat = torch.randn(tl, bs, C, *hw, device="cuda")
+    mask = (torch.rand(tl, bs, 1, *hw, device="cuda") > 0.25).float()
+    mask[0] = 1.0                                   # the own frame is always valid (multi_frame_networks.py:197)
+    x1, f1 = xyz.clone().requires_grad_(True), feat.clone().requires_grad_(True)
+    xyz_nb, feat_nb, idx = mf.conv3d_gather(x1, f1, mask, 3, stride, 9)
+    x2, f2 = xyz.clone().requires_grad_(True), feat.clone().requires_grad_(True)
+    r_xyz, r_feat, r_ind = torch_port.conv3d_gather(x2, f2, mask, 3, stride, 9)
+    assert xyz_nb.shape == r_xyz.shape and feat_nb.shape == r_feat.shape
+    # torch.topk(sorted=False) returns the winners in unspecified order: compare as sets, ordered by candidate index
+    a_x, a_i = _sort_by_index(xyz_nb, idx)
+    b_x, b_i = _sort_by_index(r_xyz, r_ind.squeeze(-1))
+    a_f, _ = _sort_by_index(feat_nb, idx)
+    b_f, _ = _sort_by_index(r_feat, r_ind.squeeze(-1))
+    # pixels with fewer than 9 unmasked candidates pad with masked ones, all tied at max+1: any choice is valid there
+    unf = torch_port.F.pad(mask, (1, 1, 1, 1)).unfold(3, 3, stride).unfold(4, 3, stride).permute(1, 3, 4, 5, 6, 0, 2).reshape(a_i.shape[0], -1)
+    decided = unf.sum(dim=1) >= 9
+    assert decided.float().mean() > 0.9
+    assert torch.equal(a_i[decided], b_i[decided]), "neighbour indices (integer work) must match"
+    assert torch.equal(a_x[decided], b_x[decided]) and torch.equal(a_f[decided], b_f[decided])
+    # gradients through both gathers (restricted to the decided pixels so that both sides select the same sets)
+    wx, wf = torch.randn_like(xyz_nb), torch.randn_like(feat_nb)
+    sel = decided.view(-1, 1, 1).float()
+    order_a = torch.argsort(idx.long(), dim=1)
+    order_b = torch.argsort(r_ind.squeeze(-1), dim=1)
+    ga = lambda t, o: torch.gather(t, 1, o.unsqueeze(-1).expand(-1, -1, t.shape[-1]))
+    ((ga(xyz_nb, order_a) * wx * sel).sum() + (ga(feat_nb, order_a) * wf * sel).sum()).backward()
+    ((ga(r_xyz, order_b) * wx * sel).sum() + (ga(r_feat, order_b) * wf * sel).sum()).backward()
+    assert_close(f1.grad, f2.grad, 1e-6, "grad feat")
+    assert_close(x1.grad, x2.grad, 1e-6, "grad xyz")

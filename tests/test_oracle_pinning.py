@@ -158,3 +158,25 @@ def test_flow_consistency_c_oracle_f64_equals_reference_f64(ref, mf):
     extra = [torch.from_numpy(pd0.astype(np.float32)), torch.from_numpy(pd1.astype(np.float32))] if mf else []
     r, p = modf(*a32, *extra), port(*a32, *extra)
     assert torch.equal(r if mf else r[0], p if mf else p[0])
+
+
+@pytest.mark.parametrize("stride", [1, 2])
+def test_conv3d_gather_port_reproduces_reference_conv3d(ref, stride):
+    """The port covers Conv3D.tforward up to the two gathers (model/multi_frame_networks.py:469-501); finishing with
+    the module's own MLP / matmul / norm must reproduce the reference layer's output."""
+    torch.manual_seed(stride)
+    tl, bs, C, h, w = 4, 2, 8, 12, 10
+    conv = ref.multi_frame_networks.Conv3D(C, C, stride=stride)
+    xyz = torch.randn(tl, bs, 3, h, w) * 0.1
+    xyz[:, :, 2] += 1.5
+    feat = torch.randn(tl, bs, C, h, w)
+    mask = (torch.rand(tl, bs, 1, h, w) > 0.3).float()
+    mask[0] = 1.0
+    with torch.no_grad():
+        out_ref = conv(xyz, feat, mask)
+        xyz_nb, feat_nb, ind = torch_port.conv3d_gather(xyz, feat, mask, 3, stride, 9)
+        d2 = conv.dense2(conv.dense1(xyz_nb))
+        fw = (d2 * feat_nb).sum(dim=1)
+        oh, ow = (h + 2 - 3) // stride + 1, (w + 2 - 3) // stride + 1
+        out = conv.bn(conv.activation(torch.matmul(fw, conv.w).view(bs, oh, ow, C).permute(0, 3, 1, 2)))
+    assert torch.equal(out, out_ref)
