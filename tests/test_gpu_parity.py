@@ -808,3 +808,21 @@ def test_conv3d_gather_vs_torch_port(mods, stride, tl, C, hw):
     ((ga(r_xyz, order_b) * wx * sel).sum() + (ga(r_feat, order_b) * wf * sel).sum()).backward()
     assert_close(f1.grad, f2.grad, 1e-6, "grad feat")
     assert_close(x1.grad, x2.grad, 1e-6, "grad xyz")
+
+
+@pytest.mark.parametrize("k", [1, 3, 7, 15])
+@pytest.mark.parametrize("lt", ["census_sad", "mse"])
+def test_fused_pattern_loss_window_sizes(mods, k, lt):
+    """Every supported window radius of the fused kernels (single-scale and 2-scale), ragged image."""
+    net, _, _ = mods
+    hw = (45, 83)
+    d, im_l, im_s, pat = _frames(2, hw, "kinect", seed=k, scales=2)
+    mod = net.RectifiedPatternSimilarityLoss(hw[0], hw[1], dev(np.repeat(pat, 3, axis=1)), loss_type=lt, block_size=k)
+    dd = [dev(p).requires_grad_(True) for p in d["disp_pred"]]
+    vals = mod.forward_multi(dd, dev(im_l), dev(im_s))
+    sum(vals).backward()
+    tid = c_oracle.TYPES[lt]
+    for s in range(2):
+        o32 = c_oracle.pattern_loss(d["disp_pred"][s], im_l, im_s, to_np(mod.pattern), k, tid, 0.5, True, "f32")
+        assert_scalar_close(vals[s].item(), o32["val"], 2e-6, f"val k={k}")
+        assert_close(dd[s].grad, o32["grad_disp"], 1e-5, f"grad k={k}", outlier_frac=5e-4 if "sad" in lt else 0)
