@@ -83,20 +83,53 @@ __device__ __forceinline__ void load_row8(const float* __restrict__ p, float (&r
   r[0] = a.x; r[1] = a.y; r[2] = a.z; r[3] = a.w; r[4] = b.x; r[5] = b.y; r[6] = b.z; r[7] = b.w;
 }
 
-// Tile 64 x 32.  Shared planes (all pitches multiples of 4 floats, every quad 16-byte aligned):
-//   sd, si  : inputs, replicate-clamped, origin (-4,-4): 40 rows x 72 cols
-//   sux, suy: u = sign(g a) a, zero outside the image, origin (-2,-2): 36 rows x 68 cols
+// Packed variant of sobel5_quad: the window holds (disp, ambient) pairs, every FFMA2 advances both images.
+// out: gx2[q] = (sobel_x(disp), sobel_x(amb)), gy2[q] likewise, for 4 adjacent responses.
+__device__ __forceinline__ void sobel5_quad2(const u64 (&win)[5][8], u64 (&gx2)[4], u64 (&gy2)[4]) {
+  constexpr float k[5][5] = {{SOB(-5.0), SOB(-4.0), 0.f, SOB(4.0), SOB(5.0)},
+                             {SOB(-8.0), SOB(-10.0), 0.f, SOB(10.0), SOB(8.0)},
+                             {SOB(-10.0), SOB(-20.0), 0.f, SOB(20.0), SOB(10.0)},
+                             {SOB(-8.0), SOB(-10.0), 0.f, SOB(10.0), SOB(8.0)},
+                             {SOB(-5.0), SOB(-4.0), 0.f, SOB(4.0), SOB(5.0)}};
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    u64 ax = pk2(0.f, 0.f), ay = pk2(0.f, 0.f);
+#pragma unroll
+    for (int i = 0; i < 5; ++i)
+#pragma unroll
+      for (int j = 0; j < 5; ++j) {
+        if (j != 2) ax = fma2(bc2(k[i][j]), win[i][q + j], ax);
+        if (i != 2) ay = fma2(bc2(k[j][i]), win[i][q + j], ay);
+      }
+    gx2[q] = ax;
+    gy2[q] = ay;
+  }
+}
+
+__device__ __forceinline__ void load_row8x2(const float2* __restrict__ p, u64 (&r)[8]) {
+#pragma unroll
+  for (int v = 0; v < 4; ++v) {
+    const float4 a = *reinterpret_cast<const float4*>(p + 2 * v);
+    r[2 * v] = pk2(a.x, a.y);
+    r[2 * v + 1] = pk2(a.z, a.w);
+  }
+}
+
+// Tile 64 x 32.  Shared planes of float2, pitches chosen so that 128-bit row loads are 16-byte aligned and, for
+// threads that walk down consecutive rows, bank-conflict free (pitch * 2 = 20 or 12 mod 32):
+//   sin : (disp, ambient), replicate-clamped, origin (-4,-4): 40 rows x 72 cols, pitch 74
+//   sux, suy : u = sign(g a) a, zero outside the image, origin (-2,-2): 36 rows x 68 cols (plain float planes: the
+//              adjoint taps carry different weights for u_x and u_y, and only a scalar FFMA takes an immediate)
 // Responses are produced in quads starting at tile-local column -2 + 4q, so their 8-wide input windows
 // (origin -4 + 4q) and their stores (origin -2 + 4q) are both aligned; the adjoint quads start at 4q and read
-// the u window starting at 4q - 2, aligned again.
+// the u window starting at 4q - 2, aligned again.  Both images go through the Sobel taps together as fp32x2.
+constexpr int PIN = 74, PU = U_P;
+
 template <bool GRAD>
 __global__ void __launch_bounds__(SNT) smooth_loss_kernel(const float* __restrict__ disp, const float* __restrict__ im,
                                                           float* __restrict__ grad_sum, float* __restrict__ partials,
                                                           int H, int W, int vec_ok) {
-  constexpr int P = IN_P;   // 72
-  constexpr int PU = U_P;   // 68
-  __shared__ __align__(16) float sd[IN_H * P];
-  __shared__ __align__(16) float si[IN_H * P];
+  __shared__ __align__(16) float2 sin[IN_H * PIN];
   __shared__ __align__(16) float sux[GRAD ? U_H * PU : 4];
   __shared__ __align__(16) float suy[GRAD ? U_H * PU : 4];
   __shared__ float red[2 * (SNT / 32)];
@@ -107,9 +140,8 @@ __global__ void __launch_bounds__(SNT) smooth_loss_kernel(const float* __restric
   const float* a = im + (size_t)n * hw;
   for (int idx = tid; idx < IN_H * IN_W; idx += SNT) {
     const int j = idx / IN_W, i = idx - j * IN_W;
-    const size_t g = (size_t)clampi(y0 - 4 + j, 0, H - 1) * W + clampi(x0 - 4 + i, 0, W - 1);
-    sd[j * P + i] = __ldg(d + g);
-    si[j * P + i] = __ldg(a + g);
+    const int g = clampi(y0 - 4 + j, 0, H - 1) * W + clampi(x0 - 4 + i, 0, W - 1);
+    sin[j * PIN + i] = make_float2(__ldg(d + g), __ldg(a + g));
   }
   __syncthreads();
 
@@ -117,28 +149,27 @@ __global__ void __launch_bounds__(SNT) smooth_loss_kernel(const float* __restric
   constexpr int UROWS = GRAD ? U_H : STH;   // rows -2..33 with the gradient, 0..31 without
   constexpr int UQ = U_W / 4;               // 17 quads: columns -2..65
   for (int item = tid; item < UROWS * UQ; item += SNT) {
-    const int jr = item / UQ, q = item - jr * UQ;
+    const int q = item / UROWS, jr = item - q * UROWS;   // consecutive threads walk down the rows of one quad
     const int ly = GRAD ? jr - 2 : jr;      // tile-local row of the responses
     const int lx = 4 * q - 2;               // tile-local column of the first response
     const int gy = y0 + ly;
     float ux[4] = {0.f, 0.f, 0.f, 0.f}, uy[4] = {0.f, 0.f, 0.f, 0.f};
     if (gy >= 0 && gy < H) {
       // response (ly, lx+c) reads tile-local rows ly-2..ly+2, cols lx+c-2..lx+c+2 = smem rows ly+2.., cols 4q+c..
-      float wd[5][8], wi[5][8];
+      u64 win[5][8];
 #pragma unroll
-      for (int i = 0; i < 5; ++i) {
-        load_row8(sd + (ly + 2 + i) * P + 4 * q, wd[i]);
-        load_row8(si + (ly + 2 + i) * P + 4 * q, wi[i]);
-      }
-      float gdx[4], gdy[4], gix[4], giy[4];
-      sobel5_quad(wd, gdx, gdy);
-      sobel5_quad(wi, gix, giy);
+      for (int i = 0; i < 5; ++i) load_row8x2(sin + (ly + 2 + i) * PIN + 4 * q, win[i]);
+      u64 gx2[4], gy2[4];
+      sobel5_quad2(win, gx2, gy2);
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
         const int gx = x0 + lx + c;
         if (gx >= 0 && gx < W) {
-          const float ax = expf(-fabsf(255.0f * gix[c])), ay = expf(-fabsf(255.0f * giy[c]));
-          const float vx = gdx[c] * ax, vy = gdy[c] * ay;
+          float gdx, gix, gdy, giy;
+          upk2(gx2[c], gdx, gix);
+          upk2(gy2[c], gdy, giy);
+          const float ax = expf(-fabsf(255.0f * gix)), ay = expf(-fabsf(255.0f * giy));
+          const float vx = gdx * ax, vy = gdy * ay;
           if (ly >= 0 && ly < STH && lx + c >= 0 && lx + c < STW) { lsum += fabsf(vx) + fabsf(vy); lcnt += 2.0f; }
           ux[c] = sign0(vx) * ax;
           uy[c] = sign0(vy) * ay;

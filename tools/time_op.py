@@ -1,0 +1,18 @@
+"""Time one op on the GPU: python tools/time_op.py smooth|lcn|multi"""
+import os, sys
+import torch
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from depthinspace_b200 import _ops
+N, H, W = 256, 512, 432
+x = torch.rand(N, 1, H, W, device="cuda")
+d = torch.rand(N, 1, H, W, device="cuda") * 60
+ops = {"smooth": lambda: _ops.smooth_loss_forward(d, x, True), "smooth_fwd": lambda: _ops.smooth_loss_forward(d, x, False),
+       "lcn": lambda: _ops.lcn_forward(x, 5, 0.05)}
+for name in sys.argv[1:]:
+    fn = ops[name]
+    for _ in range(3): fn()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize(); e0.record()
+    for _ in range(20): fn()
+    e1.record(); torch.cuda.synchronize()
+    print(name, "ms", round(e0.elapsed_time(e1) / 20, 4))
