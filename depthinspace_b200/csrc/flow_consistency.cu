@@ -51,7 +51,23 @@ __device__ __forceinline__ void project_to_view1(const Pose& P, const float* __r
   for (int j = 0; j < 3; ++j) out[j] = fmaf(c[2], K[3 * j + 2], fmaf(c[1], K[3 * j + 1], c[0] * K[3 * j]));
 }
 
-__global__ void __launch_bounds__(256) flow_consistency_kernel(FCArgs a) {
+// four-corner gather of one plane with ATen's in-bounds predicate: addresses come from the shared corner offsets
+struct CornerIdx { int o[4]; bool in[4]; };
+__device__ __forceinline__ void gather4(const float* __restrict__ plane, const CornerIdx& ci, float (&v)[4]) {
+#pragma unroll
+  for (int k = 0; k < 4; ++k) v[k] = ci.in[k] ? __ldg(plane + ci.o[k]) : 0.0f;
+}
+__device__ __forceinline__ float blend4(const float (&v)[4], const CornerIdx& ci, const Bilinear& b) {
+  float acc = 0.0f;
+  if (ci.in[0]) acc = __fmaf_rn(v[0], b.wnw, acc);
+  if (ci.in[1]) acc = __fmaf_rn(v[1], b.wne, acc);
+  if (ci.in[2]) acc = __fmaf_rn(v[2], b.wsw, acc);
+  if (ci.in[3]) acc = __fmaf_rn(v[3], b.wse, acc);
+  return acc;
+}
+
+template <bool AMB1>
+__global__ void __launch_bounds__(256, 4) flow_consistency_kernel(FCArgs a) {
   __shared__ Pose pose;      // 0 -> 1
   __shared__ Pose pose_inv;  // 1 -> 0 (reprojection mask)
   __shared__ float sK[9];
@@ -78,32 +94,49 @@ __global__ void __launch_bounds__(256) flow_consistency_kernel(FCArgs a) {
     Bilinear b;
     bilinear_setup<false>(normalize_coord(fadd(fx, (float)w), a.inv_w), normalize_coord(fadd(fy, (float)h), a.inv_h), a.H,
                           a.W, b);
-    // depth of p seen from view 1
+    // corner offsets / predicates once, then every gather of the pixel is issued before the first use
+    CornerIdx ci;
+    ci.in[0] = in_bounds(b.y0, b.x0, a.H, a.W); ci.in[1] = in_bounds(b.y0, b.x0 + 1, a.H, a.W);
+    ci.in[2] = in_bounds(b.y0 + 1, b.x0, a.H, a.W); ci.in[3] = in_bounds(b.y0 + 1, b.x0 + 1, a.H, a.W);
+    ci.o[0] = b.y0 * a.W + b.x0; ci.o[1] = ci.o[0] + 1; ci.o[2] = ci.o[0] + a.W; ci.o[3] = ci.o[2] + 1;
+    float vd[4], vfx[4], vfy[4], va[4];
+    gather4(a.depth1 + fo, ci, vd);
+    gather4(a.flow1 + (size_t)n * 2 * hw, ci, vfx);
+    gather4(a.flow1 + (size_t)n * 2 * hw + hw, ci, vfy);
+    if (AMB1) gather4(a.amb1 + fo, ci, va);
     const float dep0 = __ldg(a.depth0 + fo + pix);
+    const float amb0v = AMB1 ? __ldg(a.amb0 + fo + pix) : 0.f;
+    const float r0 = __ldg(a.ray + (size_t)pix * 3), r1 = __ldg(a.ray + (size_t)pix * 3 + 1), r2 = __ldg(a.ray + (size_t)pix * 3 + 2);
+    // depth of p seen from view 1
+    const float rayv[3] = {r0, r1, r2};
     float uvd[3];
-    project_to_view1(pose, sK, dep0, a.ray + (size_t)pix * 3, uvd);
+    project_to_view1(pose, sK, dep0, rayv, uvd);
     const float d1 = uvd[2];
-    const Corners cd = fetch_corners(a.depth1 + fo, a.H, a.W, b);
-    const float depth10 = blend(cd, b);
+    const float depth10 = blend4(vd, ci, b);
     const float raw = d1 - depth10;
     float diff = fabsf(raw);
     const bool clamped = a.clamp > 0.f && diff > a.clamp;   // torch.clamp passes gradient on [0, clamp] inclusive
     if (a.clamp > 0.f) diff = fminf(diff, a.clamp);
     if (a.orig_mask) a.orig_mask[fo + pix] = (diff < a.clamp) ? 1.0f : 0.0f;
     // forward-backward flow mask (:644-646 / :589-591)
-    const float f10x = blend(fetch_corners(a.flow1 + (size_t)n * 2 * hw, a.H, a.W, b), b);
-    const float f10y = blend(fetch_corners(a.flow1 + (size_t)n * 2 * hw + hw, a.H, a.W, b), b);
+    const float f10x = blend4(vfx, ci, b);
+    const float f10y = blend4(vfy, ci, b);
     const float sx = fadd(fx, f10x), sy = fadd(fy, f10y);
     const float lhs = fadd(fmul(sx, sx), fmul(sy, sy));
     const float mag = fadd(fadd(fmul(fx, fx), fmul(fy, fy)), fadd(fmul(f10x, f10x), fmul(f10y, f10y)));
     float mask = (lhs < fadd(0.5f, fmul(a.fb_scale, mag))) ? 1.0f : 0.0f;
     // visibility mask (:648-649): mean over channels of |amb0 - amb10| < 0.01
     float vc = 0.f;
-    for (int c = 0; c < a.amb_c; ++c) {
-      const float a10 = blend(fetch_corners(a.amb1 + ((size_t)n * a.amb_c + c) * hw, a.H, a.W, b), b);
-      vc = fadd(vc, fabsf(fsub(__ldg(a.amb0 + ((size_t)n * a.amb_c + c) * hw + pix), a10)));
+    if (AMB1) {
+      vc = fabsf(fsub(amb0v, blend4(va, ci, b)));
+    } else {
+      for (int c = 0; c < a.amb_c; ++c) {
+        float vv[4];
+        gather4(a.amb1 + ((size_t)n * a.amb_c + c) * hw, ci, vv);
+        vc = fadd(vc, fabsf(fsub(__ldg(a.amb0 + ((size_t)n * a.amb_c + c) * hw + pix), blend4(vv, ci, b))));
+      }
+      vc = vc / (float)a.amb_c;
     }
-    if (a.amb_c > 1) vc = vc / (float)a.amb_c;
     mask *= (vc < 0.01f) ? 1.0f : 0.0f;
     // reprojection mask (:591-595): view-1 pixels lifted with primary_depth1, projected into view 0, sampled at p+flow
     if (a.primary_depth1) {
@@ -130,7 +163,7 @@ __global__ void __launch_bounds__(256) flow_consistency_kernel(FCArgs a) {
       // d(diff*mask)/d d1 = mask * sign(raw) inside the clamp range; d d1 / d depth0 = ((ray R0) R1^T K^T)[2]
       const float g = (clamped ? 0.f : sign0(raw)) * mask;
       if (a.grad_depth0) {
-        const float* ray = a.ray + (size_t)pix * 3;
+        const float* ray = rayv;
         float wv3[3], c3[3];
 #pragma unroll
         for (int j = 0; j < 3; ++j) wv3[j] = fmaf(ray[2], pose.R0[6 + j], fmaf(ray[1], pose.R0[3 + j], ray[0] * pose.R0[j]));
@@ -141,10 +174,10 @@ __global__ void __launch_bounds__(256) flow_consistency_kernel(FCArgs a) {
       }
       if (a.grad_depth1 && g != 0.f) {
         float* gp = a.grad_depth1 + fo + (ptrdiff_t)b.y0 * a.W + b.x0;
-        if (cd.bnw) atomicAdd(gp, -g * b.wnw);
-        if (cd.bne) atomicAdd(gp + 1, -g * b.wne);
-        if (cd.bsw) atomicAdd(gp + a.W, -g * b.wsw);
-        if (cd.bse) atomicAdd(gp + a.W + 1, -g * b.wse);
+        if (ci.in[0]) atomicAdd(gp, -g * b.wnw);
+        if (ci.in[1]) atomicAdd(gp + 1, -g * b.wne);
+        if (ci.in[2]) atomicAdd(gp + a.W, -g * b.wsw);
+        if (ci.in[3]) atomicAdd(gp + a.W + 1, -g * b.wse);
       }
     }
   }
@@ -189,7 +222,8 @@ int flow_consistency_forward(const float* depth0, const float* depth1, const flo
            loss_mask, orig_mask, grad_depth0, grad_depth1, partials, bs, amb_c, H, W,
            clamp, fb_scale, 1.0f / (float)(W - 1), 1.0f / (float)(H - 1)};
   dim3 grid(flow_consistency_blocks_per_frame(H, W), bs);
-  flow_consistency_kernel<<<grid, 256, 0, s>>>(a);
+  if (amb_c == 1) flow_consistency_kernel<true><<<grid, 256, 0, s>>>(a);
+  else flow_consistency_kernel<false><<<grid, 256, 0, s>>>(a);
   return check_launch();
 }
 
