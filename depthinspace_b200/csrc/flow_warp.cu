@@ -38,11 +38,38 @@ __global__ void __launch_bounds__(256) flow_warp_fwd_kernel(const float* __restr
     flow_bilinear(flow, n, h, w, H, W, inv_w, inv_h, b, fx, fy);
     if (cx0) cx0[idx] = b.x0;
     if (cy0) cy0[idx] = b.y0;
+    // corner offsets and predicates once per pixel; channels in groups of 4 so that 16 gathers are in flight
+    const bool bnw = in_bounds(b.y0, b.x0, H, W), bne = in_bounds(b.y0, b.x0 + 1, H, W);
+    const bool bsw = in_bounds(b.y0 + 1, b.x0, H, W), bse = in_bounds(b.y0 + 1, b.x0 + 1, H, W);
+    const int o_nw = b.y0 * W + b.x0;
+    const float* xp = x + n * C * hw;
+    float* op = out + n * C * hw + pix;
     float o0 = 0.f, o1 = 0.f;
-    for (int c = 0; c < C; ++c) {
-      const Corners cr = fetch_corners(x + (n * C + c) * hw, H, W, b);
+    int c = 0;
+    for (; c + 4 <= C; c += 4) {
+      float v[4][4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float* p = xp + (size_t)(c + k) * hw + o_nw;
+        v[k][0] = bnw ? __ldg(p) : 0.f; v[k][1] = bne ? __ldg(p + 1) : 0.f;
+        v[k][2] = bsw ? __ldg(p + W) : 0.f; v[k][3] = bse ? __ldg(p + W + 1) : 0.f;
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        float acc = 0.f;
+        if (bnw) acc = __fmaf_rn(v[k][0], b.wnw, acc);
+        if (bne) acc = __fmaf_rn(v[k][1], b.wne, acc);
+        if (bsw) acc = __fmaf_rn(v[k][2], b.wsw, acc);
+        if (bse) acc = __fmaf_rn(v[k][3], b.wse, acc);
+        __stcs(op + (size_t)(c + k) * hw, acc);
+        if (c + k == 0) o0 = acc;
+        if (c + k == 1) o1 = acc;
+      }
+    }
+    for (; c < C; ++c) {
+      const Corners cr = fetch_corners(xp + (size_t)c * hw, H, W, b);
       const float v = blend(cr, b);
-      __stcs(out + (n * C + c) * hw + pix, v);
+      __stcs(op + (size_t)c * hw, v);
       if (c == 0) o0 = v;
       if (c == 1) o1 = v;
     }
@@ -72,6 +99,7 @@ __global__ void __launch_bounds__(256) flow_warp_bwd_kernel(const float* __restr
     const bool bsw = in_bounds(b.y0 + 1, b.x0, H, W), bse = in_bounds(b.y0 + 1, b.x0 + 1, H, W);
     const ptrdiff_t o_nw = (ptrdiff_t)b.y0 * W + b.x0;
     float gfx = 0.f, gfy = 0.f;
+#pragma unroll 4
     for (int c = 0; c < C; ++c) {
       const float g = ld_stream(go + (n * C + c) * hw + pix);
       if (gx) {
