@@ -93,6 +93,7 @@ __global__ void __launch_bounds__(NTHREADS, 3) box_photometric_fwd_kernel(PhotoA
     const float* e = a.es + ((size_t)n * a.C + c) * hw;
     const float* t = a.ta + ((size_t)n * a.C + c) * hw;
     if (c) __syncthreads();
+#pragma unroll 4
     for (int idx = tid; idx < G::ROWS * G::PITCH; idx += NTHREADS) {
       const int j = idx / G::PITCH, i = idx - j * G::PITCH;
       const int g = clampi(y0 - R + j, 0, a.H - 1) * a.W + clampi(x0 - R + i, 0, a.W - 1);
@@ -149,6 +150,7 @@ __global__ void __launch_bounds__(NTHREADS, 3) box_photometric_bwd_kernel(PhotoA
   const int x0 = blockIdx.x * TW, y0 = blockIdx.y * TH, n = blockIdx.z;
   const size_t hw = (size_t)a.H * a.W;
   const float* go = a.grad_out + (size_t)n * hw;
+#pragma unroll 4
   for (int idx = tid; idx < G::ROWS * G::PITCH; idx += NTHREADS) {
     const int j = idx / G::PITCH, i = idx - j * G::PITCH;
     const int gy = y0 - R + j, gx = x0 - R + i;
@@ -196,6 +198,8 @@ __global__ void __launch_bounds__(NTHREADS, 3) box_pattern_loss_kernel(PatternLo
   const float* disp = a.disp + (size_t)n * hw;
   const float* im = a.im + (size_t)n * hw;
   const float* sd = a.std_in ? a.std_in + (size_t)n * hw : nullptr;
+  // latency-bound staging (disp load -> 4 dependent pattern gathers): keep four positions in flight
+#pragma unroll 4
   for (int idx = tid; idx < G::ROWS * G::PITCH; idx += NTHREADS) {
     const int j = idx / G::PITCH, i = idx - j * G::PITCH;
     const int gy = y0 - R + j, gx = x0 - R + i;

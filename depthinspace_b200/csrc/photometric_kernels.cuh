@@ -157,6 +157,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) pattern_loss_kernel(PatternLossAr
   const float* im = a.im + (size_t)n * hw;
   const float* sd = a.std_in ? a.std_in + (size_t)n * hw : nullptr;
 
+#pragma unroll 2
   for (int idx = tid; idx < G::ROWS * G::COLS; idx += NTHREADS) {
     const int j = idx / G::COLS, i = idx - j * G::COLS;
     const int gy = y0 - R + j, gx = x0 - R + i;
