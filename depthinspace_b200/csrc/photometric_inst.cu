@@ -5,6 +5,7 @@
 #include "photometric_kernels.cuh"
 #include "pattern_multi.cuh"
 #include "box_kernels.cuh"
+#include "census_kernels.cuh"
 
 #ifndef DIS_R
 #error "compile with -DDIS_R=<window radius>"
@@ -70,13 +71,13 @@ template <int TYPE, int R>
 int photometric_t(const PhotoArgs& a, bool backward, cudaStream_t s) {
   const dim3 block(16, 16);
   if (!backward) {
-    const size_t smem = photo_smem_bytes<R>(false);
-    if (int rc = prepare(photometric_fwd_kernel<TYPE, R>, smem)) return rc;
-    photometric_fwd_kernel<TYPE, R><<<tile_grid(a.H, a.W, a.N), block, smem, s>>>(a);
+    const size_t smem = census_smem_bytes<R>(false, false);
+    if (int rc = prepare(census_fwd_kernel<TYPE, R>, smem)) return rc;
+    census_fwd_kernel<TYPE, R><<<tile_grid(a.H, a.W, a.N), block, smem, s>>>(a);
   } else {
-    const size_t smem = photo_smem_bytes<R>(true);
-    if (int rc = prepare(photometric_bwd_kernel<TYPE, R>, smem)) return rc;
-    photometric_bwd_kernel<TYPE, R><<<tile_grid(a.H, a.W, a.N * a.C), block, smem, s>>>(a);
+    const size_t smem = census_smem_bytes<R>(true, false);
+    if (int rc = prepare(census_bwd_kernel<TYPE, R>, smem)) return rc;
+    census_bwd_kernel<TYPE, R><<<tile_grid(a.H, a.W, a.N * a.C), block, smem, s>>>(a);
   }
   return check_launch();
 }
@@ -84,13 +85,13 @@ int photometric_t(const PhotoArgs& a, bool backward, cudaStream_t s) {
 template <int TYPE, int R>
 int pattern_loss_t(const PatternLossArgs& a, cudaStream_t s) {
   const dim3 block(16, 16);
-  const size_t smem = pattern_smem_bytes<R>();
+  const size_t smem = census_smem_bytes<R>(true, true);
   if (a.grad_num) {
-    if (int rc = prepare(pattern_loss_kernel<TYPE, R, true>, smem)) return rc;
-    pattern_loss_kernel<TYPE, R, true><<<tile_grid(a.H, a.W, a.N), block, smem, s>>>(a);
+    if (int rc = prepare(census_pattern_loss_kernel<TYPE, R, true>, smem)) return rc;
+    census_pattern_loss_kernel<TYPE, R, true><<<tile_grid(a.H, a.W, a.N), block, smem, s>>>(a);
   } else {
-    if (int rc = prepare(pattern_loss_kernel<TYPE, R, false>, smem)) return rc;
-    pattern_loss_kernel<TYPE, R, false><<<tile_grid(a.H, a.W, a.N), block, smem, s>>>(a);
+    if (int rc = prepare(census_pattern_loss_kernel<TYPE, R, false>, smem)) return rc;
+    census_pattern_loss_kernel<TYPE, R, false><<<tile_grid(a.H, a.W, a.N), block, smem, s>>>(a);
   }
   return check_launch();
 }

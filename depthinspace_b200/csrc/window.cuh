@@ -11,7 +11,8 @@
 //     gather (see grad derivation below).
 // Each thread walks the 2R+2 shared-memory rows that intersect its two windows, pulls the
 // 4+2R contiguous values per plane with 128-bit loads into registers and evaluates its
-// 4 x 2 x (2R+1) taps from registers: ~0.03 LDS per tap.
+// 4 x 2 x (2R+1) taps from registers: ~0.03 LDS per tap (main loops: census_kernels.cuh for
+// the soft-census types, box_kernels.cuh for mse / sad).
 //
 // Gradient in gather form.  With W = grad_out / k^2 and phi(x->q) the derivative of the
 // per-tap term w.r.t. the neighbour value (odd under swapping centre and neighbour),
@@ -88,63 +89,6 @@ __device__ __forceinline__ float finish_grad(float gacc, float ec, float tc, flo
   if (TYPE == SAD) return sign0(ec - tc) * gacc;
   // census_mse: f' = 2 (diff2 / 2), census_sad: f' = sign(diff2); both times h'(de) = 0.5 eps r^3
   return -0.5f * eps * gacc;
-}
-
-// Main loop over the thread's 4 x 2 patch.  se/st/sw point at the planes; (tx,ty) thread coords.
-template <int TYPE, int R, bool FWD, bool BWD>
-__device__ __forceinline__ void window_patch(const float* __restrict__ se, const float* __restrict__ st,
-                                             const float* __restrict__ sw, int tx, int ty, float eps,
-                                             float (&acc)[2][4], float (&gacc)[2][4],
-                                             float (&ec)[2][4], float (&tc)[2][4], float (&wc)[2][4]) {
-  using G = TileGeom<R>;
-  constexpr bool CENSUS = (TYPE >= CENSUS_MSE);
-  float gb[2][4];
-#pragma unroll
-  for (int r = 0; r < 2; ++r)
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int o = (2 * ty + r + R) * G::PITCH + 4 * tx + i + R;
-      ec[r][i] = se[o];
-      tc[r][i] = st[o];
-      wc[r][i] = BWD ? sw[o] : 0.0f;
-      acc[r][i] = 0.0f;
-      gacc[r][i] = 0.0f;
-      gb[r][i] = 0.0f;
-    }
-#pragma unroll 1
-  for (int j = 0; j < 2 * R + 2; ++j) {
-    float er[4 * G::NV], tr[4 * G::NV], wr[4 * G::NV];
-    const int base = (2 * ty + j) * G::PITCH + 4 * tx;
-#pragma unroll
-    for (int v = 0; v < G::NV; ++v) {
-      const float4 a = *reinterpret_cast<const float4*>(se + base + 4 * v);
-      er[4 * v] = a.x; er[4 * v + 1] = a.y; er[4 * v + 2] = a.z; er[4 * v + 3] = a.w;
-      if (FWD || CENSUS) {
-        const float4 b = *reinterpret_cast<const float4*>(st + base + 4 * v);
-        tr[4 * v] = b.x; tr[4 * v + 1] = b.y; tr[4 * v + 2] = b.z; tr[4 * v + 3] = b.w;
-      }
-      if (BWD) {
-        const float4 c = *reinterpret_cast<const float4*>(sw + base + 4 * v);
-        wr[4 * v] = c.x; wr[4 * v + 1] = c.y; wr[4 * v + 2] = c.z; wr[4 * v + 3] = c.w;
-      }
-    }
-#pragma unroll
-    for (int r = 0; r < 2; ++r) {
-      if (j - r < 0 || j - r > 2 * R) continue;  // warp-uniform
-#pragma unroll
-      for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int dx = 0; dx <= 2 * R; ++dx)
-          tap<TYPE, FWD, BWD>(ec[r][i], tc[r][i], er[i + dx], (FWD || CENSUS) ? tr[i + dx] : 0.0f,
-                              BWD ? wr[i + dx] : 0.0f, eps, acc[r][i], gacc[r][i], gb[r][i]);
-    }
-  }
-  if (BWD && CENSUS) {
-#pragma unroll
-    for (int r = 0; r < 2; ++r)
-#pragma unroll
-      for (int i = 0; i < 4; ++i) gacc[r][i] = fmaf(wc[r][i], gb[r][i], gacc[r][i]);
-  }
 }
 
 // How many offsets o in [-R,R] satisfy clamp(p + o, 0, size-1) == x  (p, x in [0,size)).
