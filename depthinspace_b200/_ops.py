@@ -274,6 +274,40 @@ def flow_warp_backward(x, flow, grad_out, want_x=True, want_flow=False):
     return gx, gf
 
 
+def _flow_ptr_array(flows, tl, bs, H, W):
+    import ctypes
+    if len(flows) != tl - 1:
+        raise ValueError(f"expected {tl - 1} flows, got {len(flows)}")
+    flows = [_chk(f, f"flow[{i}]") for i, f in enumerate(flows)]
+    for f in flows:
+        if tuple(f.shape) != (bs, 2, H, W):
+            raise ValueError(f"every flow must be {(bs, 2, H, W)}, got {tuple(f.shape)}")
+    arr = (ctypes.c_void_p * max(tl - 1, 1))(*[f.data_ptr() for f in flows])
+    return flows, arr
+
+
+def flow_warp_gather_forward(x, flows, tidx):
+    """x [tl,bs,C,h,w]; flows: the tl-1 tensors flow_{tidx,j}, j != tidx in increasing j -> out [tl,bs,C,h,w]."""
+    x = _chk(x, "x", 5)
+    tl, bs, C, H, W = x.shape
+    flows, arr = _flow_ptr_array(flows, tl, bs, H, W)
+    out = torch.empty_like(x)
+    with _on(x) as lib:
+        _lib.check(lib.dis_flow_warp_gather_forward(_ptr(x), arr, _ptr(out), tl, int(tidx), bs, C, H, W, _stream(x)))
+    return out
+
+
+def flow_warp_gather_backward(flows, grad_out, tidx):
+    grad_out = _chk(grad_out, "grad_out", 5)
+    tl, bs, C, H, W = grad_out.shape
+    flows, arr = _flow_ptr_array(flows, tl, bs, H, W)
+    gx = torch.empty_like(grad_out)
+    with _on(grad_out) as lib:
+        _lib.check(lib.dis_flow_warp_gather_backward(arr, _ptr(grad_out), _ptr(gx), tl, int(tidx), bs, C, H, W,
+                                                     _stream(grad_out)))
+    return gx
+
+
 def lcn_backward(data, lcn, std, g_lcn, g_std, radius, eps):
     data, lcn, std = _chk(data, "data"), _chk(lcn, "lcn"), _chk(std, "std")
     N, C, H, W = data.shape

@@ -24,6 +24,61 @@ __device__ __forceinline__ void flow_bilinear(const float* __restrict__ flow, si
   bilinear_setup<false>(gx, gy, H, W, b);
 }
 
+// one pixel of the forward warp: all C channels of xp (sample base) -> op (sample base + pix); returns channels 0, 1
+__device__ __forceinline__ void warp_pixel_fwd(const float* __restrict__ xp, float* __restrict__ op, const Bilinear& b,
+                                               int C, int H, int W, size_t hw, float& o0, float& o1) {
+  // corner offsets and predicates once per pixel; channels in groups of 4 so that 16 gathers are in flight
+  const bool bnw = in_bounds(b.y0, b.x0, H, W), bne = in_bounds(b.y0, b.x0 + 1, H, W);
+  const bool bsw = in_bounds(b.y0 + 1, b.x0, H, W), bse = in_bounds(b.y0 + 1, b.x0 + 1, H, W);
+  const int o_nw = b.y0 * W + b.x0;
+  o0 = 0.f; o1 = 0.f;
+  int c = 0;
+  for (; c + 4 <= C; c += 4) {
+    float v[4][4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float* p = xp + (size_t)(c + k) * hw + o_nw;
+      v[k][0] = bnw ? __ldg(p) : 0.f; v[k][1] = bne ? __ldg(p + 1) : 0.f;
+      v[k][2] = bsw ? __ldg(p + W) : 0.f; v[k][3] = bse ? __ldg(p + W + 1) : 0.f;
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      float acc = 0.f;
+      if (bnw) acc = __fmaf_rn(v[k][0], b.wnw, acc);
+      if (bne) acc = __fmaf_rn(v[k][1], b.wne, acc);
+      if (bsw) acc = __fmaf_rn(v[k][2], b.wsw, acc);
+      if (bse) acc = __fmaf_rn(v[k][3], b.wse, acc);
+      __stcs(op + (size_t)(c + k) * hw, acc);
+      if (c + k == 0) o0 = acc;
+      if (c + k == 1) o1 = acc;
+    }
+  }
+  for (; c < C; ++c) {
+    const Corners cr = fetch_corners(xp + (size_t)c * hw, H, W, b);
+    const float v = blend(cr, b);
+    __stcs(op + (size_t)c * hw, v);
+    if (c == 0) o0 = v;
+    if (c == 1) o1 = v;
+  }
+}
+
+// one pixel of the backward warp w.r.t. x: scatter go (sample base + pix) into gxp (sample base) with RED.ADD
+__device__ __forceinline__ void warp_pixel_bwd_x(const float* __restrict__ gop, float* __restrict__ gxp, const Bilinear& b,
+                                                 int C, int H, int W, size_t hw) {
+  const bool bnw = in_bounds(b.y0, b.x0, H, W), bne = in_bounds(b.y0, b.x0 + 1, H, W);
+  const bool bsw = in_bounds(b.y0 + 1, b.x0, H, W), bse = in_bounds(b.y0 + 1, b.x0 + 1, H, W);
+  const ptrdiff_t o_nw = (ptrdiff_t)b.y0 * W + b.x0;
+#pragma unroll 4
+  for (int c = 0; c < C; ++c) {
+    const float g = ld_stream(gop + (size_t)c * hw);
+    float* p = gxp + (size_t)c * hw + o_nw;
+    if (bnw) atomicAdd(p, b.wnw * g);
+    if (bne) atomicAdd(p + 1, b.wne * g);
+    if (bsw) atomicAdd(p + W, b.wsw * g);
+    if (bse) atomicAdd(p + W + 1, b.wse * g);
+  }
+}
+
 __global__ void __launch_bounds__(256) flow_warp_fwd_kernel(const float* __restrict__ x, const float* __restrict__ flow,
                                                             float* __restrict__ out, float* __restrict__ fb_mask,
                                                             int32_t* __restrict__ cx0, int32_t* __restrict__ cy0,
@@ -38,47 +93,69 @@ __global__ void __launch_bounds__(256) flow_warp_fwd_kernel(const float* __restr
     flow_bilinear(flow, n, h, w, H, W, inv_w, inv_h, b, fx, fy);
     if (cx0) cx0[idx] = b.x0;
     if (cy0) cy0[idx] = b.y0;
-    // corner offsets and predicates once per pixel; channels in groups of 4 so that 16 gathers are in flight
-    const bool bnw = in_bounds(b.y0, b.x0, H, W), bne = in_bounds(b.y0, b.x0 + 1, H, W);
-    const bool bsw = in_bounds(b.y0 + 1, b.x0, H, W), bse = in_bounds(b.y0 + 1, b.x0 + 1, H, W);
-    const int o_nw = b.y0 * W + b.x0;
-    const float* xp = x + n * C * hw;
-    float* op = out + n * C * hw + pix;
-    float o0 = 0.f, o1 = 0.f;
-    int c = 0;
-    for (; c + 4 <= C; c += 4) {
-      float v[4][4];
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const float* p = xp + (size_t)(c + k) * hw + o_nw;
-        v[k][0] = bnw ? __ldg(p) : 0.f; v[k][1] = bne ? __ldg(p + 1) : 0.f;
-        v[k][2] = bsw ? __ldg(p + W) : 0.f; v[k][3] = bse ? __ldg(p + W + 1) : 0.f;
-      }
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        float acc = 0.f;
-        if (bnw) acc = __fmaf_rn(v[k][0], b.wnw, acc);
-        if (bne) acc = __fmaf_rn(v[k][1], b.wne, acc);
-        if (bsw) acc = __fmaf_rn(v[k][2], b.wsw, acc);
-        if (bse) acc = __fmaf_rn(v[k][3], b.wse, acc);
-        __stcs(op + (size_t)(c + k) * hw, acc);
-        if (c + k == 0) o0 = acc;
-        if (c + k == 1) o1 = acc;
-      }
-    }
-    for (; c < C; ++c) {
-      const Corners cr = fetch_corners(xp + (size_t)c * hw, H, W, b);
-      const float v = blend(cr, b);
-      __stcs(op + (size_t)c * hw, v);
-      if (c == 0) o0 = v;
-      if (c == 1) o1 = v;
-    }
+    float o0, o1;
+    warp_pixel_fwd(x + n * C * hw, out + n * C * hw + pix, b, C, H, W, hw, o0, o1);
     if (fb_mask) {
       // (f + f_warped)^2 summed < 0.01 * (|f|^2 + |f_warped|^2) + 0.5   (multi_frame_networks.py:205-207)
       const float sx = fadd(fx, o0), sy = fadd(fy, o1);
       const float diff = fadd(fmul(sx, sx), fmul(sy, sy));
       const float mag = fadd(fadd(fmul(fx, fx), fmul(fy, fy)), fadd(fmul(o0, o0), fmul(o1, o1)));
       fb_mask[idx] = (diff < fadd(fmul(0.01f, mag), 0.5f)) ? 1.0f : 0.0f;
+    }
+  }
+}
+
+// Gather step of FuseNet (multi_frame_networks.py:187-214, 347-360) in one launch: output slot 0 is the own frame
+// (copied), slot k >= 1 is frame src[k] warped by flow[k]; x and out are [tl, bs, C, H, W], blockIdx.y = slot.
+constexpr int MAX_TL = 8;
+struct GatherArgs {
+  const float* flow[MAX_TL];
+  int src[MAX_TL];
+};
+
+__global__ void __launch_bounds__(256) flow_warp_gather_fwd_kernel(const float* __restrict__ x, GatherArgs g,
+                                                                   float* __restrict__ out, int C, int H, int W,
+                                                                   float inv_w, float inv_h, size_t total, size_t slot_stride) {
+  const size_t hw = (size_t)H * W;
+  const int slot = blockIdx.y;
+  const float* xs = x + (size_t)g.src[slot] * slot_stride;
+  float* os = out + (size_t)slot * slot_stride;
+  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (size_t)gridDim.x * blockDim.x) {
+    const size_t n = idx / hw;
+    const int pix = (int)(idx - n * hw), h = pix / W, w = pix - h * W;
+    if (slot == 0) {
+#pragma unroll 8
+      for (int c = 0; c < C; ++c) __stcs(os + (n * C + c) * hw + pix, ld_stream(xs + (n * C + c) * hw + pix));
+    } else {
+      Bilinear b;
+      float fx, fy, o0, o1;
+      flow_bilinear(g.flow[slot], n, h, w, H, W, inv_w, inv_h, b, fx, fy);
+      warp_pixel_fwd(xs + n * C * hw, os + n * C * hw + pix, b, C, H, W, hw, o0, o1);
+    }
+  }
+}
+
+// adjoint: gx[src[0]] = go[0]; gx[src[k]] += scatter(go[k]) (slices src[k >= 1] zero-filled by the launcher)
+__global__ void __launch_bounds__(256) flow_warp_gather_bwd_kernel(const float* __restrict__ go, GatherArgs g,
+                                                                   float* __restrict__ gx, int C, int H, int W,
+                                                                   float inv_w, float inv_h, size_t total, size_t slot_stride) {
+  const size_t hw = (size_t)H * W;
+  const int slot = blockIdx.y;
+  const float* gs = go + (size_t)slot * slot_stride;
+  float* xs = gx + (size_t)g.src[slot] * slot_stride;
+  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (size_t)gridDim.x * blockDim.x) {
+    const size_t n = idx / hw;
+    const int pix = (int)(idx - n * hw), h = pix / W, w = pix - h * W;
+    if (slot == 0) {
+#pragma unroll 8
+      for (int c = 0; c < C; ++c) xs[(n * C + c) * hw + pix] = ld_stream(gs + (n * C + c) * hw + pix);
+    } else {
+      Bilinear b;
+      float fx, fy;
+      flow_bilinear(g.flow[slot], n, h, w, H, W, inv_w, inv_h, b, fx, fy);
+      warp_pixel_bwd_x(gs + n * C * hw + pix, xs + n * C * hw, b, C, H, W, hw);
     }
   }
 }
@@ -127,7 +204,49 @@ inline int flat_grid(size_t total) {
   return (int)(want < cap ? (want ? want : 1) : cap);
 }
 
+int make_gather_args(const float* const* flows, int tl, int tidx, GatherArgs& g) {
+  if (tl < 1 || tl > MAX_TL || tidx < 0 || tidx >= tl) return DIS_ERR_BAD_SHAPE;
+  g.src[0] = tidx;
+  g.flow[0] = nullptr;
+  for (int j = 0, k = 1; j < tl; ++j) {
+    if (j == tidx) continue;
+    if (!flows[k - 1]) return DIS_ERR_NULL_POINTER;
+    g.src[k] = j;
+    g.flow[k] = flows[k - 1];
+    ++k;
+  }
+  return DIS_OK;
+}
+
 }  // namespace
+
+int flow_warp_gather_forward(const float* x, const float* const* flows, float* out, int tl, int tidx, int bs, int C,
+                             int H, int W, cudaStream_t s) {
+  GatherArgs g;
+  if (int rc = make_gather_args(flows, tl, tidx, g)) return rc;
+  const size_t total = (size_t)bs * H * W;
+  const dim3 grid(flat_grid(total), tl);
+  flow_warp_gather_fwd_kernel<<<grid, 256, 0, s>>>(x, g, out, C, H, W, 1.0f / (float)(W - 1), 1.0f / (float)(H - 1), total,
+                                                   total * C);
+  return check_launch();
+}
+
+int flow_warp_gather_backward(const float* const* flows, const float* go, float* gx, int tl, int tidx, int bs, int C,
+                              int H, int W, cudaStream_t s) {
+  GatherArgs g;
+  if (int rc = make_gather_args(flows, tl, tidx, g)) return rc;
+  const size_t total = (size_t)bs * H * W, stride = total * C;
+  // zero the scatter targets (every slice but the own frame's, which is overwritten by a plain copy)
+  cudaError_t e = cudaSuccess;
+  if (tidx > 0) e = cudaMemsetAsync(gx, 0, sizeof(float) * stride * tidx, s);
+  if (e == cudaSuccess && tidx + 1 < tl)
+    e = cudaMemsetAsync(gx + stride * (tidx + 1), 0, sizeof(float) * stride * (tl - 1 - tidx), s);
+  if (e != cudaSuccess) { set_last_cuda_error(e); return DIS_ERR_CUDA_LAUNCH; }
+  const dim3 grid(flat_grid(total), tl);
+  flow_warp_gather_bwd_kernel<<<grid, 256, 0, s>>>(go, g, gx, C, H, W, 1.0f / (float)(W - 1), 1.0f / (float)(H - 1), total,
+                                                   stride);
+  return check_launch();
+}
 
 int flow_warp_forward(const float* x, const float* flow, float* out, float* fb_mask, int32_t* cx0, int32_t* cy0, int N,
                       int C, int H, int W, cudaStream_t s) {

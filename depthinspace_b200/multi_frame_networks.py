@@ -41,25 +41,40 @@ def warp_with_fb_mask(flow_back, flow_fwd):
     return out, mask
 
 
+class _GatherWarped(torch.autograd.Function):
+    """[x[tidx], warp(x[j], flow_{tidx,j}) for j != tidx] written straight into the stacked output by one launch
+    (no per-warp tensors, no torch.stack copy); backward is one launch into a [tl,bs,C,h,w] gradient."""
+
+    @staticmethod
+    def forward(ctx, x, tidx, *flows):
+        ctx.tidx = tidx
+        ctx.save_for_backward(*flows)
+        return _ops.flow_warp_gather_forward(x, flows, tidx)
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        gx = _ops.flow_warp_gather_backward(ctx.saved_tensors, grad_out.contiguous(), ctx.tidx)
+        return (gx, None) + (None,) * len(ctx.saved_tensors)
+
+
 def gather_warped(x, flow, tidx, with_fb_mask=False):
     """Stack [x[tidx], warp(x[j], flow_{tidx,j}) for j != tidx] -> [tl, bs, C, h, w]: the gather step of
     FuseNet.gather_warped_xyz (reference :187-214) and Block2D3D.gather_warped_feat (:347-360).
-    x: [tl, bs, C, h, w]; flow: {'flow_ij': [bs, 2, h, w]} at the resolution of x.
+    x: [tl, bs, C, h, w] (or a list of tl [bs, C, h, w] tensors); flow: {'flow_ij': [bs, 2, h, w]} at the
+    resolution of x.  Gradients flow to x only (the reference detaches / never differentiates the flows).
     with_fb_mask additionally returns the float masks [tl, bs, 1, h, w] (ones for the own frame, the
     forward-backward consistency mask of :202-209 for the others)."""
+    if isinstance(x, (list, tuple)):
+        x = torch.stack(list(x), dim=0)
     tl = x.shape[0]
-    warped, masks = [x[tidx]], []
-    if with_fb_mask:
-        masks.append(torch.ones_like(x[tidx][:, :1]))
-    for j in range(tl):
-        if j == tidx:
-            continue
-        f = flow[f'flow_{tidx}{j}']
-        warped.append(warp(x[j].contiguous(), f))
-        if with_fb_mask:
-            masks.append(warp_with_fb_mask(flow[f'flow_{j}{tidx}'], f)[1])
-    out = torch.stack(warped, dim=0)
-    return (out, torch.stack(masks, dim=0)) if with_fb_mask else out
+    others = [j for j in range(tl) if j != tidx]
+    out = _GatherWarped.apply(x, tidx, *[flow[f'flow_{tidx}{j}'].detach() for j in others])
+    if not with_fb_mask:
+        return out
+    masks = [torch.ones_like(x[tidx][:, :1])]
+    for j in others:
+        masks.append(warp_with_fb_mask(flow[f'flow_{j}{tidx}'], flow[f'flow_{tidx}{j}'])[1])
+    return out, torch.stack(masks, dim=0)
 
 
 class _Conv3DGather(torch.autograd.Function):

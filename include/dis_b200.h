@@ -160,6 +160,19 @@ DIS_API int dis_flow_warp_backward(const float* x, const float* flow, const floa
                                    float* grad_x, float* grad_flow, int N, int C, int H, int W,
                                    void* stream);
 
+/* ---- a7  gather step of FuseNet: gather_warped_xyz / Block2D3D.gather_warped_feat,
+ *          model/multi_frame_networks.py:187-214, 347-360 -------------------------------------------
+ * x, out, grad_out, grad_x [tl,bs,C,H,W] (tl <= 8).  One launch builds the stacked tensor the reference
+ * assembles with tl-1 warp() calls + torch.stack:
+ *   out[0] = x[tidx];  out[k] = warp(x[j_k], flows[k-1]),  j_k = the k-th frame index != tidx in
+ *   increasing order, flows[k-1] = flow_{tidx, j_k} [bs,2,H,W] (HOST array of tl-1 device pointers).
+ * backward: grad_x[tidx] = grad_out[0]; grad_x[j_k] = warp^T(grad_out[k]) (zero-filled here, RED.ADD). */
+DIS_API int dis_flow_warp_gather_forward(const float* x, const float* const* flows, float* out, int tl,
+                                         int tidx, int bs, int C, int H, int W, void* stream);
+DIS_API int dis_flow_warp_gather_backward(const float* const* flows, const float* grad_out,
+                                          float* grad_x, int tl, int tidx, int bs, int C, int H, int W,
+                                          void* stream);
+
 /* ---- a9  flow-consistency (geometric) loss, ONE direction (frame 0 -> frame 1) -------------------------
  * Single_Frame_Flow_Consistency_Loss.fwd / Multi_Frame_Flow_Consistency_Loss.fwd, model/networks.py:619-655,
  * 564-601 (+ ProjectionBaseLoss :455-488).  depth*, amb* [bs,C,H,W] (depth C=1), flow* [bs,2,H,W],

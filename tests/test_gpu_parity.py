@@ -655,24 +655,44 @@ def test_full_single_frame_assembly_with_geometric_terms(mods):
         assert_close(outs[s].grad, refs[s].grad, 1e-4, f"grad scale {s}", outlier_frac=5e-3)
 
 
-def test_gather_warped_matches_reference_composition(mods):
+@pytest.mark.parametrize("tl,tidx,C", [(4, 1, 5), (4, 0, 32), (4, 3, 3), (2, 1, 2), (1, 0, 4)])
+def test_gather_warped_matches_reference_composition(mods, tl, tidx, C):
+    """One-launch gather (dis_flow_warp_gather_*) == the reference's tl-1 warp() calls + torch.stack, bit for bit;
+    its backward == autograd through that composition."""
     _, _, mf = mods
-    tl, bs, C, hw = 4, 2, 5, (64, 54)
+    bs, hw = 2, (64, 54)
     x = torch.randn(tl, bs, C, *hw, device="cuda", requires_grad=True)
     flow = {f"flow_{i}{j}": dev(synth.make_flows(bs, hw, max_mag=4.0, seed=7 * i + j)[0]) for i in range(tl) for j in range(tl) if i != j}
-    out, masks = mf.gather_warped(x, flow, 1, with_fb_mask=True)
+    out, masks = mf.gather_warped(x, flow, tidx, with_fb_mask=True)
     assert out.shape == (tl, bs, C, *hw) and masks.shape == (tl, bs, 1, *hw)
     w = torch.randn_like(out)
     (out * w).sum().backward()
     xr = x.detach().clone().requires_grad_(True)
+    others = [j for j in range(tl) if j != tidx]
     with torch.backends.cudnn.flags(enabled=False):
-        ref = [xr[1]] + [torch_port.flow_warp(xr[j], flow[f"flow_1{j}"]) for j in (0, 2, 3)]
+        ref = [xr[tidx]] + [torch_port.flow_warp(xr[j], flow[f"flow_{tidx}{j}"]) for j in others]
         rmask = [torch.ones(bs, 1, *hw, device="cuda")] + [
-            torch_port.fb_mask(flow[f"flow_1{j}"], torch_port.flow_warp(flow[f"flow_{j}1"], flow[f"flow_1{j}"])) for j in (0, 2, 3)]
+            torch_port.fb_mask(flow[f"flow_{tidx}{j}"], torch_port.flow_warp(flow[f"flow_{j}{tidx}"], flow[f"flow_{tidx}{j}"])) for j in others]
         ref = torch.stack(ref)
         (ref * w).sum().backward()
     assert torch.equal(out, ref) and torch.equal(masks, torch.stack(rmask))
     assert_close(x.grad, xr.grad, 2e-6, "grad through the gather")
+    # list-of-frames input (the reference keeps per-frame tensors in a list) gives the same stacked tensor
+    assert torch.equal(mf.gather_warped([x[i].detach() for i in range(tl)], flow, tidx), out)
+
+
+def test_gather_warped_rejects_bad_arguments(mods):
+    from depthinspace_b200 import _ops
+    x = torch.randn(3, 1, 2, 8, 9, device="cuda")
+    f = torch.zeros(1, 2, 8, 9, device="cuda")
+    with pytest.raises(ValueError):
+        _ops.flow_warp_gather_forward(x, [f], 0)                  # needs tl-1 = 2 flows
+    with pytest.raises(ValueError):
+        _ops.flow_warp_gather_forward(x, [f, torch.zeros(1, 2, 8, 8, device="cuda")], 0)
+    with pytest.raises(Exception):
+        _ops.flow_warp_gather_forward(x, [f, f], 3)               # tidx out of range -> DIS_ERR_BAD_SHAPE
+    with pytest.raises(Exception):
+        _ops.flow_warp_gather_forward(torch.randn(9, 1, 2, 8, 9, device="cuda"), [f] * 8, 0)   # tl > 8
 
 
 def test_lcn_backward_vs_reference_autograd(mods):

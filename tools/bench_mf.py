@@ -1,0 +1,158 @@
+"""DIS-MF hot path (BASELINE configs[2]) timed on one GPU: frames/s of everything the path covers in one
+multi-frame training step, forward + backward, device-resident inputs, CUDA events.
+
+Per track of tl = 4 frames (reference call sites in brackets):
+  * copy_data:   transpose + LCN + cat of the IR frames                       [worker.py:418-452]
+  * FuseNet:     24 xyz / flow warps with forward-backward masks at 256x216   [multi_frame_networks.py:187-214]
+                 96 feature warps, C = 32: 4 blocks x 4 frames x 3 neighbours at 256x216 and 128x108 [:347-360]
+                 each run forward, forward again (torch.utils.checkpoint recompute) and backward w.r.t. x
+  * loss:        1-scale census_sad 9x9 pattern loss + 0.8 smoothness + 6 pairs x 2 directions of the multi-frame
+                 flow-consistency loss + primary-disparity L1, forward + backward   [multi_frame_worker.py:103-175]
+The FuseNet convolutions / Conv3D MLPs stay on PyTorch (north star) and are not part of the timed region.
+
+    python tools/bench_mf.py [--bs 4 32] [--steps 10] [--warmup 3]
+
+One JSON line per batch size; `frames` = tl * bs.  bs = 4 is one GPU's share of configs[2] (batch 32 over 8 GPUs).
+"""
+import argparse
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from depthinspace_b200 import _lib, losses, multi_frame_networks as mfn, networks, synth  # noqa: E402
+
+TL = 4
+HW = synth.DATASET_HW
+FEAT = ((HW[0] // 2, HW[1] // 2), (HW[0] // 4, HW[1] // 4))   # 256x216, 128x108
+C_FEAT, BLOCKS = 32, 4
+
+
+def build(bs, dev):
+    n = TL * bs
+    base = min(n, 8)                      # a few distinct synthetic frames, tiled up to the batch
+    fr = synth.make_frames(base, HW, "default", n_scales=1, seed=42)
+    rep = lambda a: torch.from_numpy(np.concatenate([a] * ((n + base - 1) // base))[:n]).to(dev)
+    im, amb, disp, dgt = rep(fr["im"]), rep(fr["ambient"]), rep(fr["disp_pred"][0]), rep(fr["disp_gt"])
+    g = synth.make_geometry(min(bs, 2), HW, seed=5)
+    repb = lambda a: torch.from_numpy(np.concatenate([a] * bs)[:bs]).to(dev)
+    K = torch.from_numpy(g["K"].astype(np.float64))
+    Ki = torch.from_numpy(np.linalg.inv(g["K"].astype(np.float64)))
+    # every ordered frame pair of the track uses the two-view geometry (even frames = view 0, odd = view 1)
+    R = torch.stack([repb(g["R0"] if i % 2 == 0 else g["R1"]) for i in range(TL)])
+    t = torch.stack([repb(g["t0"] if i % 2 == 0 else g["t1"]) for i in range(TL)])
+    flow = {}
+    for i in range(TL):
+        for j in range(TL):
+            if i != j:
+                same = (i % 2) == (j % 2)
+                f = np.zeros_like(g["flow01"]) if same else (g["flow01"] if i % 2 == 0 else g["flow10"])
+                flow[f"flow_{i}{j}"] = repb(f)
+    view = lambda a: a.view(TL, bs, *a.shape[1:])
+    pattern = torch.from_numpy(np.repeat(fr["pattern"], 3, axis=1)).to(dev)
+    focal, baseline = float(g["K"][0, 0]), 0.075
+    loss = losses.MultiFrameLoss(HW[0], HW[1], pattern, K=K, Ki=Ki, focal_length=focal, baseline=baseline).to(dev)
+    lcn = networks.LCN(5, 0.05).to(dev)
+    feats, flows_lr, grads = [], [], []
+    gen = torch.Generator(device=dev).manual_seed(0)
+    for (h, w) in FEAT:
+        feats.append(torch.randn(TL, bs, C_FEAT, h, w, device=dev, generator=gen).requires_grad_(True))
+        sc = h / HW[0]
+        flows_lr.append({k: torch.nn.functional.interpolate(v, size=(h, w), mode="bilinear", align_corners=True) * sc
+                         for k, v in flow.items()})
+        grads.append(torch.randn(TL, bs, C_FEAT, h, w, device=dev, generator=gen))
+    xyz = torch.randn(TL, bs, 3, *FEAT[0], device=dev, generator=gen)
+    return dict(im=view(im), amb=view(amb), disp=view(disp), prim=view(dgt + 0.3), R=R, t=t, flow=flow, loss=loss, lcn=lcn,
+                feats=feats, flows_lr=flows_lr, grads=grads, xyz=xyz, bs=bs)
+
+
+class Sections:
+    """CUDA-event stopwatch per section of the step (accumulated over the timed steps)."""
+
+    def __init__(self):
+        self.marks, self.on = [], False
+
+    def mark(self, name):
+        if self.on:
+            e = torch.cuda.Event(enable_timing=True)
+            e.record()
+            self.marks.append((name, e))
+
+    def summary(self, steps):
+        acc = {}
+        for (_, e0), (name, e1) in zip(self.marks, self.marks[1:]):
+            if name != "start":
+                acc[name] = acc.get(name, 0.0) + e0.elapsed_time(e1)
+        return {k: round(v / steps, 3) for k, v in acc.items()}
+
+
+SEC = Sections()
+
+
+def step(w):
+    SEC.mark("start")
+    # ---- copy_data: LCN + cat(lcn, raw), [tl, bs, 2, H, W]
+    im_cat, std = w["lcn"].prepare_input(w["im"].transpose(0, 1).contiguous())   # reference hands over [bs, tl, ...]
+    SEC.mark("copy_data_ms")
+    # ---- FuseNet warps
+    with torch.no_grad():
+        for tidx in range(TL):
+            mfn.gather_warped(w["xyz"], w["flows_lr"][0], tidx, with_fb_mask=True)          # 12 xyz + 12 flow warps
+    SEC.mark("xyz_flow_warps_ms")
+    for lvl in range(2):
+        x, fl, go = w["feats"][lvl], w["flows_lr"][lvl], w["grads"][lvl]
+        x.grad = None
+        for _ in range(BLOCKS):
+            for tidx in range(TL):
+                with torch.no_grad():
+                    mfn.gather_warped(x, fl, tidx)                                          # checkpointed forward
+                out = mfn.gather_warped(x, fl, tidx)                                        # recompute in backward
+                out.backward(go)
+        SEC.mark(f"feature_warps_{FEAT[lvl][0]}x{FEAT[lvl][1]}_ms")
+    # ---- loss
+    disp = w["disp"].detach().requires_grad_(True)
+    vals = w["loss"]([disp], im_cat, std, w["amb"], primary_disp=w["prim"], R=w["R"], t=w["t"], flow_out=w["flow"])
+    total = torch.stack([v.reshape(()) for v in vals]).sum()
+    total.backward()
+    SEC.mark("loss_ms")
+    return total
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--bs", type=int, nargs="+", default=[4, 32])
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    a = ap.parse_args()
+    dev = torch.device("cuda")
+    for bs in a.bs:
+        w = build(bs, dev)
+        for _ in range(a.warmup):
+            total = step(w)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        l0 = _lib.LAUNCHES
+        SEC.marks, SEC.on = [], True
+        e0.record()
+        for _ in range(a.steps):
+            total = step(w)
+        e1.record()
+        torch.cuda.synchronize()
+        SEC.on = False
+        ms = e0.elapsed_time(e1) / a.steps
+        launches = (_lib.LAUNCHES - l0) // a.steps
+        n = TL * bs
+        print(json.dumps({"workload": "BASELINE configs[2]: DIS-MF hot path (copy_data LCN + 24 xyz/flow warps + 96 C=32 feature warps "
+                                      "fwd/recompute/bwd + 1-scale census_sad loss + smoothness + 12 flow-consistency terms + L1), fwd+bwd",
+                          "bs": bs, "tl": TL, "frames": n, "ms_per_step": round(ms, 3), "frames_per_s": round(n / (ms * 1e-3), 1),
+                          "gpu_launches_per_step": launches, "sections": SEC.summary(a.steps), "loss": float(total.detach())}), flush=True)
+        del w
+        torch.cuda.empty_cache()
+
+
+if __name__ == "__main__":
+    main()
