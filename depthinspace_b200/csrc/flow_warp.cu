@@ -68,7 +68,7 @@ __device__ __forceinline__ void warp_pixel_bwd_x(const float* __restrict__ gop, 
   const bool bnw = in_bounds(b.y0, b.x0, H, W), bne = in_bounds(b.y0, b.x0 + 1, H, W);
   const bool bsw = in_bounds(b.y0 + 1, b.x0, H, W), bse = in_bounds(b.y0 + 1, b.x0 + 1, H, W);
   const ptrdiff_t o_nw = (ptrdiff_t)b.y0 * W + b.x0;
-#pragma unroll 4
+#pragma unroll 8
   for (int c = 0; c < C; ++c) {
     const float g = ld_stream(gop + (size_t)c * hw);
     float* p = gxp + (size_t)c * hw + o_nw;
@@ -113,7 +113,7 @@ struct GatherArgs {
   int src[MAX_TL];
 };
 
-__global__ void __launch_bounds__(256) flow_warp_gather_fwd_kernel(const float* __restrict__ x, GatherArgs g,
+__global__ void __launch_bounds__(256) flow_warp_gather_fwd_kernel(const float* __restrict__ x, const __grid_constant__ GatherArgs g,
                                                                    float* __restrict__ out, int C, int H, int W,
                                                                    float inv_w, float inv_h, size_t total, size_t slot_stride) {
   const size_t hw = (size_t)H * W;
@@ -137,7 +137,7 @@ __global__ void __launch_bounds__(256) flow_warp_gather_fwd_kernel(const float* 
 }
 
 // adjoint: gx[src[0]] = go[0]; gx[src[k]] += scatter(go[k]) (slices src[k >= 1] zero-filled by the launcher)
-__global__ void __launch_bounds__(256) flow_warp_gather_bwd_kernel(const float* __restrict__ go, GatherArgs g,
+__global__ void __launch_bounds__(256) flow_warp_gather_bwd_kernel(const float* __restrict__ go, const __grid_constant__ GatherArgs g,
                                                                    float* __restrict__ gx, int C, int H, int W,
                                                                    float inv_w, float inv_h, size_t total, size_t slot_stride) {
   const size_t hw = (size_t)H * W;

@@ -8,6 +8,15 @@ x = torch.rand(N, 1, H, W, device="cuda")
 d = torch.rand(N, 1, H, W, device="cuda") * 60
 ops = {"smooth": lambda: _ops.smooth_loss_forward(d, x, True), "smooth_fwd": lambda: _ops.smooth_loss_forward(d, x, False),
        "lcn": lambda: _ops.lcn_forward(x, 5, 0.05)}
+if any(a.startswith("gather") for a in sys.argv[1:]):
+    tl, bs, C, h, w = 4, 32, 32, 256, 216
+    xf = torch.randn(tl, bs, C, h, w, device="cuda")
+    go = torch.randn(tl, bs, C, h, w, device="cuda")
+    yy, xx = torch.meshgrid(torch.linspace(0, 6.28, h, device="cuda"), torch.linspace(0, 6.28, w, device="cuda"), indexing="ij")
+    flows = [torch.stack((4 * torch.sin(xx + k) + 2 * torch.cos(yy), 3 * torch.cos(yy * 2 + k) - torch.sin(xx)), 0)[None].repeat(bs, 1, 1, 1).contiguous()
+             for k in range(tl - 1)]
+    ops["gather_fwd"] = lambda: _ops.flow_warp_gather_forward(xf, flows, 1)
+    ops["gather_bwd"] = lambda: _ops.flow_warp_gather_backward(flows, go, 1)
 for name in sys.argv[1:]:
     fn = ops[name]
     for _ in range(3): fn()
