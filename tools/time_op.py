@@ -17,6 +17,7 @@ if any(a.startswith("gather") for a in sys.argv[1:]):
              for k in range(tl - 1)]
     ops["gather_fwd"] = lambda: _ops.flow_warp_gather_forward(xf, flows, 1)
     ops["gather_bwd"] = lambda: _ops.flow_warp_gather_backward(flows, go, 1)
+    ops["gather_warp_bwd"] = lambda: _ops.flow_warp_backward(None, flows[0], go[0], True, False)
 for name in sys.argv[1:]:
     fn = ops[name]
     for _ in range(3): fn()
