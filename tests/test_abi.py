@@ -58,6 +58,13 @@ def test_argument_validation_without_gpu(lib_path):
     assert lib.dis_photometric_loss_forward(one, one, one, 0, 1, 8, 8, 9, 3, 0.5, None) == 0    # empty batch
     assert lib.dis_lcn_forward(one, one, one, 1, 8, 8, 9, 0.05, None) == -2                      # radius >= size
     assert lib.dis_sobel_forward(one, one, 1, 8, 8, 4, None) == -6
+    # FuseNet gather: tl in 1..8, tidx in range, flows required for tl > 1
+    assert lib.dis_flow_warp_gather_forward(one, None, one, 4, 1, 2, 3, 8, 8, None) == -4
+    assert lib.dis_flow_warp_gather_forward(one, None, one, 9, 1, 2, 3, 8, 8, None) == -4
+    arr = (ctypes.c_void_p * 8)(*[16] * 8)
+    assert lib.dis_flow_warp_gather_forward(one, arr, one, 9, 1, 2, 3, 8, 8, None) == -2         # tl > 8
+    assert lib.dis_flow_warp_gather_forward(one, arr, one, 4, 4, 2, 3, 8, 8, None) == -2         # tidx out of range
+    assert lib.dis_flow_warp_gather_backward(arr, one, one, 4, 0, 0, 3, 8, 8, None) == 0         # empty batch
     assert lib.dis_pattern_loss_num_partials(2, 512, 432) == 2 * 16 * 7
     with pytest.raises(Exception, match="invalid loss type"):
         _lib.check(-1)
