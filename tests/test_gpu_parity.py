@@ -846,3 +846,60 @@ def test_fused_pattern_loss_window_sizes(mods, k, lt):
         o32 = c_oracle.pattern_loss(d["disp_pred"][s], im_l, im_s, to_np(mod.pattern), k, tid, 0.5, True, "f32")
         assert_scalar_close(vals[s].item(), o32["val"], 2e-6, f"val k={k}")
         assert_close(dd[s].grad, o32["grad_disp"], 1e-5, f"grad k={k}", outlier_frac=5e-4 if "sad" in lt else 0)
+
+
+# ----------------------------------------------------------------------------- BASELINE full size, size-independent properties
+def test_full_size_step_properties(mods):
+    """BASELINE configs[1] size (256 frames of 512x432, 4 scales): properties that need no oracle run.
+    (1) bitwise reproducible; (2) (num, den) of the batch == sum over its quarters (what weak scaling relies on);
+    (3) a frame whose estimate equals its target contributes exactly 0 to num and gets a zero gradient;
+    (4) the gradient predicts the loss change along a random direction (directional finite difference in fp64 sums);
+    (5) the oracle agrees on a 2-frame slice of the same inputs."""
+    from depthinspace_b200 import _ops
+    net, _, _ = mods
+    hw, n, base = synth.DATASET_HW, 256, 8
+    fr = synth.make_frames(base, hw, "default", n_scales=4, seed=21)
+    lcn = net.LCN(5, 0.05)
+    gen = torch.Generator(device="cuda").manual_seed(3)
+    rep = lambda a: dev(a).repeat(n // base, 1, 1, 1)
+    im = rep(fr["im"])
+    disps = [(rep(p) + 0.3 * torch.randn(n, 1, *hw, device="cuda", generator=gen)).clamp_(0.01, 120.0) for p in fr["disp_pred"]]
+    im_l, im_s = lcn(im)
+    pat_l, _ = lcn(dev(fr["pattern"]))
+    # frame 5: make the target equal to the warped pattern of scale 0 -> zero photometric term for that scale
+    proj5, _, _, _ = _ops.pattern_warp(disps[0][5:6], pat_l)
+    im_l = im_l.clone()
+    im_l[5:6] = proj5
+
+    def run(dd, sl=slice(None)):
+        dd = [d[sl].contiguous() for d in dd]
+        out3, grads = _ops.pattern_loss_multi_forward(dd, im_l[sl].contiguous(), im_s[sl].contiguous(), pat_l, 9, "census_sad", 0.5, True)
+        return out3.double().cpu(), grads
+
+    a3, ag = run(disps)
+    b3, bg = run(disps)
+    assert torch.equal(a3, b3) and all(torch.equal(x, y) for x, y in zip(ag, bg)), "not bitwise reproducible"
+    q = n // 4
+    parts = [run(disps, slice(i * q, (i + 1) * q))[0] for i in range(4)]
+    for s in range(4):
+        assert_scalar_close(sum(p[s, 0] for p in parts).item(), a3[s, 0].item(), 2e-6, f"num scale {s}")
+        assert_scalar_close(sum(p[s, 1] for p in parts).item(), a3[s, 1].item(), 2e-6, f"den scale {s}")
+    assert float(ag[0][5].abs().max()) == 0.0, "estimate == target must give an exactly zero gradient"
+    one = run(disps, slice(5, 6))[0]
+    assert one[0, 0].item() == 0.0 and one[1, 0].item() > 0.0
+    # directional derivative of num_0 (sum of sigma * D over the batch)
+    direction = ag[0] / ag[0].abs().max()            # steepest ascent: every pixel contributes with the same sign
+    predicted = float((ag[0].double() * direction.double()).sum())
+    h = 2e-3
+    plus = run([disps[0] + h * direction] + disps[1:])[0][0, 0].item()
+    minus = run([disps[0] - h * direction] + disps[1:])[0][0, 0].item()
+    fd = (plus - minus) / (2 * h)
+    assert predicted > 0 and abs(fd - predicted) <= 5e-2 * predicted, (fd, predicted)
+    # a slice against the fp64 oracle
+    sl = slice(16, 18)
+    r = disps[1][sl].double().requires_grad_(True)
+    rv, _ = torch_port.pattern_loss(r, im_l[sl].double(), im_s[sl].double(), pat_l.double(), loss_type="census_sad")
+    o3, og = run(disps, sl)
+    assert_scalar_close(o3[1, 2].item(), rv.item(), name="slice value vs oracle")
+    rv.backward()
+    assert_close(og[1] / o3[1, 1].float().cuda(), r.grad, 5e-5, name="slice gradient vs oracle", outlier_frac=2e-3)
