@@ -903,3 +903,43 @@ def test_full_size_step_properties(mods):
     assert_scalar_close(o3[1, 2].item(), rv.item(), name="slice value vs oracle")
     rv.backward()
     assert_close(og[1] / o3[1, 1].float().cuda(), r.grad, 5e-5, name="slice gradient vs oracle", outlier_frac=2e-3)
+
+
+def test_full_size_lcn_smooth_warp_properties(mods):
+    """256 frames of 512x432 (LCN, smoothness) / 32 samples x 32 channels of 256x216 (flow warp): exact identities.
+    LCN of a constant frame is exactly 0 with std = sqrt(1e-6) + eps; LCN is shift invariant; the smoothness term is
+    exactly homogeneous under power-of-two scaling and ~0 for a constant disparity; a zero flow is the identity
+    and an integer translation a shift with zero fill (both up to the reference's 1e-5 px coordinate round trip)."""
+    from depthinspace_b200 import _ops
+    net, _, mf = mods
+    hw, n = synth.DATASET_HW, 256
+    gen = torch.Generator(device="cuda").manual_seed(11)
+    x = torch.rand(n, 1, *hw, device="cuda", generator=gen)
+    x[3] = 0.375
+    lcn, std = net.LCN(5, 0.05)(x)
+    assert float(lcn[3].abs().max()) == 0.0
+    assert torch.all(std[3] == std[3, 0, 0, 0]) and abs(float(std[3, 0, 0, 0]) - (1e-3 + 0.05)) < 1e-7
+    lcn_b, std_b = net.LCN(5, 0.05)(x + 0.25)
+    assert_close(lcn_b, lcn, 2e-5, "LCN shift invariance")
+    assert_close(std_b, std, 2e-5, "LCN std shift invariance")
+    # smoothness: homogeneous of degree 1, exact for powers of two
+    disp = torch.rand(n, 1, *hw, device="cuda", generator=gen) * 60
+    amb = torch.rand(n, 1, *hw, device="cuda", generator=gen)
+    a3, ag = _ops.smooth_loss_forward(disp, amb, True)
+    b3, bg = _ops.smooth_loss_forward(disp * 4.0, amb, True)
+    assert b3[0].item() == 4.0 * a3[0].item() and torch.equal(ag, bg), "smoothness must scale exactly with 4x"
+    c3, cg = _ops.smooth_loss_forward(torch.full_like(disp, 7.5), amb, True)
+    assert c3[0].item() <= 1e-7 * a3[0].item()      # Sobel weights (k / 240) cancel only up to fp32 rounding
+    # flow warp
+    bs, C, h, w = 32, 32, 256, 216
+    f = torch.randn(bs, C, h, w, device="cuda", generator=gen)
+    zero = torch.zeros(bs, 2, h, w, device="cuda")
+    # not bit-exact by design: the reference's normalise -> un-normalise round trip moves coordinates by ~1e-5 px
+    assert_close(mf.warp(f, zero), f, 1e-4, "zero flow")
+    shift = zero.clone()
+    shift[:, 0] = 3.0
+    shift[:, 1] = -2.0
+    out = mf.warp(f, shift)                      # out(v, u) = f(v - 2, u + 3), zeros outside
+    ref = torch.zeros_like(f)
+    ref[:, :, 2:, : w - 3] = f[:, :, : h - 2, 3:]
+    assert_close(out, ref, 1e-4, "integer translation")
