@@ -56,34 +56,13 @@ __device__ __forceinline__ float sobel5_adjoint(F u_at, int qy, int qx) {
   return acc;
 }
 
-// 4 horizontally adjacent Sobel responses from a 5 x 8 register window (rows r0..r4 of 8 floats each)
-__device__ __forceinline__ void sobel5_quad(const float (&win)[5][8], float (&gx)[4], float (&gy)[4]) {
-  constexpr float k[5][5] = {{SOB(-5.0), SOB(-4.0), 0.f, SOB(4.0), SOB(5.0)},
-                             {SOB(-8.0), SOB(-10.0), 0.f, SOB(10.0), SOB(8.0)},
-                             {SOB(-10.0), SOB(-20.0), 0.f, SOB(20.0), SOB(10.0)},
-                             {SOB(-8.0), SOB(-10.0), 0.f, SOB(10.0), SOB(8.0)},
-                             {SOB(-5.0), SOB(-4.0), 0.f, SOB(4.0), SOB(5.0)}};
-#pragma unroll
-  for (int q = 0; q < 4; ++q) {
-    float ax = 0.f, ay = 0.f;
-#pragma unroll
-    for (int i = 0; i < 5; ++i)
-#pragma unroll
-      for (int j = 0; j < 5; ++j) {
-        if (j != 2) ax = fmaf(k[i][j], win[i][q + j], ax);
-        if (i != 2) ay = fmaf(k[j][i], win[i][q + j], ay);
-      }
-    gx[q] = ax;
-    gy[q] = ay;
-  }
-}
-
 __device__ __forceinline__ void load_row8(const float* __restrict__ p, float (&r)[8]) {
   const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
   r[0] = a.x; r[1] = a.y; r[2] = a.z; r[3] = a.w; r[4] = b.x; r[5] = b.y; r[6] = b.z; r[7] = b.w;
 }
 
-// Packed variant of sobel5_quad: the window holds (disp, ambient) pairs, every FFMA2 advances both images.
+// 4 horizontally adjacent Sobel responses from a 5 x 8 register window of (disp, ambient) pairs: every FFMA2
+// advances both images.
 // out: gx2[q] = (sobel_x(disp), sobel_x(amb)), gy2[q] likewise, for 4 adjacent responses.
 __device__ __forceinline__ void sobel5_quad2(const u64 (&win)[5][8], u64 (&gx2)[4], u64 (&gy2)[4]) {
   constexpr float k[5][5] = {{SOB(-5.0), SOB(-4.0), 0.f, SOB(4.0), SOB(5.0)},
