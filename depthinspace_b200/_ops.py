@@ -308,6 +308,48 @@ def flow_warp_gather_backward(flows, grad_out, tidx):
     return gx
 
 
+def _flow_matrix_ptr_array(flows, tl, bs, H, W):
+    """flows: dict {(i, j): tensor} for all i != j -> ctypes array of tl*tl pointers (diagonal NULL) + keep-alive list"""
+    import ctypes
+    keep, ptrs = [], []
+    for i in range(tl):
+        for j in range(tl):
+            if i == j:
+                ptrs.append(None)
+                continue
+            f = _chk(flows[(i, j)], f"flow_{i}{j}")
+            if tuple(f.shape) != (bs, 2, H, W):
+                raise ValueError(f"flow_{i}{j} must be {(bs, 2, H, W)}, got {tuple(f.shape)}")
+            keep.append(f)
+            ptrs.append(f.data_ptr())
+    return keep, (ctypes.c_void_p * (tl * tl))(*ptrs)
+
+
+def flow_warp_gather_all_forward(x, flows):
+    """x [tl,bs,C,h,w]; flows {(i, j): flow_ij [bs,2,h,w]} -> out [tl,tl,bs,C,h,w], out[i] = gather for target frame i."""
+    x = _chk(x, "x", 5)
+    tl, bs, C, H, W = x.shape
+    keep, arr = _flow_matrix_ptr_array(flows, tl, bs, H, W)
+    out = torch.empty((tl, tl, bs, C, H, W), dtype=x.dtype, device=x.device)
+    with _on(x) as lib:
+        _lib.check(lib.dis_flow_warp_gather_all_forward(_ptr(x), arr, _ptr(out), tl, bs, C, H, W, _stream(x)),
+                   launches=2 if tl > 1 else 1)
+    return out
+
+
+def flow_warp_gather_all_backward(flows, grad_out):
+    grad_out = _chk(grad_out, "grad_out", 6)
+    tl, tl2, bs, C, H, W = grad_out.shape
+    if tl != tl2:
+        raise ValueError("grad_out must be [tl,tl,bs,C,h,w]")
+    keep, arr = _flow_matrix_ptr_array(flows, tl, bs, H, W)
+    gx = torch.empty((tl, bs, C, H, W), dtype=grad_out.dtype, device=grad_out.device)
+    with _on(grad_out) as lib:
+        _lib.check(lib.dis_flow_warp_gather_all_backward(arr, _ptr(grad_out), _ptr(gx), tl, bs, C, H, W, _stream(grad_out)),
+                   launches=2 if tl > 1 else 1)
+    return gx
+
+
 def lcn_backward(data, lcn, std, g_lcn, g_std, radius, eps):
     data, lcn, std = _chk(data, "data"), _chk(lcn, "lcn"), _chk(std, "std")
     N, C, H, W = data.shape

@@ -32,6 +32,8 @@ int flow_warp_forward(const float*, const float*, float*, float*, int32_t*, int3
 int flow_warp_backward(const float*, const float*, const float*, float*, float*, int, int, int, int, cudaStream_t);
 int flow_warp_gather_forward(const float*, const float* const*, float*, int, int, int, int, int, int, cudaStream_t);
 int flow_warp_gather_backward(const float* const*, const float*, float*, int, int, int, int, int, int, cudaStream_t);
+int flow_warp_gather_all_forward(const float*, const float* const*, float*, int, int, int, int, int, cudaStream_t);
+int flow_warp_gather_all_backward(const float* const*, const float*, float*, int, int, int, int, int, cudaStream_t);
 
 int flow_consistency_blocks_per_frame(int, int);
 int flow_consistency_forward(const float*, const float*, const float*, const float*, const float*, const float*,
@@ -389,6 +391,22 @@ int dis_flow_warp_gather_backward(const float* const* flows, const float* grad_o
   if (tl < 1 || tl > 8 || tidx < 0 || tidx >= tl || bs < 0 || C < 1 || H < 2 || W < 2) return DIS_ERR_BAD_SHAPE;
   if (bs == 0) return DIS_OK;
   return flow_warp_gather_backward(flows, grad_out, grad_x, tl, tidx, bs, C, H, W, as_stream(stream));
+}
+
+int dis_flow_warp_gather_all_forward(const float* x, const float* const* flows, float* out, int tl, int bs, int C, int H,
+                                     int W, void* stream) {
+  if (!x || !out || (!flows && tl > 1)) return DIS_ERR_NULL_POINTER;
+  if (tl < 1 || tl > 8 || bs < 0 || C < 1 || H < 2 || W < 2) return DIS_ERR_BAD_SHAPE;
+  if (bs == 0) return DIS_OK;
+  return flow_warp_gather_all_forward(x, flows, out, tl, bs, C, H, W, as_stream(stream));
+}
+
+int dis_flow_warp_gather_all_backward(const float* const* flows, const float* grad_out, float* grad_x, int tl, int bs,
+                                      int C, int H, int W, void* stream) {
+  if (!grad_out || !grad_x || (!flows && tl > 1)) return DIS_ERR_NULL_POINTER;
+  if (tl < 1 || tl > 8 || bs < 0 || C < 1 || H < 2 || W < 2) return DIS_ERR_BAD_SHAPE;
+  if (bs == 0) return DIS_OK;
+  return flow_warp_gather_all_backward(flows, grad_out, grad_x, tl, bs, C, H, W, as_stream(stream));
 }
 
 int dis_flow_consistency_num_partials(int bs, int H, int W) {

@@ -105,12 +105,15 @@ __global__ void __launch_bounds__(256) flow_warp_fwd_kernel(const float* __restr
   }
 }
 
-// Gather step of FuseNet (multi_frame_networks.py:187-214, 347-360) in one launch: output slot 0 is the own frame
-// (copied), slot k >= 1 is frame src[k] warped by flow[k]; x and out are [tl, bs, C, H, W], blockIdx.y = slot.
-constexpr int MAX_TL = 8;
+// Gather step of FuseNet (multi_frame_networks.py:187-214, 347-360) in one launch.  A slot table tells every
+// blockIdx.y which frame it reads (src), which slice of the stacked output it owns (dst) and which flow warps it
+// (flow == NULL: the own frame, a plain copy).  x is [tl,bs,C,H,W]; out is [n_dst,bs,C,H,W] with n_dst = tl for
+// one target frame and tl*tl for all of them (out[tidx*tl + k]).
+constexpr int MAX_TL = 8, MAX_SLOTS = MAX_TL * MAX_TL;
 struct GatherArgs {
-  const float* flow[MAX_TL];
-  int src[MAX_TL];
+  const float* flow[MAX_SLOTS];
+  short src[MAX_SLOTS];
+  short dst[MAX_SLOTS];
 };
 
 __global__ void __launch_bounds__(256) flow_warp_gather_fwd_kernel(const float* __restrict__ x, const __grid_constant__ GatherArgs g,
@@ -118,43 +121,46 @@ __global__ void __launch_bounds__(256) flow_warp_gather_fwd_kernel(const float* 
                                                                    float inv_w, float inv_h, size_t total, size_t slot_stride) {
   const size_t hw = (size_t)H * W;
   const int slot = blockIdx.y;
+  const float* flow = g.flow[slot];
   const float* xs = x + (size_t)g.src[slot] * slot_stride;
-  float* os = out + (size_t)slot * slot_stride;
+  float* os = out + (size_t)g.dst[slot] * slot_stride;
   for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
        idx += (size_t)gridDim.x * blockDim.x) {
     const size_t n = idx / hw;
     const int pix = (int)(idx - n * hw), h = pix / W, w = pix - h * W;
-    if (slot == 0) {
+    if (!flow) {
 #pragma unroll 8
       for (int c = 0; c < C; ++c) __stcs(os + (n * C + c) * hw + pix, ld_stream(xs + (n * C + c) * hw + pix));
     } else {
       Bilinear b;
       float fx, fy, o0, o1;
-      flow_bilinear(g.flow[slot], n, h, w, H, W, inv_w, inv_h, b, fx, fy);
+      flow_bilinear(flow, n, h, w, H, W, inv_w, inv_h, b, fx, fy);
       warp_pixel_fwd(xs + n * C * hw, os + n * C * hw + pix, b, C, H, W, hw, o0, o1);
     }
   }
 }
 
-// adjoint: gx[src[0]] = go[0]; gx[src[k]] += scatter(go[k]) (slices src[k >= 1] zero-filled by the launcher)
+// adjoint: copy slots  gx[src] = go[dst]  (plain stores);  warp slots  gx[src] += scatter(go[dst])  (RED.ADD).
+// A copy slot and a warp slot with the same src must not share a launch (the launcher orders them).
 __global__ void __launch_bounds__(256) flow_warp_gather_bwd_kernel(const float* __restrict__ go, const __grid_constant__ GatherArgs g,
                                                                    float* __restrict__ gx, int C, int H, int W,
                                                                    float inv_w, float inv_h, size_t total, size_t slot_stride) {
   const size_t hw = (size_t)H * W;
   const int slot = blockIdx.y;
-  const float* gs = go + (size_t)slot * slot_stride;
+  const float* flow = g.flow[slot];
+  const float* gs = go + (size_t)g.dst[slot] * slot_stride;
   float* xs = gx + (size_t)g.src[slot] * slot_stride;
   for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
        idx += (size_t)gridDim.x * blockDim.x) {
     const size_t n = idx / hw;
     const int pix = (int)(idx - n * hw), h = pix / W, w = pix - h * W;
-    if (slot == 0) {
+    if (!flow) {
 #pragma unroll 8
       for (int c = 0; c < C; ++c) xs[(n * C + c) * hw + pix] = ld_stream(gs + (n * C + c) * hw + pix);
     } else {
       Bilinear b;
       float fx, fy;
-      flow_bilinear(g.flow[slot], n, h, w, H, W, inv_w, inv_h, b, fx, fy);
+      flow_bilinear(flow, n, h, w, H, W, inv_w, inv_h, b, fx, fy);
       warp_pixel_bwd_x(gs + n * C * hw + pix, xs + n * C * hw, b, C, H, W, hw);
     }
   }
@@ -204,16 +210,41 @@ inline int flat_grid(size_t total) {
   return (int)(want < cap ? (want ? want : 1) : cap);
 }
 
+// slot table of one target frame: slot 0 = own frame, slot k = k-th other frame (flows[k-1] = flow_{tidx,j_k})
 int make_gather_args(const float* const* flows, int tl, int tidx, GatherArgs& g) {
   if (tl < 1 || tl > MAX_TL || tidx < 0 || tidx >= tl) return DIS_ERR_BAD_SHAPE;
-  g.src[0] = tidx;
+  g.src[0] = (short)tidx;
+  g.dst[0] = 0;
   g.flow[0] = nullptr;
   for (int j = 0, k = 1; j < tl; ++j) {
     if (j == tidx) continue;
     if (!flows[k - 1]) return DIS_ERR_NULL_POINTER;
-    g.src[k] = j;
+    g.src[k] = (short)j;
+    g.dst[k] = (short)k;
     g.flow[k] = flows[k - 1];
     ++k;
+  }
+  return DIS_OK;
+}
+
+// slot tables of ALL target frames: flows[i*tl + j] = flow_{ij} (diagonal ignored); copy slots and warp slots in
+// separate tables (the backward pass must finish the copies before the reductions start)
+int make_gather_all_args(const float* const* flows, int tl, GatherArgs& copies, GatherArgs& warps) {
+  if (tl < 1 || tl > MAX_TL) return DIS_ERR_BAD_SHAPE;
+  int nw = 0;
+  for (int i = 0; i < tl; ++i) {
+    copies.src[i] = (short)i;
+    copies.dst[i] = (short)(i * tl);
+    copies.flow[i] = nullptr;
+    for (int j = 0, k = 1; j < tl; ++j) {
+      if (j == i) continue;
+      if (!flows[i * tl + j]) return DIS_ERR_NULL_POINTER;
+      warps.src[nw] = (short)j;
+      warps.dst[nw] = (short)(i * tl + k);
+      warps.flow[nw] = flows[i * tl + j];
+      ++nw;
+      ++k;
+    }
   }
   return DIS_OK;
 }
@@ -246,6 +277,39 @@ int flow_warp_gather_backward(const float* const* flows, const float* go, float*
   flow_warp_gather_bwd_kernel<<<grid, 256, 0, s>>>(go, g, gx, C, H, W, 1.0f / (float)(W - 1), 1.0f / (float)(H - 1), total,
                                                    stride);
   return check_launch();
+}
+
+int flow_warp_gather_all_forward(const float* x, const float* const* flows, float* out, int tl, int bs, int C, int H, int W,
+                                 cudaStream_t s) {
+  GatherArgs copies, warps;
+  if (int rc = make_gather_all_args(flows, tl, copies, warps)) return rc;
+  const size_t total = (size_t)bs * H * W;
+  const float iw = 1.0f / (float)(W - 1), ih = 1.0f / (float)(H - 1);
+  flow_warp_gather_fwd_kernel<<<dim3(flat_grid(total), tl), 256, 0, s>>>(x, copies, out, C, H, W, iw, ih, total, total * C);
+  if (int rc = check_launch()) return rc;
+  if (tl > 1) {
+    flow_warp_gather_fwd_kernel<<<dim3(flat_grid(total), tl * (tl - 1)), 256, 0, s>>>(x, warps, out, C, H, W, iw, ih, total,
+                                                                                     total * C);
+    return check_launch();
+  }
+  return DIS_OK;
+}
+
+int flow_warp_gather_all_backward(const float* const* flows, const float* go, float* gx, int tl, int bs, int C, int H, int W,
+                                  cudaStream_t s) {
+  GatherArgs copies, warps;
+  if (int rc = make_gather_all_args(flows, tl, copies, warps)) return rc;
+  const size_t total = (size_t)bs * H * W;
+  const float iw = 1.0f / (float)(W - 1), ih = 1.0f / (float)(H - 1);
+  // gx[i] = go[i][0] first (no zero-fill needed), then every warped slot reduces into its source frame
+  flow_warp_gather_bwd_kernel<<<dim3(flat_grid(total), tl), 256, 0, s>>>(go, copies, gx, C, H, W, iw, ih, total, total * C);
+  if (int rc = check_launch()) return rc;
+  if (tl > 1) {
+    flow_warp_gather_bwd_kernel<<<dim3(flat_grid(total), tl * (tl - 1)), 256, 0, s>>>(go, warps, gx, C, H, W, iw, ih, total,
+                                                                                     total * C);
+    return check_launch();
+  }
+  return DIS_OK;
 }
 
 int flow_warp_forward(const float* x, const float* flow, float* out, float* fb_mask, int32_t* cx0, int32_t* cy0, int N,

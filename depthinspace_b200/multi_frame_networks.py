@@ -77,6 +77,31 @@ def gather_warped(x, flow, tidx, with_fb_mask=False):
     return out, torch.stack(masks, dim=0)
 
 
+class _GatherWarpedAll(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, keys, *flows):
+        ctx.keys = keys
+        ctx.save_for_backward(*flows)
+        return _ops.flow_warp_gather_all_forward(x, dict(zip(keys, flows)))
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        gx = _ops.flow_warp_gather_all_backward(dict(zip(ctx.keys, ctx.saved_tensors)), grad_out.contiguous())
+        return (gx, None) + (None,) * len(ctx.saved_tensors)
+
+
+def gather_warped_all(x, flow):
+    """gather_warped for every target frame at once: [tl, tl, bs, C, h, w] with out[tidx] == gather_warped(x, flow, tidx),
+    i.e. the `warped_feat` stack that Block2D3D.fwd_3d_1 / fwd_3d_2 build in their tidx loops (reference :376-404).
+    Two launches forward; the backward pass writes every frame's own-slot gradient and reduces the tl-1 scattered
+    ones on top in two launches (no zero-fill pass, no per-tidx gradient accumulation in autograd)."""
+    if isinstance(x, (list, tuple)):
+        x = torch.stack(list(x), dim=0)
+    tl = x.shape[0]
+    keys = tuple((i, j) for i in range(tl) for j in range(tl) if i != j)
+    return _GatherWarpedAll.apply(x, keys, *[flow[f'flow_{i}{j}'].detach() for (i, j) in keys])
+
+
 class _Conv3DGather(torch.autograd.Function):
     @staticmethod
     def forward(ctx, xyz, feat, mask, ksize, stride, neighbors):

@@ -173,6 +173,15 @@ DIS_API int dis_flow_warp_gather_backward(const float* const* flows, const float
                                           float* grad_x, int tl, int tidx, int bs, int C, int H, int W,
                                           void* stream);
 
+/* The same for ALL target frames at once (the tidx loop of Block2D3D.fwd_3d_1 / fwd_3d_2, :376-404, whose results the
+ * reference stacks into [tl,tl,bs,C,H,W]): out[tidx*tl + k] as above for every tidx; flows = HOST array of tl*tl
+ * device pointers, flows[i*tl + j] = flow_{ij} [bs,2,H,W] (diagonal ignored).  backward: grad_out [tl*tl,bs,C,H,W] ->
+ * grad_x [tl,bs,C,H,W] = every frame's own-slot gradient plus the tl-1 scattered ones, no zero-fill pass. */
+DIS_API int dis_flow_warp_gather_all_forward(const float* x, const float* const* flows, float* out, int tl,
+                                             int bs, int C, int H, int W, void* stream);
+DIS_API int dis_flow_warp_gather_all_backward(const float* const* flows, const float* grad_out,
+                                              float* grad_x, int tl, int bs, int C, int H, int W, void* stream);
+
 /* ---- a9  flow-consistency (geometric) loss, ONE direction (frame 0 -> frame 1) -------------------------
  * Single_Frame_Flow_Consistency_Loss.fwd / Multi_Frame_Flow_Consistency_Loss.fwd, model/networks.py:619-655,
  * 564-601 (+ ProjectionBaseLoss :455-488).  depth*, amb* [bs,C,H,W] (depth C=1), flow* [bs,2,H,W],

@@ -681,6 +681,25 @@ def test_gather_warped_matches_reference_composition(mods, tl, tidx, C):
     assert torch.equal(mf.gather_warped([x[i].detach() for i in range(tl)], flow, tidx), out)
 
 
+@pytest.mark.parametrize("tl,C,hw", [(4, 32, (64, 54)), (3, 5, (37, 50)), (2, 2, (16, 9)), (1, 3, (8, 8))])
+def test_gather_warped_all_equals_per_frame_gathers(mods, tl, C, hw):
+    """dis_flow_warp_gather_all_* == the tidx loop of Block2D3D.fwd_3d_1 (reference :376-389): forward bit for bit,
+    backward == autograd through tl separate gathers (sum of their gradients)."""
+    _, _, mf = mods
+    bs = 2
+    x = torch.randn(tl, bs, C, *hw, device="cuda", requires_grad=True)
+    flow = {f"flow_{i}{j}": dev(synth.make_flows(bs, hw, max_mag=5.0, seed=11 * i + j)[0]) for i in range(tl) for j in range(tl) if i != j}
+    out = mf.gather_warped_all(x, flow)
+    assert out.shape == (tl, tl, bs, C, *hw)
+    w = torch.randn_like(out)
+    (out * w).sum().backward()
+    xr = x.detach().clone().requires_grad_(True)
+    ref = torch.stack([mf.gather_warped(xr, flow, t) for t in range(tl)])
+    (ref * w).sum().backward()
+    assert torch.equal(out, ref)
+    assert_close(x.grad, xr.grad, 2e-6, "gradient of the all-frames gather")
+
+
 def test_gather_warped_rejects_bad_arguments(mods):
     from depthinspace_b200 import _ops
     x = torch.randn(3, 1, 2, 8, 9, device="cuda")

@@ -30,6 +30,7 @@ TL = 4
 HW = synth.DATASET_HW
 FEAT = ((HW[0] // 2, HW[1] // 2), (HW[0] // 4, HW[1] // 4))   # 256x216, 128x108
 C_FEAT, BLOCKS = 32, 4
+ALL_FRAMES = True
 
 
 def build(bs, dev):
@@ -57,7 +58,7 @@ def build(bs, dev):
     focal, baseline = float(g["K"][0, 0]), 0.075
     loss = losses.MultiFrameLoss(HW[0], HW[1], pattern, K=K, Ki=Ki, focal_length=focal, baseline=baseline).to(dev)
     lcn = networks.LCN(5, 0.05).to(dev)
-    feats, flows_lr, grads = [], [], []
+    feats, flows_lr, grads, grads_all = [], [], [], []
     gen = torch.Generator(device=dev).manual_seed(0)
     for (h, w) in FEAT:
         feats.append(torch.randn(TL, bs, C_FEAT, h, w, device=dev, generator=gen).requires_grad_(True))
@@ -65,9 +66,10 @@ def build(bs, dev):
         flows_lr.append({k: torch.nn.functional.interpolate(v, size=(h, w), mode="bilinear", align_corners=True) * sc
                          for k, v in flow.items()})
         grads.append(torch.randn(TL, bs, C_FEAT, h, w, device=dev, generator=gen))
+        grads_all.append(grads[-1][None].expand(TL, -1, -1, -1, -1, -1).contiguous())
     xyz = torch.randn(TL, bs, 3, *FEAT[0], device=dev, generator=gen)
     return dict(im=view(im), amb=view(amb), disp=view(disp), prim=view(dgt + 0.3), R=R, t=t, flow=flow, loss=loss, lcn=lcn,
-                feats=feats, flows_lr=flows_lr, grads=grads, xyz=xyz, bs=bs)
+                feats=feats, flows_lr=flows_lr, grads=grads, grads_all=grads_all, xyz=xyz, bs=bs)
 
 
 class Sections:
@@ -107,6 +109,11 @@ def step(w):
         x, fl, go = w["feats"][lvl], w["flows_lr"][lvl], w["grads"][lvl]
         x.grad = None
         for _ in range(BLOCKS):
+            if ALL_FRAMES:       # one gather for all target frames (the tidx loop of fwd_3d_1 / fwd_3d_2 as one op)
+                with torch.no_grad():
+                    mfn.gather_warped_all(x, fl)
+                mfn.gather_warped_all(x, fl).backward(w["grads_all"][lvl])
+                continue
             for tidx in range(TL):
                 with torch.no_grad():
                     mfn.gather_warped(x, fl, tidx)                                          # checkpointed forward
@@ -127,7 +134,10 @@ def main():
     ap.add_argument("--bs", type=int, nargs="+", default=[4, 32])
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--per-frame-gathers", action="store_true", help="one gather call per target frame (reference loop shape)")
     a = ap.parse_args()
+    global ALL_FRAMES
+    ALL_FRAMES = not a.per_frame_gathers
     dev = torch.device("cuda")
     for bs in a.bs:
         w = build(bs, dev)
@@ -148,7 +158,7 @@ def main():
         n = TL * bs
         print(json.dumps({"workload": "BASELINE configs[2]: DIS-MF hot path (copy_data LCN + 24 xyz/flow warps + 96 C=32 feature warps "
                                       "fwd/recompute/bwd + 1-scale census_sad loss + smoothness + 12 flow-consistency terms + L1), fwd+bwd",
-                          "bs": bs, "tl": TL, "frames": n, "ms_per_step": round(ms, 3), "frames_per_s": round(n / (ms * 1e-3), 1),
+                          "gather": "all frames per call" if ALL_FRAMES else "one call per target frame", "bs": bs, "tl": TL, "frames": n, "ms_per_step": round(ms, 3), "frames_per_s": round(n / (ms * 1e-3), 1),
                           "gpu_launches_per_step": launches, "sections": SEC.summary(a.steps), "loss": float(total.detach())}), flush=True)
         del w
         torch.cuda.empty_cache()
