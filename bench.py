@@ -52,6 +52,15 @@ def measured_traffic(kernel, frames):
         return None
 
 
+def measured_pipes(kernel):
+    """Pipe utilisation of the dominant kernel from the committed ncu capture (% of peak, sustained), or None."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            return json.load(f)[kernel]["pipes_pct_of_peak"]
+    except Exception:
+        return None
+
+
 def measured_peak():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -372,6 +381,7 @@ def run_ours(args):
                          "kernel": "pattern_multi_kernel<census_sad, R=4, 4 scales, grad>",
                          "kernel_ms": kernel_ms, "peak_source": peak_src,
                          "limiter": "XU (rsqrt) + FP32 issue, not HBM: ~100 rsqrt per pixel-scale (see DESIGN.md)",
+                         "pipes_pct_of_peak": measured_pipes("pattern_multi_kernel<census_sad, R=4, 4 scales, grad>"),
                          "step_algorithmic_gbs": step_gbs, "step_frac": step_gbs / peak},
             "cpu_baseline": cpu,
         }
