@@ -8,12 +8,14 @@
 // Ties (equal keys) are broken by the lowest candidate index; torch.topk(sorted=False) leaves them unspecified.
 // Backward is a deterministic gather (no atomics): every source element looks up the <= k*k output pixels whose
 // window contains it and adds the gradients of the slots that selected it.
+#include <cstdint>
 #include "common.cuh"
 
 namespace dis {
 namespace {
 
 constexpr int MAX_CAND = 64;
+constexpr int MAX_KK = 64;   // window positions k*k (api.cu admits k*k*tl <= 64)
 
 struct C3Args {
   const float* xyz; const float* feat; const float* mask;
@@ -43,15 +45,18 @@ __device__ __forceinline__ float plane_sq(const float v[3], const float cpl[3]) 
   return __fmaf_rn(d2, d2, __fmaf_rn(d1, d1, __fmul_rn(d0, d0)));
 }
 
-template <bool SELECT>
+// FIXED: the reference configuration (3 x 3 window, 4 frames = 36 candidates) with every loop unrolled, so that the
+// keys live in registers instead of a local-memory array
+template <bool SELECT, bool FIXED>
 __global__ void __launch_bounds__(128) conv3d_rank_kernel(C3Args a) {
   const int m = blockIdx.x * blockDim.x + threadIdx.x;
   const int M = a.bs * a.oh * a.ow;
   float local_max = 0.f;
   if (m < M) {
     const int b = m / (a.oh * a.ow), r = m - b * a.oh * a.ow, oy = r / a.ow, ox = r - oy * a.ow;
-    const int ncand = a.k * a.k * a.tl;
-    const int pad = (a.k - 1) / 2;
+    const int kw = FIXED ? 3 : a.k, tl = FIXED ? 4 : a.tl;
+    const int ncand = FIXED ? 36 : a.k * a.k * a.tl;
+    const int pad = (kw - 1) / 2;
     // centre candidate: (ky, kx) = (pad, pad), t = 0   (tidx = (k*k // 2) * tl, :491)
     int cy, cx; bool cin;
     cand_pos(a, oy, ox, pad, pad, cy, cx, cin);
@@ -59,12 +64,12 @@ __global__ void __launch_bounds__(128) conv3d_rank_kernel(C3Args a) {
     load_xyz(a, 0, b, cy, cx, cin, cxyz);
     const float cden = cxyz[2] + 1e-12f;
     const float cpl[3] = {__fdiv_rn(cxyz[0], cden), __fdiv_rn(cxyz[1], cden), __fdiv_rn(cxyz[2], cden)};
-    float key[MAX_CAND];
+    float key[FIXED ? 36 : MAX_CAND];
     const float big = SELECT ? __ldg(a.gmax) + 1.0f : 0.f;
     const size_t hw = (size_t)a.h * a.w;
-#pragma unroll 1
+#pragma unroll (FIXED ? 36 : 1)
     for (int c = 0; c < ncand; ++c) {
-      const int t = c % a.tl, kk = c / a.tl, ky = kk / a.k, kx = kk - ky * a.k;   // index = (ky*k + kx)*tl + t, :485
+      const int t = c % tl, kk = c / tl, ky = kk / kw, kx = kk - ky * kw;   // index = (ky*k + kx)*tl + t, :485
       int y, x; bool in;
       cand_pos(a, oy, ox, ky, kx, y, x, in);
       float v[3];
@@ -81,13 +86,14 @@ __global__ void __launch_bounds__(128) conv3d_rank_kernel(C3Args a) {
       uint64_t taken = 0;
       for (int j = 0; j < a.nb; ++j) {
         int best = -1; float bk = 0.f;
+#pragma unroll (FIXED ? 36 : 1)
         for (int c = 0; c < ncand; ++c) {
-          if ((taken >> c) & 1) continue;
-          if (best < 0 || key[c] < bk) { best = c; bk = key[c]; }
+          const bool better = !((taken >> c) & 1) && (best < 0 || key[c] < bk);   // ties: lowest index wins
+          if (better) { best = c; bk = key[c]; }
         }
         taken |= (uint64_t)1 << best;
         a.idx[(size_t)m * a.nb + j] = (uint8_t)best;
-        const int t = best % a.tl, kk = best / a.tl, ky = kk / a.k, kx = kk - ky * a.k;
+        const int t = best % tl, kk = best / tl, ky = kk / kw, kx = kk - ky * kw;
         int y, x; bool in;
         cand_pos(a, oy, ox, ky, kx, y, x, in);
         float v[3];
@@ -106,20 +112,47 @@ __global__ void __launch_bounds__(128) conv3d_rank_kernel(C3Args a) {
   }
 }
 
-// feat_nb[m, j, :] = feat[t, b, :, y, x] of the selected candidate (zeros when it lies in the padding)
-__global__ void __launch_bounds__(256) conv3d_feat_gather_kernel(C3Args a) {
-  const size_t total = (size_t)a.bs * a.oh * a.ow * a.nb;
+// feat_nb[m, j, :] = feat[t, b, :, y, x] of the selected candidate (zeros when it lies in the padding).
+// The source is channel-planar (stride h*w between channels), the destination channel-contiguous, so the copy is a
+// transpose.  One WARP owns a (32 consecutive output pixels) x (one slot) item: it reads with lanes = pixels
+// (neighbouring pixels pick neighbouring candidates: mostly the same 128-byte lines) with all 32 channel loads in
+// flight, turns the 32 x 32 tile around in its private slice of shared memory (__syncwarp only, no CTA barrier) and
+// writes with lanes = channels, one full 128-byte line per pixel.
+constexpr int FT = 32, FW = 8;   // pixels per item, warps per CTA
+__global__ void __launch_bounds__(32 * FW) conv3d_feat_gather_kernel(C3Args a) {
+  __shared__ float tiles[FW][32][FT + 1];
+  const int M = a.bs * a.oh * a.ow;
   const size_t hw = (size_t)a.h * a.w;
-  for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < total; i += (size_t)gridDim.x * 256) {
-    const int m = (int)(i / a.nb);
-    const int b = m / (a.oh * a.ow), r = m - b * a.oh * a.ow, oy = r / a.ow, ox = r - oy * a.ow;
-    const int c = a.idx[i];
-    const int t = c % a.tl, kk = c / a.tl, ky = kk / a.k, kx = kk - ky * a.k;
-    int y, x; bool in;
-    cand_pos(a, oy, ox, ky, kx, y, x, in);
-    float* o = a.feat_nb + i * a.C;
-    const float* src = a.feat + ((size_t)(t * a.bs + b) * a.C) * hw + (size_t)y * a.w + x;
-    for (int ch = 0; ch < a.C; ++ch) o[ch] = in ? __ldg(src + ch * hw) : 0.f;
+  const int lane = threadIdx.x & 31, wv = threadIdx.x >> 5;
+  float (*tile)[FT + 1] = tiles[wv];
+  const size_t items = (size_t)((M + FT - 1) / FT) * a.nb;
+  for (size_t it = (size_t)blockIdx.x * FW + wv; it < items; it += (size_t)gridDim.x * FW) {
+    const int j = (int)(it % a.nb), m0 = (int)(it / a.nb) * FT, m = m0 + lane;
+    long long off = -1;                              // element offset of channel 0 of my pixel's candidate
+    if (m < M) {
+      const int b = m / (a.oh * a.ow), r = m - b * a.oh * a.ow, oy = r / a.ow, ox = r - oy * a.ow;
+      const int c = a.idx[(size_t)m * a.nb + j];
+      const int t = c % a.tl, kk = c / a.tl, ky = kk / a.k, kx = kk - ky * a.k;
+      int y, x; bool in;
+      cand_pos(a, oy, ox, ky, kx, y, x, in);
+      if (in) off = (long long)((size_t)(t * a.bs + b) * a.C * hw + (size_t)y * a.w + x);
+    }
+    for (int c0 = 0; c0 < a.C; c0 += 32) {
+      const int nc = min(32, a.C - c0);
+      float v[32];
+#pragma unroll
+      for (int ch = 0; ch < 32; ++ch) v[ch] = (off >= 0 && ch < nc) ? __ldg(a.feat + off + (size_t)(c0 + ch) * hw) : 0.f;
+#pragma unroll
+      for (int ch = 0; ch < 32; ++ch) tile[ch][lane] = v[ch];
+      __syncwarp();
+      const int np = min(FT, M - m0);
+      if (lane < nc) {
+        float* o = a.feat_nb + ((size_t)m0 * a.nb + j) * a.C + c0 + lane;
+#pragma unroll 8
+        for (int p = 0; p < np; ++p) __stcs(o + (size_t)p * a.nb * a.C, tile[lane][p]);
+      }
+      __syncwarp();
+    }
   }
 }
 
@@ -138,7 +171,7 @@ __global__ void __launch_bounds__(256) conv3d_gather_bwd_kernel(C3BwdArgs a) {
     const int tb = (int)(i / hw), pix = (int)(i - (size_t)tb * hw), y = pix / a.w, x = pix - y * a.w;
     const int t = tb / a.bs, b = tb - t * a.bs;
     float gx[3] = {0.f, 0.f, 0.f};
-    int match[16];      // (m * nb + j) of the slots that picked this element; <= k*k of them
+    int match[MAX_KK];  // (m * nb + j) of the slots that picked this element; <= k*k of them
     int nmatch = 0;
     for (int ky = 0; ky < a.k; ++ky)
       for (int kx = 0; kx < a.k; ++kx) {
@@ -150,7 +183,7 @@ __global__ void __launch_bounds__(256) conv3d_gather_bwd_kernel(C3BwdArgs a) {
         const int m = (b * a.oh + oy) * a.ow + ox;
         const int cand = (ky * a.k + kx) * a.tl + t;
         for (int j = 0; j < a.nb; ++j)
-          if (a.idx[(size_t)m * a.nb + j] == cand) { if (nmatch < 16) match[nmatch++] = m * a.nb + j; break; }
+          if (a.idx[(size_t)m * a.nb + j] == cand) { match[nmatch++] = m * a.nb + j; break; }
       }
     if (a.g_xyz) {
       for (int q = 0; q < nmatch; ++q)
@@ -172,6 +205,89 @@ __global__ void __launch_bounds__(256) conv3d_gather_bwd_kernel(C3BwdArgs a) {
   }
 }
 
+// g_feat[t, b, :, y, x] = sum of g_feat_nb over the slots that selected (t, b, y, x): the transpose of the forward
+// copy, with the same warp-private scheme.  A warp takes 32 consecutive pixels of one (t, b) plane: with lanes = pixels
+// it finds, per window position, the slot that picked the pixel; then a quarter-warp per pixel sums the matching rows
+// of g_feat_nb with 128-bit loads (8 lanes x float4 = one 32-channel row, 4 pixels per instruction, 9 in flight); the
+// sums go through the warp's shared-memory tile and are written with lanes = pixels.  Deterministic: fixed summation
+// order, no atomics.  Needs C % 4 == 0 and a window of at most 5 x 5 (else conv3d_gather_bwd_kernel does the work).
+constexpr int BW = 4, BKK = 25;
+template <int KK, bool S1>   // KK = 9: the reference's 3 x 3 window, fully unrolled (0: generic); S1: stride == 1
+__global__ void __launch_bounds__(32 * BW) conv3d_feat_bwd_kernel(C3BwdArgs a, int z0) {
+  __shared__ float tiles[BW][32][FT + 1];
+  __shared__ int smatch[BW][BKK][FT];
+  const size_t hw = (size_t)a.h * a.w;
+  const int lane = threadIdx.x & 31, wv = threadIdx.x >> 5;
+  const int tb = z0 + blockIdx.y, t = tb / a.bs, b = tb - t * a.bs;
+  const int pix0 = (blockIdx.x * BW + wv) * FT;
+  if (pix0 >= (int)hw) return;                       // whole warp
+  float (*tile)[FT + 1] = tiles[wv];
+  int (*match)[FT] = smatch[wv];
+  const int pad = (a.k - 1) / 2, kk2 = KK > 0 ? KK : a.k * a.k, kw = KK == 9 ? 3 : a.k;
+  const int pix = pix0 + lane;
+  const int y = pix / a.w, x = pix - y * a.w;
+#pragma unroll
+  for (int kk = 0; kk < kk2; ++kk) {
+    const int ky = kk / kw, kx = kk - ky * kw;
+    int found = -1;
+    // output pixel (oy, ox) sees (y, x) as candidate (ky, kx) iff oy*stride + ky - pad == y
+    const int ny = y - ky + pad, nx = x - kx + pad;
+    const bool on_grid = S1 || (ny % a.stride == 0 && nx % a.stride == 0);
+    if (pix < (int)hw && ny >= 0 && nx >= 0 && on_grid) {
+      const int oy = S1 ? ny : ny / a.stride, ox = S1 ? nx : nx / a.stride;
+      if (oy < a.oh && ox < a.ow) {
+        const int m = (b * a.oh + oy) * a.ow + ox;
+        const int cand = kk * a.tl + t;
+        const uint8_t* row = a.idx + (size_t)m * a.nb;
+        // no early exit: the loads of one row are independent (a candidate occupies at most one slot)
+#pragma unroll 9
+        for (int j = 0; j < a.nb; ++j)
+          if (__ldg(row + j) == cand) found = m * a.nb + j;
+      }
+    }
+    match[kk][lane] = found;
+  }
+  __syncwarp();
+  const int pp = lane >> 3, cq = lane & 7;           // pixel within the group of 4, channel quad
+  for (int c0 = 0; c0 < a.C; c0 += 32) {
+    const int nc = min(32, a.C - c0);
+    const bool live = 4 * cq < nc;
+    const float* src = a.g_feat_nb + c0 + 4 * cq;
+    for (int p0 = 0; p0 < FT; p0 += 4) {
+      float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (live) {
+        if (KK > 0) {
+          float4 v[KK > 0 ? KK : 1];
+#pragma unroll
+          for (int q = 0; q < KK; ++q) {
+            const int mt = match[q][p0 + pp];
+            v[q] = mt >= 0 ? __ldg(reinterpret_cast<const float4*>(src + (size_t)mt * a.C)) : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+#pragma unroll
+          for (int q = 0; q < KK; ++q) { sum.x += v[q].x; sum.y += v[q].y; sum.z += v[q].z; sum.w += v[q].w; }
+        } else {
+          for (int kk = 0; kk < kk2; ++kk) {
+            const int mt = match[kk][p0 + pp];
+            if (mt >= 0) {
+              const float4 v = __ldg(reinterpret_cast<const float4*>(src + (size_t)mt * a.C));
+              sum.x += v.x; sum.y += v.y; sum.z += v.z; sum.w += v.w;
+            }
+          }
+        }
+      }
+      tile[4 * cq][p0 + pp] = sum.x; tile[4 * cq + 1][p0 + pp] = sum.y;
+      tile[4 * cq + 2][p0 + pp] = sum.z; tile[4 * cq + 3][p0 + pp] = sum.w;
+    }
+    __syncwarp();
+    if (pix < (int)hw) {
+      float* o = a.g_feat + ((size_t)tb * a.C + c0) * hw + pix;
+#pragma unroll 8
+      for (int ch = 0; ch < nc; ++ch) o[(size_t)ch * hw] = tile[ch][lane];
+    }
+    __syncwarp();
+  }
+}
+
 inline int flat_grid(size_t total, int threads) {
   const size_t want = (total + threads - 1) / threads, cap = 148 * 32;
   return (int)(want < cap ? (want ? want : 1) : cap);
@@ -189,9 +305,14 @@ int conv3d_gather_forward(const float* xyz, const float* feat, const float* mask
   const int M = bs * a.oh * a.ow;
   cudaError_t e = cudaMemsetAsync(gmax, 0, sizeof(float), s);
   if (e != cudaSuccess) { set_last_cuda_error(e); return DIS_ERR_CUDA_LAUNCH; }
-  conv3d_rank_kernel<false><<<(M + 127) / 128, 128, 0, s>>>(a);
-  conv3d_rank_kernel<true><<<(M + 127) / 128, 128, 0, s>>>(a);
-  conv3d_feat_gather_kernel<<<flat_grid((size_t)M * nb, 256), 256, 0, s>>>(a);
+  if (k == 3 && tl == 4) {
+    conv3d_rank_kernel<false, true><<<(M + 127) / 128, 128, 0, s>>>(a);
+    conv3d_rank_kernel<true, true><<<(M + 127) / 128, 128, 0, s>>>(a);
+  } else {
+    conv3d_rank_kernel<false, false><<<(M + 127) / 128, 128, 0, s>>>(a);
+    conv3d_rank_kernel<true, false><<<(M + 127) / 128, 128, 0, s>>>(a);
+  }
+  conv3d_feat_gather_kernel<<<flat_grid((size_t)((M + FT - 1) / FT) * nb, FW), 32 * FW, 0, s>>>(a);
   return check_launch();
 }
 
@@ -199,8 +320,26 @@ int conv3d_gather_backward(const float* g_xyz_nb, const float* g_feat_nb, const 
                            int tl, int bs, int C, int h, int w, int k, int stride, int nb, cudaStream_t s) {
   C3BwdArgs a{g_xyz_nb, g_feat_nb, idx, g_xyz, g_feat, tl, bs, C, h, w, k, stride, nb,
               conv3d_out_size(h, k, stride), conv3d_out_size(w, k, stride)};
-  conv3d_gather_bwd_kernel<<<flat_grid((size_t)tl * bs * h * w, 256), 256, 0, s>>>(a);
-  return check_launch();
+  const bool fast_feat = g_feat && k * k <= BKK && C % 4 == 0 && (reinterpret_cast<uintptr_t>(g_feat_nb) & 15) == 0;
+  if (g_xyz || (g_feat && !fast_feat)) {
+    C3BwdArgs ax = a;
+    if (fast_feat) ax.g_feat = nullptr;
+    if (!g_xyz) ax.g_xyz = nullptr;
+    conv3d_gather_bwd_kernel<<<flat_grid((size_t)tl * bs * h * w, 256), 256, 0, s>>>(ax);
+    if (int rc = check_launch()) return rc;
+  }
+  if (fast_feat) {
+    const int tiles = (h * w + FT - 1) / FT;
+    for (int z0 = 0; z0 < tl * bs; z0 += 65535) {
+      const int nz = tl * bs - z0 < 65535 ? tl * bs - z0 : 65535;
+      const dim3 grid((tiles + BW - 1) / BW, nz);
+      if (k == 3 && stride == 1) conv3d_feat_bwd_kernel<9, true><<<grid, 32 * BW, 0, s>>>(a, z0);
+      else if (k == 3) conv3d_feat_bwd_kernel<9, false><<<grid, 32 * BW, 0, s>>>(a, z0);
+      else conv3d_feat_bwd_kernel<0, false><<<grid, 32 * BW, 0, s>>>(a, z0);
+      if (int rc = check_launch()) return rc;
+    }
+  }
+  return DIS_OK;
 }
 
 }  // namespace dis

@@ -70,6 +70,29 @@ def main():
         go = torch.randn_like(feat)
         report(f"flow_warp_forward C=32 {h}x{w}", timeit(lambda: _ops.flow_warp_forward(feat, f)), (8 + 8 * 32) * p * bs, samples=bs)
         report(f"flow_warp_backward(x) C=32 {h}x{w}", timeit(lambda: _ops.flow_warp_backward(None, f, go, True, False)), (8 + 8 * 32) * p * bs, samples=bs)
+    # FuseNet gather (own frame + 3 warped neighbours per target frame) and the Conv3D neighbour selection behind it
+    tl, bs, C, h, w = 4, 32, 32, 256, 216
+    p = h * w
+    feat5 = torch.randn(tl, bs, C, h, w, device=dev)
+    fl = {(i, j): torch.from_numpy(synth.make_flows(bs, (h, w), max_mag=6.0, seed=3 * i + j)[0]).to(dev)
+          for i in range(tl) for j in range(tl) if i != j}
+    go6 = torch.randn(tl, tl, bs, C, h, w, device=dev)
+    report("flow_warp_gather_all_forward tl=4 C=32 256x216", timeit(lambda: _ops.flow_warp_gather_all_forward(feat5, fl)),
+           4 * C * p * bs * (tl + tl * tl), samples=bs)
+    report("flow_warp_gather_all_backward tl=4 C=32 256x216", timeit(lambda: _ops.flow_warp_gather_all_backward(fl, go6)),
+           4 * C * p * bs * (tl + tl * tl), samples=bs)
+    del go6
+    bs = 4
+    xyz = torch.randn(tl, bs, 3, h, w, device=dev)
+    feat4 = torch.randn(tl, bs, C, h, w, device=dev)
+    mask = (torch.rand(tl, bs, 1, h, w, device=dev) > 0.2).float()
+    xyz_nb, feat_nb, idx, _ = _ops.conv3d_gather_forward(xyz, feat4, mask, 3, 1, 9)
+    nb_bytes = 4 * (3 + C) * 9 * p * bs
+    report("conv3d_gather_forward tl=4 C=32 256x216 (top-9 of 36)", timeit(lambda: _ops.conv3d_gather_forward(xyz, feat4, mask, 3, 1, 9)),
+           4 * (3 + C + 1) * tl * p * bs + nb_bytes + 9 * p * bs, samples=bs)
+    g_nb = torch.randn_like(feat_nb)
+    report("conv3d_gather_backward(feat) tl=4 C=32 256x216", timeit(lambda: _ops.conv3d_gather_backward(None, g_nb, idx, (tl, bs, C, h, w), 3, 1, 9, False, True)),
+           4 * C * 9 * p * bs + 9 * p * bs + 4 * C * tl * p * bs, samples=bs)
     # flow-consistency loss, one pair, both directions
     bs = 64
     gm = synth.make_geometry(2, (H, W), seed=1)
