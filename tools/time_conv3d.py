@@ -1,4 +1,5 @@
-"""Runs the Conv3D neighbour gather (forward + feature backward) three times on realistic geometry; meant to be run under\n`ncu --metrics gpu__time_duration.sum -k regex:conv3d` for per-kernel times."""
+"""Runs the Conv3D neighbour gather (forward + feature backward) three times on realistic geometry; meant to be run under
+`ncu --metrics gpu__time_duration.sum -k regex:conv3d` for per-kernel times."""
 import os, sys, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from depthinspace_b200 import _ops
