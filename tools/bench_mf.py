@@ -129,35 +129,72 @@ def step(w):
     return total
 
 
+def build_sf(bs, dev):
+    """DIS-SF loss with its geometric terms (single_frame_worker.py:101-149): 4 scales + smoothness + 6 pairs x 2 directions."""
+    w = build(bs, dev)
+    n = TL * bs
+    fr = synth.make_frames(min(n, 8), HW, "default", n_scales=4, seed=42)
+    rep = lambda a: torch.from_numpy(np.concatenate([a] * ((n + 7) // 8))[:n]).to(dev)
+    w["disps"] = [rep(p).view(TL, bs, 1, *HW) for p in fr["disp_pred"]]
+    old = w["loss"]
+    pattern = old.ph_loss.pattern.repeat(1, 3, 1, 1)
+    g = synth.make_geometry(1, HW, seed=5)
+    K = torch.from_numpy(g["K"].astype(np.float64))
+    w["loss"] = losses.SingleFrameLoss(HW[0], HW[1], pattern, K=K, Ki=torch.linalg.inv(K), focal_length=float(g["K"][0, 0]),
+                                       baseline=0.075).to(dev)
+    for k in ("feats", "flows_lr", "grads", "grads_all", "xyz"):
+        w.pop(k)
+    return w
+
+
+def step_sf(w):
+    SEC.mark("start")
+    im_cat, std = w["lcn"].prepare_input(w["im"].transpose(0, 1).contiguous())
+    SEC.mark("copy_data_ms")
+    disps = [d.detach().requires_grad_(True) for d in w["disps"]]
+    vals = w["loss"](disps, im_cat, std, w["amb"], R=w["R"], t=w["t"], flow_out=w["flow"])
+    total = torch.stack([v.reshape(()) for v in vals]).sum()
+    total.backward()
+    SEC.mark("loss_ms")
+    return total
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--bs", type=int, nargs="+", default=[4, 32])
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--per-frame-gathers", action="store_true", help="one gather call per target frame (reference loop shape)")
+    ap.add_argument("--sf", action="store_true", help="time the DIS-SF loss WITH its 12 flow-consistency terms instead (bs 64 = 256 frames)")
     a = ap.parse_args()
     global ALL_FRAMES
     ALL_FRAMES = not a.per_frame_gathers
     dev = torch.device("cuda")
+    run_step = step_sf if a.sf else step
+    if a.sf and a.bs == [4, 32]:
+        a.bs = [64]
     for bs in a.bs:
-        w = build(bs, dev)
+        w = build_sf(bs, dev) if a.sf else build(bs, dev)
         for _ in range(a.warmup):
-            total = step(w)
+            total = run_step(w)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         torch.cuda.synchronize()
         l0 = _lib.LAUNCHES
         SEC.marks, SEC.on = [], True
         e0.record()
         for _ in range(a.steps):
-            total = step(w)
+            total = run_step(w)
         e1.record()
         torch.cuda.synchronize()
         SEC.on = False
         ms = e0.elapsed_time(e1) / a.steps
         launches = (_lib.LAUNCHES - l0) // a.steps
         n = TL * bs
-        print(json.dumps({"workload": "BASELINE configs[2]: DIS-MF hot path (copy_data LCN + 24 xyz/flow warps + 96 C=32 feature warps "
-                                      "fwd/recompute/bwd + 1-scale census_sad loss + smoothness + 12 flow-consistency terms + L1), fwd+bwd",
+        name = ("DIS-SF loss path with geometric terms (copy_data LCN + 4 x census_sad 9x9 + smoothness + 12 flow-consistency terms), fwd+bwd"
+                if a.sf else
+                "BASELINE configs[2]: DIS-MF hot path (copy_data LCN + 24 xyz/flow warps + 96 C=32 feature warps "
+                "fwd/recompute/bwd + 1-scale census_sad loss + smoothness + 12 flow-consistency terms + L1), fwd+bwd")
+        print(json.dumps({"workload": name,
                           "gather": "all frames per call" if ALL_FRAMES else "one call per target frame", "bs": bs, "tl": TL, "frames": n, "ms_per_step": round(ms, 3), "frames_per_s": round(n / (ms * 1e-3), 1),
                           "gpu_launches_per_step": launches, "sections": SEC.summary(a.steps), "loss": float(total.detach())}), flush=True)
         del w
