@@ -205,6 +205,15 @@ def run_ours(args):
     disps = [p.to(dev).requires_grad_(True) for p in h_disp]
 
     def step(im_d, amb_d, disps_d):
+        """LCN + fused loss/gradient kernels: every term of the assembly and d(total)/d(disparity map) for all 4 scales
+        (losses.SingleFrameLoss.value_and_grad; the gradients are what autograd.backward(outs, grads) feeds DispNet)."""
+        im_l, im_s = lcn(im_d)
+        vals, grads = loss.value_and_grad(disps_d, im_l, im_s, amb_d, global_frames=n * world)
+        step.grads = grads
+        return torch.stack(vals).sum()
+
+    def autograd_step(im_d, amb_d, disps_d):
+        """The same through the nn.Module / autograd surface (forward() + backward(), five gradient-scaling passes)."""
         for d in disps_d:
             d.grad = None
         im_l, im_s = lcn(im_d)
@@ -244,6 +253,20 @@ def run_ours(args):
             torch.cuda.synchronize()
     ms = ev0.elapsed_time(ev1)
     loss_value = float(total.detach())
+
+    # ---- the same work through the nn.Module / autograd surface (forward() + backward()) ----
+    for _ in range(2):
+        autograd_step(im, amb, disps)
+    a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    a0.record()
+    for _ in range(args.steps):
+        a_total = autograd_step(im, amb, disps)
+    a1.record()
+    torch.cuda.synchronize()
+    autograd_ms = a0.elapsed_time(a1) / args.steps
+    grad_gap = max(float((g.view_as(d) - d.grad).abs().max() / d.grad.abs().max()) for g, d in zip(step.grads, disps))
+    assert abs(float(a_total.detach()) - loss_value) <= 2e-6 * abs(loss_value) and grad_gap < 1e-5, (grad_gap, loss_value)
 
     # ---- the same step captured once into a CUDA graph and replayed (launch gaps and Python overhead removed) ----
     graph_ms = None
@@ -368,13 +391,14 @@ def run_ours(args):
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"BASELINE configs[1]: DIS-SF loss path, {n} frames/GPU (bs 64 x tl 4), {HW[0]}x{HW[1]}, "
-                                   "default pattern, LCN r5 + 4 x (pattern warp + census_sad 9x9, sigma-weighted) + smoothness, fwd+bwd",
+                                   "default pattern, LCN r5 + 4 x (pattern warp + census_sad 9x9, sigma-weighted) + smoothness, "
+                                   "loss terms + gradients w.r.t. all 4 disparity maps (SingleFrameLoss.value_and_grad)",
                        "frames_per_gpu": n, "l2": "inputs (2.7 GB/step) exceed the 126 MB L2; no flush needed",
                        "loss": loss_value},
             "clocks": clocks.summary(),
             "e2e": {"value": e2e_value, "unit": UNIT,
                     "h2d_bytes_per_step": int((2 + N_SCALES) * 4 * P * n), "d2h_bytes_per_step": 4},
-            "gpu_launches": launches, "cuda_graph_ms_per_step": graph_ms,
+            "gpu_launches": launches, "cuda_graph_ms_per_step": graph_ms, "autograd_modules_ms_per_step": autograd_ms,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": measured_traffic("pattern_multi_kernel<census_sad, R=4, 4 scales, grad>", n),
                          "algorithmic_bytes": KERNEL_ALGO_BYTES_PER_FRAME * P * n,

@@ -33,6 +33,7 @@ SIGNATURES = {
     "dis_reduce_pairs_batched": [_f, _i, _i, _f, _st],
     "dis_pattern_loss_multi_num_partials": [_i, _i, _i],
     "dis_pattern_loss_multi_forward": [_c.POINTER(_c.c_void_p), _i, _f, _f, _f, _c.POINTER(_c.c_void_p), _f, _i, _i, _i, _i, _i, _fl, _st],
+    "dis_pattern_loss_multi_forward_scaled": [_c.POINTER(_c.c_void_p), _i, _f, _f, _f, _c.POINTER(_c.c_void_p), _f, _f, _i, _i, _i, _i, _i, _fl, _st],
     "dis_scale_by_device_scalar": [_f, _f, _sz, _f, _f, _st],
     "dis_mul": [_f, _f, _f, _sz, _st],
     "dis_l1_num_partials": [_sz],
@@ -41,6 +42,7 @@ SIGNATURES = {
     "dis_sobel_backward": [_f, _f, _i, _i, _i, _i, _st],
     "dis_smooth_loss_num_partials": [_i, _i, _i],
     "dis_smooth_loss_forward": [_f, _f, _f, _f, _i, _i, _i, _st],
+    "dis_smooth_loss_forward_scaled": [_f, _f, _f, _f, _i, _i, _i, _fl, _i, _st],
     "dis_flow_warp_forward": [_f, _f, _f, _f, _f, _f, _i, _i, _i, _i, _st],
     "dis_flow_warp_backward": [_f, _f, _f, _f, _f, _i, _i, _i, _i, _st],
     "dis_flow_warp_gather_forward": [_f, _c.POINTER(_c.c_void_p), _f, _i, _i, _i, _i, _i, _i, _st],

@@ -144,9 +144,10 @@ def pattern_loss_forward(disp, im, std, pattern, block_size, type, eps, want_pro
     return out3, proj, diff, gnum
 
 
-def pattern_loss_multi_forward(disps, im, std, pattern, block_size, type, eps, want_grad):
+def pattern_loss_multi_forward(disps, im, std, pattern, block_size, type, eps, want_grad, grad_scale=None):
     """S = 2 or 4 disparity maps of the same frames, census types only.
-    -> (out3 [S,3] rows (num_s, den, num_s/den), list of grad_num | None)"""
+    -> (out3 [S,3] rows (num_s, den, num_s/den), list of grad_num | None)
+    grad_scale: optional device tensor of S floats; grad_num[s] is multiplied by it inside the kernel (final gradients)."""
     import ctypes
     S = len(disps)
     disps = [_chk(d, f"disp[{i}]") for i, d in enumerate(disps)]
@@ -170,8 +171,13 @@ def pattern_loss_multi_forward(disps, im, std, pattern, block_size, type, eps, w
         npart = lib.dis_pattern_loss_multi_num_partials(N, H, W)
         partials = torch.empty(2 * S * max(npart, 1), dtype=torch.float32, device=im.device)
         s = _stream(im)
-        _lib.check(lib.dis_pattern_loss_multi_forward(d_arr, S, _ptr(im), _ptr(std), _ptr(pattern), g_arr, _ptr(partials),
-                                                      N, H, W, int(block_size), loss_type_id(type), float(eps), s))
+        if grad_scale is not None:
+            grad_scale = _chk(grad_scale, "grad_scale", 1)
+            if grad_scale.numel() != S:
+                raise ValueError(f"grad_scale must have {S} elements")
+        _lib.check(lib.dis_pattern_loss_multi_forward_scaled(d_arr, S, _ptr(im), _ptr(std), _ptr(pattern), g_arr,
+                                                             _ptr(grad_scale), _ptr(partials), N, H, W, int(block_size),
+                                                             loss_type_id(type), float(eps), s))
         _lib.check(lib.dis_reduce_pairs_batched(_ptr(partials), npart, S, _ptr(out3), s))
     return out3, grads
 
@@ -186,10 +192,16 @@ def scale_by_device_scalar(x, numer, denom=None):
     return out
 
 
+def abs_sum(a):
+    """-> out3 [sum|a|, count, mean] (device tensor, no host sync); the sigma normaliser of the photometric terms."""
+    return l1_forward(a, None, False)[0]
+
+
 def l1_forward(a, b, want_grad):
-    """-> (out3 [sum|a-b|, count, mean], sign(a-b) | None)"""
-    a, b = _chk(a, "a", None), _chk(b, "b", None)
-    if a.shape != b.shape:
+    """-> (out3 [sum|a-b|, count, mean], sign(a-b) | None); b = None means 0"""
+    a = _chk(a, "a", None)
+    b = _chk(b, "b", None) if b is not None else None
+    if b is not None and a.shape != b.shape:
         b = b.expand_as(a).contiguous()
     sgn = torch.empty_like(a) if want_grad else None
     out3 = torch.empty(3, dtype=torch.float32, device=a.device)
@@ -230,19 +242,26 @@ def sobel_backward(grad_out, ksize):
     return gx
 
 
-def smooth_loss_forward(disp, im, want_grad):
-    """-> (out3 [sum, count, mean], grad_sum|None)"""
+def smooth_loss_forward(disp, im, want_grad, grad_scale=1.0, accumulate_into=None):
+    """-> (out3 [sum, count, mean], grad_sum * grad_scale | None); accumulate_into: an existing gradient tensor of disp's
+    shape that the scaled gradient is ADDED to (returned in place of a fresh tensor)."""
     disp, im = _chk(disp, "disp"), _chk(im, "im")
     if disp.shape != im.shape or disp.shape[1] != 1:
         raise ValueError(f"disp and im must both be [N,1,H,W]; got {tuple(disp.shape)} and {tuple(im.shape)}")
     N, _, H, W = disp.shape
-    gsum = torch.empty_like(disp) if want_grad else None
+    if accumulate_into is not None:
+        gsum = _chk(accumulate_into, "accumulate_into")
+        if gsum.shape != disp.shape or gsum.data_ptr() != accumulate_into.data_ptr():
+            raise ValueError("accumulate_into must be a contiguous tensor of disp's shape")
+    else:
+        gsum = torch.empty_like(disp) if want_grad else None
     out3 = torch.empty(3, dtype=torch.float32, device=disp.device)
     with _on(disp) as lib:
         npart = lib.dis_smooth_loss_num_partials(N, H, W)
         partials = torch.empty(2 * max(npart, 1), dtype=torch.float32, device=disp.device)
         s = _stream(disp)
-        _lib.check(lib.dis_smooth_loss_forward(_ptr(disp), _ptr(im), _ptr(gsum), _ptr(partials), N, H, W, s))
+        _lib.check(lib.dis_smooth_loss_forward_scaled(_ptr(disp), _ptr(im), _ptr(gsum), _ptr(partials), N, H, W,
+                                                      float(grad_scale), int(accumulate_into is not None), s))
         _lib.check(lib.dis_reduce_pairs(_ptr(partials), npart, _ptr(out3), s))
     return out3, gsum
 

@@ -25,7 +25,7 @@ int mul(const float*, const float*, float*, size_t, cudaStream_t);
 int l1_num_partials(size_t);
 int l1_forward(const float*, const float*, float*, float*, size_t, cudaStream_t);
 int smooth_loss_num_partials(int, int, int);
-int smooth_loss_forward(const float*, const float*, float*, float*, int, int, int, cudaStream_t);
+int smooth_loss_forward(const float*, const float*, float*, float*, int, int, int, float, int, cudaStream_t);
 int sobel_forward(const float*, float*, int, int, int, int, cudaStream_t);
 int sobel_backward(const float*, float*, int, int, int, int, cudaStream_t);
 int flow_warp_forward(const float*, const float*, float*, float*, int32_t*, int32_t*, int, int, int, int, cudaStream_t);
@@ -267,6 +267,14 @@ int dis_pattern_loss_multi_num_partials(int N, int H, int W) {
 int dis_pattern_loss_multi_forward(const float* const* disps, int S, const float* im, const float* std_in,
                                    const float* pattern, float* const* grad_nums, float* partials, int N, int H,
                                    int W, int block_size, int type, float eps, void* stream) {
+  return dis_pattern_loss_multi_forward_scaled(disps, S, im, std_in, pattern, grad_nums, nullptr, partials, N, H, W,
+                                               block_size, type, eps, stream);
+}
+
+int dis_pattern_loss_multi_forward_scaled(const float* const* disps, int S, const float* im, const float* std_in,
+                                          const float* pattern, float* const* grad_nums, const float* grad_scale,
+                                          float* partials, int N, int H, int W, int block_size, int type, float eps,
+                                          void* stream) {
   if (int rc = check_block(block_size, type)) return rc;
   if (type != CENSUS_MSE && type != CENSUS_SAD) return DIS_ERR_UNSUPPORTED_COMBINATION;
   if (S != 2 && S != 4) return DIS_ERR_UNSUPPORTED_COMBINATION;
@@ -293,6 +301,7 @@ int dis_pattern_loss_multi_forward(const float* const* disps, int S, const float
     }
     a.im = im + n0 * hw; a.std_in = std_in ? std_in + n0 * hw : nullptr; a.pattern = pattern;
     a.partials = partials;
+    a.grad_scale = grad_scale;
     a.N = N - n0 < MAX_GRID_Z ? N - n0 : MAX_GRID_Z; a.H = H; a.W = W;
     a.num_blocks = N * per_frame; a.block_offset = n0 * per_frame;
     a.eps = eps; a.inv_k2 = 1.0f / (float)(block_size * block_size);
@@ -313,7 +322,7 @@ int dis_scale_by_device_scalar(const float* in, float* out, size_t n, const floa
 int dis_l1_num_partials(size_t n) { return l1_num_partials(n); }
 
 int dis_l1_forward(const float* a, const float* b, float* sign_out, float* partials, size_t n, void* stream) {
-  if (!a || !b || !partials) return DIS_ERR_NULL_POINTER;
+  if (!a || !partials) return DIS_ERR_NULL_POINTER;   // b == NULL: sum |a|
   if (n == 0) return DIS_ERR_BAD_SHAPE;
   return l1_forward(a, b, sign_out, partials, n, as_stream(stream));
 }
@@ -347,6 +356,11 @@ int dis_smooth_loss_num_partials(int N, int H, int W) {
 
 int dis_smooth_loss_forward(const float* disp, const float* im, float* grad_sum, float* partials, int N, int H,
                             int W, void* stream) {
+  return dis_smooth_loss_forward_scaled(disp, im, grad_sum, partials, N, H, W, 1.0f, 0, stream);
+}
+
+int dis_smooth_loss_forward_scaled(const float* disp, const float* im, float* grad_sum, float* partials, int N, int H,
+                                   int W, float grad_scale, int accumulate, void* stream) {
   if (!disp || !im || !partials) return DIS_ERR_NULL_POINTER;
   if (N < 0 || H < 1 || W < 1) return DIS_ERR_BAD_SHAPE;
   if (N == 0) return DIS_OK;
@@ -355,7 +369,7 @@ int dis_smooth_loss_forward(const float* disp, const float* im, float* grad_sum,
   for (int n0 = 0; n0 < N; n0 += MAX_GRID_Z) {
     const int nb = N - n0 < MAX_GRID_Z ? N - n0 : MAX_GRID_Z;
     if (int rc = smooth_loss_forward(disp + n0 * hw, im + n0 * hw, grad_sum ? grad_sum + n0 * hw : nullptr,
-                                     partials + (size_t)2 * n0 * per_frame, nb, H, W, as_stream(stream)))
+                                     partials + (size_t)2 * n0 * per_frame, nb, H, W, grad_scale, accumulate, as_stream(stream)))
       return rc;
   }
   return DIS_OK;

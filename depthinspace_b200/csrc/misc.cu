@@ -67,7 +67,7 @@ __global__ void __launch_bounds__(256) mul_kernel(const float* __restrict__ a, c
   const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   for (size_t i = t; i < n4; i += stride) {
     const float4 u = __ldcs(reinterpret_cast<const float4*>(a) + i);
-    const float4 v = __ldcs(reinterpret_cast<const float4*>(b) + i);
+    const float4 v = b ? __ldcs(reinterpret_cast<const float4*>(b) + i) : make_float4(0.f, 0.f, 0.f, 0.f);
     __stcs(reinterpret_cast<float4*>(out) + i, make_float4(u.x * v.x, u.y * v.y, u.z * v.z, u.w * v.w));
   }
   for (size_t i = 4 * n4 + t; i < n; i += stride) out[i] = a[i] * b[i];
@@ -84,14 +84,14 @@ __global__ void __launch_bounds__(256) l1_kernel(const float* __restrict__ a, co
   float s = 0.f, c = 0.f;
   for (size_t i = t; i < n4; i += stride) {
     const float4 u = __ldcs(reinterpret_cast<const float4*>(a) + i);
-    const float4 v = __ldcs(reinterpret_cast<const float4*>(b) + i);
+    const float4 v = b ? __ldcs(reinterpret_cast<const float4*>(b) + i) : make_float4(0.f, 0.f, 0.f, 0.f);
     const float d0 = u.x - v.x, d1 = u.y - v.y, d2 = u.z - v.z, d3 = u.w - v.w;
     s += (fabsf(d0) + fabsf(d1)) + (fabsf(d2) + fabsf(d3));
     c += 4.0f;
     if (sgn) __stcs(reinterpret_cast<float4*>(sgn) + i, make_float4(sign0(d0), sign0(d1), sign0(d2), sign0(d3)));
   }
   for (size_t i = 4 * n4 + t; i < n; i += stride) {
-    const float d = a[i] - b[i];
+    const float d = a[i] - (b ? b[i] : 0.f);
     s += fabsf(d);
     c += 1.0f;
     if (sgn) sgn[i] = sign0(d);

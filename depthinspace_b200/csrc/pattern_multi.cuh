@@ -43,6 +43,7 @@ struct PatternMultiArgs {
   const float* im;
   const float* std_in;
   const float* pattern;
+  const float* grad_scale;       // optional device float[S]: the stored gradient of scale s is multiplied by it
   float* partials;               // [S][num_blocks][2] = (num_s, den)
   int N, H, W;
   int num_blocks;                // CTAs of the whole call (stride between scales in `partials`)
@@ -156,6 +157,9 @@ __global__ void __launch_bounds__(256, 2) pattern_multi_kernel(PatternMultiArgs 
 
   const float fs = fwd_scale<TYPE>() * a.inv_k2;
   const float gs = -0.5f * a.eps * a.inv_k2;
+  float gss[S];                  // census chain-rule constant x the caller's per-scale factor (weight / sum of sigma)
+#pragma unroll
+  for (int s = 0; s < S; ++s) gss[s] = (GRAD && a.grad_scale) ? gs * __ldg(a.grad_scale + s) : gs;
   const u64 eps2 = bc2(a.eps);
   float num[S], den = 0.0f;
 #pragma unroll
@@ -277,7 +281,7 @@ __global__ void __launch_bounds__(256, 2) pattern_multi_kernel(PatternMultiArgs 
         for (int h = 0; h < 2; ++h) {
           const int s = 2 * p + h;
           if (valid) num[s] = fmaf(wc[i], acc[p][i][h] * fs, num[s]);
-          if (GRAD) gout[s][i] = (h ? g1 : g0) * gs * sdd[(s * MTH + ly) * MTW + 2 * tx + i];
+          if (GRAD) gout[s][i] = (h ? g1 : g0) * gss[s] * sdd[(s * MTH + ly) * MTW + 2 * tx + i];
         }
       }
     }

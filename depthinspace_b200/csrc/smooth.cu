@@ -107,7 +107,7 @@ constexpr int PIN = 74, PU = U_P;
 template <bool GRAD>
 __global__ void __launch_bounds__(SNT) smooth_loss_kernel(const float* __restrict__ disp, const float* __restrict__ im,
                                                           float* __restrict__ grad_sum, float* __restrict__ partials,
-                                                          int H, int W, int vec_ok) {
+                                                          int H, int W, int vec_ok, float grad_scale, int accumulate) {
   __shared__ __align__(16) float2 sin[IN_H * PIN];
   __shared__ __align__(16) float sux[GRAD ? U_H * PU : 4];
   __shared__ __align__(16) float suy[GRAD ? U_H * PU : 4];
@@ -207,6 +207,17 @@ __global__ void __launch_bounds__(SNT) smooth_loss_kernel(const float* __restric
         }
       }
       float* o = go + (size_t)gy * W + gx;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) acc[c] *= grad_scale;      // 1 for the plain sum; weight / count for a final gradient
+      if (accumulate) {                                       // add to a gradient another term already left there
+        if (vec_ok && gx + 3 < W) {
+          const float4 old = *reinterpret_cast<const float4*>(o);
+          acc[0] += old.x; acc[1] += old.y; acc[2] += old.z; acc[3] += old.w;
+        } else {
+#pragma unroll
+          for (int c = 0; c < 4; ++c) if (gx + c < W) acc[c] += o[c];
+        }
+      }
       if (vec_ok && gx + 3 < W) __stcs(reinterpret_cast<float4*>(o), make_float4(acc[0], acc[1], acc[2], acc[3]));
       else {
 #pragma unroll
@@ -300,11 +311,11 @@ inline int flat_grid(size_t total) {
 int smooth_loss_num_partials(int N, int H, int W) { return N * ((H + STH - 1) / STH) * ((W + STW - 1) / STW); }
 
 int smooth_loss_forward(const float* disp, const float* im, float* grad_sum, float* partials, int N, int H, int W,
-                        cudaStream_t s) {
+                        float grad_scale, int accumulate, cudaStream_t s) {
   dim3 grid((W + STW - 1) / STW, (H + STH - 1) / STH, N);
   const int vec_ok = (W % 4 == 0) && ((reinterpret_cast<uintptr_t>(grad_sum) & 15) == 0);
-  if (grad_sum) smooth_loss_kernel<true><<<grid, SNT, 0, s>>>(disp, im, grad_sum, partials, H, W, vec_ok);
-  else smooth_loss_kernel<false><<<grid, SNT, 0, s>>>(disp, im, nullptr, partials, H, W, vec_ok);
+  if (grad_sum) smooth_loss_kernel<true><<<grid, SNT, 0, s>>>(disp, im, grad_sum, partials, H, W, vec_ok, grad_scale, accumulate);
+  else smooth_loss_kernel<false><<<grid, SNT, 0, s>>>(disp, im, nullptr, partials, H, W, vec_ok, grad_scale, 0);
   return check_launch();
 }
 

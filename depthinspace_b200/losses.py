@@ -75,11 +75,82 @@ class _HotPathLoss(torch.nn.Module):
         return vals
 
 
+    # ---- fused value + gradient (no autograd graph, no scaling passes) -------------------------------------------------
+    def _value_and_grad(self, out, im_lcn, std, ambient, l1_target, l1_weights, global_frames=None):
+        """Loss terms and their FINAL gradients w.r.t. every disparity map in one pass per kernel.
+        The assembly knows its own weights (1/2^s, smooth_weight, ...), so the kernels store weight * d term / d disp
+        directly: the denominators are known before the launch (sum of sigma: one streaming reduction of `std`; the
+        smoothness count is 2*N*H*W), which removes autograd's five gradient-scaling passes over the batch.
+        -> (list of 0-dim terms exactly like forward(), list of gradients shaped like `out`).  Continue into the network
+        with  torch.autograd.backward(out, grads).  Geometric terms are not part of this path (use forward()).
+        global_frames: frames of the whole data-parallel batch (all ranks); if omitted with a process group it is
+        all-reduced and read back (one host sync).  Nothing else touches the host: the call can be graph-captured."""
+        from .parallel import all_reduce_sum_
+        if not isinstance(out, (tuple, list)):
+            out = [out]
+        ph = self.ph_loss
+        type_id = _ops.loss_type_id(ph.loss_type)
+        S = len(out)
+        if type_id < 2 or S not in (2, 4):
+            raise ValueError("value_and_grad covers the census losses with 2 or 4 scales; use forward() otherwise")
+        im, std_m, amb = _merge(im_lcn)[:, 0:1].contiguous(), _merge(std), _merge(ambient)
+        disps = [_merge(o).detach() for o in out]
+        dev, group = im.device, ph.process_group
+        ph.pattern = ph.pattern.to(device=dev, dtype=torch.float32)
+        n_local = disps[0].shape[0]
+        hw = disps[0].shape[-1] * disps[0].shape[-2]
+        if group is None:
+            n_global = n_local
+        elif global_frames is not None:
+            n_global = int(global_frames)
+        else:
+            count = torch.full((1,), float(n_local), device=dev)
+            all_reduce_sum_(count, group)
+            n_global = int(round(float(count)))
+        if std_m is not None:
+            den = _ops.abs_sum(std_m)[0:1].clone()
+            if group is not None:
+                all_reduce_sum_(den, group)
+        else:
+            den = torch.full((1,), float(n_global * hw), device=dev)
+        key = (S, str(dev))
+        if getattr(self, "_w_ph_key", None) != key:      # constant weights 1 / 2^s, uploaded once
+            self._w_ph, self._w_ph_key = torch.tensor([1.0 / 2 ** s for s in range(S)], device=dev), key
+        w_ph = self._w_ph
+        out3, grads = _ops.pattern_loss_multi_forward(disps, im, std_m, ph.pattern, ph.block_size, type_id, ph.loss_eps, True,
+                                                      grad_scale=(w_ph / den).contiguous())
+        num = out3[:, 0].contiguous()
+        if group is not None:
+            all_reduce_sum_(num, group)
+        vals = list((num / den * w_ph).unbind(0))                      # reference :108-115, weights 1 / 2^s
+        # smoothness on scale 0: mean over 2 * N * H * W elements (:118-124)
+        per_frame = 2.0 * hw
+        s3, _ = _ops.smooth_loss_forward(disps[0], amb.contiguous(), True, grad_scale=self.smooth_weight / (per_frame * n_global),
+                                         accumulate_into=grads[0])
+        ssum = s3[0:1].clone()
+        if group is not None:
+            all_reduce_sum_(ssum, group)
+        vals.append(ssum[0] * (self.smooth_weight / (per_frame * n_global)))
+        if l1_target is not None:                                      # pseudo-GT / primary-disparity L1 terms
+            tgt = _merge(l1_target).detach()
+            for s, wgt in l1_weights:
+                o3, sgn = _ops.l1_forward(disps[s], tgt, True)
+                cnt = o3[1:2].clone()
+                tot = o3[0:1].clone()
+                if group is not None:
+                    all_reduce_sum_(cnt, group)
+                    all_reduce_sum_(tot, group)
+                vals.append(tot[0] / cnt[0] * wgt)
+                grads[s].add_(_ops.scale_by_device_scalar(sgn, torch.full((1,), wgt, device=dev), cnt).view_as(grads[s]))
+        return vals, [g.view_as(o) for g, o in zip(grads, out)]
+
+
 class SingleFrameLoss(_HotPathLoss):
     """out: list of per-scale disparities (all full resolution, model/networks.py:290-295).
     With R, t ([tl,bs,3,3], [tl,bs,3]) and flow_out ({'flow_ij': [bs,2,H,W]}) the 6 x 2 geometric terms are added
     in the reference's position (after smoothness, before the pseudo-GT terms); `out` must then be [tl,bs,1,H,W]."""
     ge_class = Single_Frame_Flow_Consistency_Loss
+    smooth_weight = 0.4
 
     def forward(self, out, im_lcn, std, ambient, pseudo_gt=None, R=None, t=None, flow_out=None):
         if not isinstance(out, (tuple, list)):
@@ -87,7 +158,7 @@ class SingleFrameLoss(_HotPathLoss):
         im, std, amb = _merge(im_lcn)[:, 0:1], _merge(std), _merge(ambient)
         ph = self.ph_loss.forward_multi([_merge(o) for o in out], im, std)   # :108-115, all scales fused
         vals = [v / (2 ** s) for s, v in enumerate(ph)]
-        vals.append(self.disparity_loss(_merge(out[0]), amb) * 0.4)   # :118-124 (scale 0 only)
+        vals.append(self.disparity_loss(_merge(out[0]), amb) * self.smooth_weight)   # :118-124 (scale 0 only)
         if flow_out is not None:                                      # :127-149
             vals += self._geometric_terms(out[0], R, t, ambient, flow_out)
         if pseudo_gt is not None:                                     # :152-155 (DIS-FTSF)
@@ -95,9 +166,16 @@ class SingleFrameLoss(_HotPathLoss):
                 vals.append(l1_mean(o, pseudo_gt) * 0.1 / (2 ** s))
         return vals
 
+    def value_and_grad(self, out, im_lcn, std, ambient, pseudo_gt=None, global_frames=None):
+        """Same terms as forward() (without geometric terms) plus d(sum of terms)/d out[s], see _value_and_grad."""
+        n = len(out) if isinstance(out, (tuple, list)) else 1
+        return self._value_and_grad(out, im_lcn, std, ambient, pseudo_gt, [(s, 0.1 / 2 ** s) for s in range(n)],
+                                    global_frames)
+
 
 class MultiFrameLoss(_HotPathLoss):
     ge_class = Multi_Frame_Flow_Consistency_Loss
+    smooth_weight = 0.8
 
     def forward(self, out, im_lcn, std, ambient, primary_disp=None, R=None, t=None, flow_out=None, warmup=True):
         if not isinstance(out, (tuple, list)):
@@ -105,7 +183,7 @@ class MultiFrameLoss(_HotPathLoss):
         im, std, amb = _merge(im_lcn)[:, 0:1], _merge(std), _merge(ambient)
         ph = self.ph_loss.forward_multi([_merge(o) for o in out], im, std)   # :110-117
         vals = [v / (2 ** s) for s, v in enumerate(ph)]
-        vals.append(self.disparity_loss(_merge(out[0]), amb) * 0.8)   # :120-126
+        vals.append(self.disparity_loss(_merge(out[0]), amb) * self.smooth_weight)   # :120-126
         if flow_out is not None:                                      # :128-157 (needs primary_disp)
             vals += self._geometric_terms(out[0], R, t, ambient, flow_out, primary_disp=primary_disp)
         if primary_disp is not None and warmup:                       # :160-165 (first two epochs)

@@ -122,6 +122,14 @@ DIS_API int dis_pattern_loss_multi_forward(const float* const* disps, int S, con
                                            const float* std_in, const float* pattern,
                                            float* const* grad_nums, float* partials, int N, int H, int W,
                                            int block_size, int type, float eps, void* stream);
+/* Same, with the stored gradients already final: grad_nums[s] = grad_scale[s] * d(num_s)/d disp_s, grad_scale a DEVICE
+ * array of S floats (typically weight_s / sum(sigma), sum(sigma) from dis_l1_forward(std, NULL)): the loss assembly
+ * (model/single_frame_worker.py:108-115) knows its weights, so no separate scaling pass over the gradients is needed. */
+DIS_API int dis_pattern_loss_multi_forward_scaled(const float* const* disps, int S, const float* im,
+                                                  const float* std_in, const float* pattern,
+                                                  float* const* grad_nums, const float* grad_scale,
+                                                  float* partials, int N, int H, int W, int block_size,
+                                                  int type, float eps, void* stream);
 
 /* out[i] = in[i] * (*numer) / (*denom) (denom may be NULL = 1).  Scalars live on the device
  * so no host synchronisation is needed between forward and backward. */
@@ -132,6 +140,7 @@ DIS_API int dis_scale_by_device_scalar(const float* in, float* out, size_t n, co
  * dis_reduce_pairs -> mean in out3[2]); sign_out (optional) = sign(a - b), the gradient of the sum w.r.t. a. */
 DIS_API int dis_l1_num_partials(size_t n);
 DIS_API int dis_l1_forward(const float* a, const float* b, float* sign_out, float* partials, size_t n, void* stream);
+/* b may be NULL (treated as 0): sum |a|, e.g. the sigma normaliser of the photometric terms. */
 /* out[i] = a[i] * b[i] */
 DIS_API int dis_mul(const float* a, const float* b, float* out, size_t n, void* stream);
 
@@ -147,6 +156,11 @@ DIS_API int dis_sobel_backward(const float* grad_out, float* grad_x, int N, int 
 DIS_API int dis_smooth_loss_num_partials(int N, int H, int W);
 DIS_API int dis_smooth_loss_forward(const float* disp, const float* im, float* grad_sum,
                                     float* partials, int N, int H, int W, void* stream);
+/* grad_sum multiplied by grad_scale on the way out (weight / (2*N*H*W) makes it the final gradient of the term);
+ * accumulate != 0: added to what grad_sum already holds (the photometric gradient of scale 0) instead of overwriting. */
+DIS_API int dis_smooth_loss_forward_scaled(const float* disp, const float* im, float* grad_sum,
+                                           float* partials, int N, int H, int W, float grad_scale,
+                                           int accumulate, void* stream);
 
 /* ---- a6  warp(x, flow), model/multi_frame_networks.py:83-99 ---------------------------
  * x [N,C,H,W], flow [N,2,H,W] -> out [N,C,H,W]; bilinear, zeros padding, align_corners.

@@ -962,3 +962,46 @@ def test_full_size_lcn_smooth_warp_properties(mods):
     ref = torch.zeros_like(f)
     ref[:, :, 2:, : w - 3] = f[:, :, : h - 2, 3:]
     assert_close(out, ref, 1e-4, "integer translation")
+
+
+@pytest.mark.parametrize("n_scales,pgt,hw", [(4, False, (64, 80)), (2, True, (37, 52)), (4, True, (48, 64))])
+def test_value_and_grad_equals_autograd_assembly(mods, n_scales, pgt, hw):
+    """SingleFrameLoss.value_and_grad (final gradients written by the forward kernels, no scaling passes) ==
+    forward() + autograd: same terms, same gradients."""
+    from depthinspace_b200 import losses
+    tl, bs = 2, 2
+    d, im_l, im_s, pat = _frames(tl * bs, hw, "kinect", seed=31, scales=n_scales)
+    view = lambda a: dev(a).view(tl, bs, *a.shape[1:])
+    im_cat = torch.cat((view(im_l), view(d["im"])), dim=2)
+    pgt_t = view((d["disp_gt"] + 0.1).astype(np.float32)) if pgt else None
+    loss = losses.SingleFrameLoss(hw[0], hw[1], dev(np.repeat(pat, 3, axis=1)))
+    outs = [view(p).requires_grad_(True) for p in d["disp_pred"]]
+    vals = loss(outs, im_cat, view(im_s), view(d["ambient"]), pseudo_gt=pgt_t)
+    sum(vals).backward()
+    fvals, grads = loss.value_and_grad([o.detach() for o in outs], im_cat, view(im_s), view(d["ambient"]), pseudo_gt=pgt_t)
+    assert len(fvals) == len(vals) and len(grads) == n_scales
+    for k, (a, b) in enumerate(zip(fvals, vals)):
+        assert_scalar_close(a.item(), b.item(), 2e-6, f"term {k}")
+    for s in range(n_scales):
+        assert grads[s].shape == outs[s].shape
+        assert_close(grads[s], outs[s].grad, 2e-6, f"gradient scale {s}")
+    # the gradients plug into autograd of whatever produced the disparities
+    net_out = [o.detach().clone().requires_grad_(True) for o in outs]
+    torch.autograd.backward([n * 1.0 for n in net_out], grads)
+    assert_close(net_out[0].grad, outs[0].grad, 2e-6, "through autograd.backward")
+
+
+def test_smooth_loss_accumulates_into_existing_gradient(mods):
+    from depthinspace_b200 import _ops
+    hw = (45, 70)
+    gen = torch.Generator(device="cuda").manual_seed(5)
+    disp = torch.rand(3, 1, *hw, device="cuda", generator=gen) * 40
+    amb = torch.rand(3, 1, *hw, device="cuda", generator=gen)
+    base = torch.randn(3, 1, *hw, device="cuda", generator=gen)
+    _, g = _ops.smooth_loss_forward(disp, amb, True)
+    acc = base.clone()
+    _, g2 = _ops.smooth_loss_forward(disp, amb, True, grad_scale=0.25, accumulate_into=acc)
+    assert g2.data_ptr() == acc.data_ptr()
+    assert_close(acc, base + 0.25 * g, 1e-6, "accumulated smoothness gradient")
+    s3 = _ops.abs_sum(amb - 0.5)
+    assert_scalar_close(s3[0].item(), float((amb - 0.5).abs().double().sum()), 1e-6, "abs_sum")
