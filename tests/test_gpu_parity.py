@@ -1005,3 +1005,60 @@ def test_smooth_loss_accumulates_into_existing_gradient(mods):
     assert_close(acc, base + 0.25 * g, 1e-6, "accumulated smoothness gradient")
     s3 = _ops.abs_sum(amb - 0.5)
     assert_scalar_close(s3[0].item(), float((amb - 0.5).abs().double().sum()), 1e-6, "abs_sum")
+
+
+# ----------------------------------------------------------------------------- seeded random sweep over ragged shapes
+def _sweep_cases(n, seed):
+    rng = np.random.default_rng(seed)
+    cases = []
+    for i in range(n):
+        H, W = int(rng.integers(2, 90)), int(rng.integers(2, 140))
+        cases.append((i, H, W, int(rng.integers(1, 4)), int(rng.choice([1, 3, 5, 7, 9, 11, 13, 15])), str(rng.choice(TYPES))))
+    return cases
+
+
+@pytest.mark.parametrize("i,H,W,N,k,t", _sweep_cases(24, 2024))
+def test_random_shape_sweep_vs_c_oracle(mods, i, H, W, N, k, t):
+    """Random (seeded) image sizes from 2 px up, batch sizes, window sizes and loss types through every kernel of the
+    single-frame path, each against the C oracle: ext photometric fwd/bwd, fused pattern loss, LCN, smoothness."""
+    from depthinspace_b200 import _ops
+    net, ext, _ = mods
+    rng = np.random.default_rng(1000 + i)
+    tid = c_oracle.TYPES[t]
+    sad = t in ("sad", "census_sad")
+    es, ta = rng.standard_normal((N, 1, H, W)).astype(np.float32), rng.standard_normal((N, 1, H, W)).astype(np.float32)
+    go = rng.standard_normal((N, 1, H, W)).astype(np.float32)
+    e = dev(es).requires_grad_(True)
+    out = ext.photometric_loss(e, dev(ta), k, t, 0.5)
+    out.backward(dev(go))
+    assert_close(out, c_oracle.photometric_forward(es, ta, k, tid, 0.5, "f64"), name="ext fwd")
+    assert_close(e.grad, c_oracle.photometric_backward(es, ta, go, k, tid, 0.5, "f64"), name="ext bwd", outlier_frac=2e-3 if sad else 0)
+    # LCN (radius must stay below the image size: reflection padding)
+    radius = int(min(5, H - 1, W - 1))
+    x = rng.random((N, 1, H, W)).astype(np.float32)
+    lcn, std = net.LCN(radius, 0.05)(dev(x))
+    o_l, o_s = c_oracle.lcn_forward(x, radius, 0.05, "f64")
+    assert_close(lcn, o_l, 2e-6, "lcn")
+    assert_close(std, o_s, 2e-6, "std")
+    # smoothness (value + gradient)
+    disp = (rng.random((N, 1, H, W)) * 30).astype(np.float32)
+    amb = rng.random((N, 1, H, W)).astype(np.float32)
+    dd = dev(disp).requires_grad_(True)
+    val = net.DisparitySmoothLoss()(dd, dev(amb))
+    val.backward()
+    o_v, o_g = c_oracle.smooth_loss(disp, amb, True, "f64")
+    assert_scalar_close(val.item(), o_v, name="smooth value")
+    assert_close(dd.grad, o_g, 2e-5, "smooth grad", outlier_frac=2e-3)
+    # fused pattern loss (value, projection bit-exact vs the fp32 oracle, gradient vs the fp32 oracle)
+    pat = rng.random((1, 1, H, W)).astype(np.float32)
+    sig = (0.05 + rng.random((N, 1, H, W))).astype(np.float32)
+    dsp = (rng.random((N, 1, H, W)) * (W / 2)).astype(np.float32)
+    mod = net.RectifiedPatternSimilarityLoss(H, W, dev(np.repeat(pat, 3, axis=1)), loss_type=t, block_size=k)
+    d2 = dev(dsp).requires_grad_(True)
+    v, proj = mod(d2, dev(ta), dev(sig))
+    v.backward()
+    o = c_oracle.pattern_loss(dsp, ta, sig, to_np(mod.pattern), k, tid, 0.5, True, "f32")
+    o64 = c_oracle.pattern_loss(dsp, ta, sig, to_np(mod.pattern), k, tid, 0.5, False, "f64")
+    assert_scalar_close(v.item(), o64["val"], 2e-5, "pattern loss value")
+    assert np.array_equal(to_np(proj), o["proj"]), "pattern_proj differs from the fp32 oracle"
+    assert_close(d2.grad, o["grad_disp"], 2e-5, "pattern loss grad", outlier_frac=2e-3 if sad else 1e-4)
