@@ -1062,3 +1062,71 @@ def test_random_shape_sweep_vs_c_oracle(mods, i, H, W, N, k, t):
     assert_scalar_close(v.item(), o64["val"], 2e-5, "pattern loss value")
     assert np.array_equal(to_np(proj), o["proj"]), "pattern_proj differs from the fp32 oracle"
     assert_close(d2.grad, o["grad_disp"], 2e-5, "pattern loss grad", outlier_frac=2e-3 if sad else 1e-4)
+
+
+def _mf_sweep_cases(n, seed):
+    rng = np.random.default_rng(seed)
+    return [(i, int(rng.integers(2, 70)), int(rng.integers(2, 90)), int(rng.integers(1, 4)), int(rng.choice([1, 2, 3, 5, 8, 32, 33, 36, 40])))
+            for i in range(n)]
+
+
+@pytest.mark.parametrize("i,H,W,N,C", _mf_sweep_cases(12, 77))
+def test_random_shape_sweep_flow_warp(mods, i, H, W, N, C):
+    """Flow warp forward (bit-exact incl. corner indices) and backward for random ragged shapes and channel counts,
+    and the one-launch gathers built on it."""
+    _, _, mf = mods
+    rng = np.random.default_rng(500 + i)
+    x = rng.standard_normal((N, C, H, W)).astype(np.float32)
+    f01 = (rng.standard_normal((N, 2, H, W)) * 3).astype(np.float32)
+    f01[0, :, 0, 0] = 0.0
+    f01[-1, 0, H // 2, :] = 1e6
+    xt = dev(x).requires_grad_(True)
+    y = mf.warp(xt, dev(f01))
+    go = rng.standard_normal((N, C, H, W)).astype(np.float32)
+    y.backward(dev(go))
+    o_y, _, _ = c_oracle.flow_warp_forward(x, f01, "f32")
+    assert np.array_equal(to_np(y), o_y), "warp output not bit-exact vs the fp32 oracle"
+    o_gx = c_oracle.flow_warp_backward(x, f01, go, False, "f32")
+    assert_close(xt.grad, o_gx, 2e-6, name="grad x vs fp32 oracle")
+    # gathers: tl = 3 frames made of the same data shifted, all-frames version against per-frame version
+    tl = 3
+    x5 = torch.stack([dev(np.roll(x, t, axis=3)) for t in range(tl)]).requires_grad_(True)
+    flow = {f"flow_{a}{b}": dev(np.roll(f01, a + 2 * b, axis=2)) for a in range(tl) for b in range(tl) if a != b}
+    out = mf.gather_warped_all(x5, flow)
+    for t in range(tl):
+        assert torch.equal(out[t], mf.gather_warped(x5.detach(), flow, t))
+        assert torch.equal(out[t, 0], x5[t])
+
+
+@pytest.mark.parametrize("k,tl,C,stride,hw", [(3, 4, 36, 1, (21, 19)), (3, 4, 33, 1, (16, 16)), (5, 2, 8, 1, (17, 12)), (3, 4, 64, 2, (15, 22)),
+                                              (1, 4, 4, 1, (9, 9)), (3, 1, 16, 1, (12, 10))])
+def test_conv3d_gather_more_configurations(mods, k, tl, C, stride, hw):
+    """Window / frame / channel configurations beyond the reference's (3 x 3, 4 frames, 32 channels): channel counts
+    above 32 and not divisible by 4, a 5 x 5 window, one frame, stride 2."""
+    _, _, mf = mods
+    torch.manual_seed(k * 100 + C)
+    bs = 2
+    nb = min(9, k * k * tl)
+    xyz = torch.randn(tl, bs, 3, *hw, device="cuda") * 0.1
+    xyz[:, :, 2] += 1.5
+    feat = torch.randn(tl, bs, C, *hw, device="cuda")
+    mask = torch.ones(tl, bs, 1, *hw, device="cuda")      # every candidate valid: the selection is fully determined
+    f1, f2 = feat.clone().requires_grad_(True), feat.clone().requires_grad_(True)
+    xyz_nb, feat_nb, idx = mf.conv3d_gather(xyz, f1, mask, k, stride, nb)
+    r_xyz, r_feat, r_ind = torch_port.conv3d_gather(xyz, f2, mask, k, stride, nb)
+    a_x, a_i = _sort_by_index(xyz_nb, idx)
+    b_x, b_i = _sort_by_index(r_xyz, r_ind.squeeze(-1))
+    a_f, _ = _sort_by_index(feat_nb, idx)
+    b_f, _ = _sort_by_index(r_feat, r_ind.squeeze(-1))
+    # border pixels see zero-padded candidates (xyz = 0 -> plane 0/1e-12): ties among them are unspecified in topk
+    same = (a_i == b_i).all(dim=1)
+    assert same.float().mean() > 0.6
+    assert torch.equal(a_x[same], b_x[same]) and torch.equal(a_f[same], b_f[same])
+    wf = torch.randn_like(feat_nb)
+    sel = same.view(-1, 1, 1).float()
+    order_a = torch.argsort(idx.long(), dim=1)
+    order_b = torch.argsort(r_ind.squeeze(-1), dim=1)
+    ga = lambda t, o: torch.gather(t, 1, o.unsqueeze(-1).expand(-1, -1, t.shape[-1]))
+    (ga(feat_nb, order_a) * wf * sel).sum().backward()
+    (ga(r_feat, order_b) * wf * sel).sum().backward()
+    assert_close(f1.grad, f2.grad, 1e-6, "grad feat")
