@@ -106,9 +106,11 @@ __global__ void __launch_bounds__(256) flow_warp_fwd_kernel(const float* __restr
 }
 
 // Gather step of FuseNet (multi_frame_networks.py:187-214, 347-360) in one launch.  A slot table tells every
-// blockIdx.y which frame it reads (src), which slice of the stacked output it owns (dst) and which flow warps it
+// blockIdx.x which frame it reads (src), which slice of the stacked output it owns (dst) and which flow warps it
 // (flow == NULL: the own frame, a plain copy).  x is [tl,bs,C,H,W]; out is [n_dst,bs,C,H,W] with n_dst = tl for
-// one target frame and tl*tl for all of them (out[tidx*tl + k]).
+// one target frame and tl*tl for all of them (out[tidx*tl + k]).  The slot is the FAST grid dimension and the tables
+// list slots of the same source frame next to each other: the CTAs that read (forward) or reduce into (backward) the
+// same pixels of a frame run at the same time and meet in L2 instead of each making its own trip to HBM.
 constexpr int MAX_TL = 8, MAX_SLOTS = MAX_TL * MAX_TL;
 struct GatherArgs {
   const float* flow[MAX_SLOTS];
@@ -120,12 +122,12 @@ __global__ void __launch_bounds__(256) flow_warp_gather_fwd_kernel(const float* 
                                                                    float* __restrict__ out, int C, int H, int W,
                                                                    float inv_w, float inv_h, size_t total, size_t slot_stride) {
   const size_t hw = (size_t)H * W;
-  const int slot = blockIdx.y;
+  const int slot = blockIdx.x;
   const float* flow = g.flow[slot];
   const float* xs = x + (size_t)g.src[slot] * slot_stride;
   float* os = out + (size_t)g.dst[slot] * slot_stride;
-  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
-       idx += (size_t)gridDim.x * blockDim.x) {
+  for (size_t idx = (size_t)blockIdx.y * blockDim.x + threadIdx.x; idx < total;
+       idx += (size_t)gridDim.y * blockDim.x) {
     const size_t n = idx / hw;
     const int pix = (int)(idx - n * hw), h = pix / W, w = pix - h * W;
     if (!flow) {
@@ -146,12 +148,12 @@ __global__ void __launch_bounds__(256) flow_warp_gather_bwd_kernel(const float* 
                                                                    float* __restrict__ gx, int C, int H, int W,
                                                                    float inv_w, float inv_h, size_t total, size_t slot_stride) {
   const size_t hw = (size_t)H * W;
-  const int slot = blockIdx.y;
+  const int slot = blockIdx.x;
   const float* flow = g.flow[slot];
   const float* gs = go + (size_t)g.dst[slot] * slot_stride;
   float* xs = gx + (size_t)g.src[slot] * slot_stride;
-  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
-       idx += (size_t)gridDim.x * blockDim.x) {
+  for (size_t idx = (size_t)blockIdx.y * blockDim.x + threadIdx.x; idx < total;
+       idx += (size_t)gridDim.y * blockDim.x) {
     const size_t n = idx / hw;
     const int pix = (int)(idx - n * hw), h = pix / W, w = pix - h * W;
     if (!flow) {
@@ -231,21 +233,21 @@ int make_gather_args(const float* const* flows, int tl, int tidx, GatherArgs& g)
 // separate tables (the backward pass must finish the copies before the reductions start)
 int make_gather_all_args(const float* const* flows, int tl, GatherArgs& copies, GatherArgs& warps) {
   if (tl < 1 || tl > MAX_TL) return DIS_ERR_BAD_SHAPE;
-  int nw = 0;
   for (int i = 0; i < tl; ++i) {
     copies.src[i] = (short)i;
     copies.dst[i] = (short)(i * tl);
     copies.flow[i] = nullptr;
-    for (int j = 0, k = 1; j < tl; ++j) {
-      if (j == i) continue;
+  }
+  int nw = 0;
+  for (int j = 0; j < tl; ++j)            // source frame-major: the tl-1 slots that touch frame j sit next to each other
+    for (int i = 0; i < tl; ++i) {
+      if (i == j) continue;
       if (!flows[i * tl + j]) return DIS_ERR_NULL_POINTER;
       warps.src[nw] = (short)j;
-      warps.dst[nw] = (short)(i * tl + k);
+      warps.dst[nw] = (short)(i * tl + (j < i ? j + 1 : j));   // slot k of target i: own frame first, others ascending
       warps.flow[nw] = flows[i * tl + j];
       ++nw;
-      ++k;
     }
-  }
   return DIS_OK;
 }
 
@@ -256,7 +258,7 @@ int flow_warp_gather_forward(const float* x, const float* const* flows, float* o
   GatherArgs g;
   if (int rc = make_gather_args(flows, tl, tidx, g)) return rc;
   const size_t total = (size_t)bs * H * W;
-  const dim3 grid(flat_grid(total), tl);
+  const dim3 grid(tl, flat_grid(total));
   flow_warp_gather_fwd_kernel<<<grid, 256, 0, s>>>(x, g, out, C, H, W, 1.0f / (float)(W - 1), 1.0f / (float)(H - 1), total,
                                                    total * C);
   return check_launch();
@@ -273,7 +275,7 @@ int flow_warp_gather_backward(const float* const* flows, const float* go, float*
   if (e == cudaSuccess && tidx + 1 < tl)
     e = cudaMemsetAsync(gx + stride * (tidx + 1), 0, sizeof(float) * stride * (tl - 1 - tidx), s);
   if (e != cudaSuccess) { set_last_cuda_error(e); return DIS_ERR_CUDA_LAUNCH; }
-  const dim3 grid(flat_grid(total), tl);
+  const dim3 grid(tl, flat_grid(total));
   flow_warp_gather_bwd_kernel<<<grid, 256, 0, s>>>(go, g, gx, C, H, W, 1.0f / (float)(W - 1), 1.0f / (float)(H - 1), total,
                                                    stride);
   return check_launch();
@@ -285,10 +287,10 @@ int flow_warp_gather_all_forward(const float* x, const float* const* flows, floa
   if (int rc = make_gather_all_args(flows, tl, copies, warps)) return rc;
   const size_t total = (size_t)bs * H * W;
   const float iw = 1.0f / (float)(W - 1), ih = 1.0f / (float)(H - 1);
-  flow_warp_gather_fwd_kernel<<<dim3(flat_grid(total), tl), 256, 0, s>>>(x, copies, out, C, H, W, iw, ih, total, total * C);
+  flow_warp_gather_fwd_kernel<<<dim3(tl, flat_grid(total)), 256, 0, s>>>(x, copies, out, C, H, W, iw, ih, total, total * C);
   if (int rc = check_launch()) return rc;
   if (tl > 1) {
-    flow_warp_gather_fwd_kernel<<<dim3(flat_grid(total), tl * (tl - 1)), 256, 0, s>>>(x, warps, out, C, H, W, iw, ih, total,
+    flow_warp_gather_fwd_kernel<<<dim3(tl * (tl - 1), flat_grid(total)), 256, 0, s>>>(x, warps, out, C, H, W, iw, ih, total,
                                                                                      total * C);
     return check_launch();
   }
@@ -302,10 +304,10 @@ int flow_warp_gather_all_backward(const float* const* flows, const float* go, fl
   const size_t total = (size_t)bs * H * W;
   const float iw = 1.0f / (float)(W - 1), ih = 1.0f / (float)(H - 1);
   // gx[i] = go[i][0] first (no zero-fill needed), then every warped slot reduces into its source frame
-  flow_warp_gather_bwd_kernel<<<dim3(flat_grid(total), tl), 256, 0, s>>>(go, copies, gx, C, H, W, iw, ih, total, total * C);
+  flow_warp_gather_bwd_kernel<<<dim3(tl, flat_grid(total)), 256, 0, s>>>(go, copies, gx, C, H, W, iw, ih, total, total * C);
   if (int rc = check_launch()) return rc;
   if (tl > 1) {
-    flow_warp_gather_bwd_kernel<<<dim3(flat_grid(total), tl * (tl - 1)), 256, 0, s>>>(go, warps, gx, C, H, W, iw, ih, total,
+    flow_warp_gather_bwd_kernel<<<dim3(tl * (tl - 1), flat_grid(total)), 256, 0, s>>>(go, warps, gx, C, H, W, iw, ih, total,
                                                                                      total * C);
     return check_launch();
   }

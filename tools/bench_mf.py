@@ -68,7 +68,8 @@ def build(bs, dev):
         grads.append(torch.randn(TL, bs, C_FEAT, h, w, device=dev, generator=gen))
         grads_all.append(grads[-1][None].expand(TL, -1, -1, -1, -1, -1).contiguous())
     xyz = torch.randn(TL, bs, 3, *FEAT[0], device=dev, generator=gen)
-    return dict(im=view(im), amb=view(amb), disp=view(disp), prim=view(dgt + 0.3), R=R, t=t, flow=flow, loss=loss, lcn=lcn,
+    im_bt = view(im).transpose(0, 1).contiguous()      # the DataLoader hands frames over as [bs, tl, 1, H, W]
+    return dict(im=view(im), im_bt=im_bt, amb=view(amb), disp=view(disp), prim=view(dgt + 0.3), R=R, t=t, flow=flow, loss=loss, lcn=lcn,
                 feats=feats, flows_lr=flows_lr, grads=grads, grads_all=grads_all, xyz=xyz, bs=bs)
 
 
@@ -98,7 +99,7 @@ SEC = Sections()
 def step(w):
     SEC.mark("start")
     # ---- copy_data: LCN + cat(lcn, raw), [tl, bs, 2, H, W]
-    im_cat, std = w["lcn"].prepare_input(w["im"].transpose(0, 1).contiguous())   # reference hands over [bs, tl, ...]
+    im_cat, std = w["lcn"].prepare_input(w["im_bt"])
     SEC.mark("copy_data_ms")
     # ---- FuseNet warps
     with torch.no_grad():
@@ -149,7 +150,7 @@ def build_sf(bs, dev):
 
 def step_sf(w):
     SEC.mark("start")
-    im_cat, std = w["lcn"].prepare_input(w["im"].transpose(0, 1).contiguous())
+    im_cat, std = w["lcn"].prepare_input(w["im_bt"])
     SEC.mark("copy_data_ms")
     disps = [d.detach().requires_grad_(True) for d in w["disps"]]
     vals = w["loss"](disps, im_cat, std, w["amb"], R=w["R"], t=w["t"], flow_out=w["flow"])
