@@ -51,6 +51,7 @@ SIGNATURES = {
     "dis_flow_warp_gather_all_backward": [_c.POINTER(_c.c_void_p), _f, _f, _i, _i, _i, _i, _i, _st],
     "dis_flow_consistency_num_partials": [_i, _i, _i],
     "dis_flow_consistency_forward": [_f] * 10 + [_i, _f, _f, _f, _fl, _fl, _f, _f, _f, _f, _f, _i, _i, _i, _st],
+    "dis_geometric_grad_combine": [_c.POINTER(_c.c_void_p), _c.POINTER(_c.c_int), _i, _f, _f, _fl, _f, _i, _i, _i, _i, _st],
     "dis_conv3d_out_size": [_i, _i, _i],
     "dis_conv3d_gather_forward": [_f, _f, _f, _f, _f, _f, _f, _i, _i, _i, _i, _i, _i, _i, _i, _st],
     "dis_conv3d_gather_backward": [_f, _f, _f, _f, _f, _i, _i, _i, _i, _i, _i, _i, _i, _st],

@@ -429,6 +429,29 @@ def combine2(a, b, numer, den_a, den_b, eps):
     return out
 
 
+def geometric_grad_combine(planes, frame_of, scale, disp, baseline_focal):
+    """planes: list of [bs,1,H,W] gradient planes, frame_of: their frame indices, scale: device tensor [len(planes)],
+    disp [tl,bs,1,H,W] -> grad_disp [tl,bs,1,H,W] (see dis_geometric_grad_combine)."""
+    import ctypes
+    disp = _chk(disp, "disp", 5)
+    tl, bs, C, H, W = disp.shape
+    planes = [_chk(p, f"plane[{i}]") for i, p in enumerate(planes)]
+    for p in planes:
+        if tuple(p.shape) != (bs, 1, H, W):
+            raise ValueError(f"every gradient plane must be {(bs, 1, H, W)}, got {tuple(p.shape)}")
+    n = len(planes)
+    scale = _chk(scale, "scale", 1)
+    if C != 1 or scale.numel() != n or len(frame_of) != n:
+        raise ValueError("geometric_grad_combine: inconsistent arguments")
+    out = torch.empty_like(disp)
+    arr = (ctypes.c_void_p * max(n, 1))(*[p.data_ptr() for p in planes])
+    fo = (ctypes.c_int * max(n, 1))(*[int(f) for f in frame_of])
+    with _on(disp) as lib:
+        _lib.check(lib.dis_geometric_grad_combine(arr, fo, n, _ptr(scale), _ptr(disp), float(baseline_focal), _ptr(out),
+                                                  tl, bs, H, W, _stream(disp)))
+    return out
+
+
 def conv3d_gather_forward(xyz, feat, mask, ksize, stride, neighbors):
     """-> (xyz_nb [M,nb,3], feat_nb [M,nb,C], idx uint8 [M,nb], (oh, ow))"""
     xyz, feat, mask = _chk(xyz, "xyz", 5), _chk(feat, "feat", 5), _chk(mask, "mask", 5)

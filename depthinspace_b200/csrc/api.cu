@@ -41,6 +41,8 @@ int flow_consistency_forward(const float*, const float*, const float*, const flo
                              const float*, float, float, float*, float*, float*, float*, float*, int, int, int,
                              cudaStream_t);
 int combine2(const float*, const float*, float*, size_t, const float*, const float*, const float*, float, cudaStream_t);
+int geometric_grad_combine(const float* const*, const int*, int, const float*, const float*, float, float*, int, size_t,
+                           cudaStream_t);
 
 int conv3d_out_size(int, int, int);
 int conv3d_gather_forward(const float*, const float*, const float*, float*, float*, uint8_t*, float*, int, int, int, int,
@@ -448,6 +450,16 @@ int dis_combine2(const float* a, const float* b, float* out, size_t n, const flo
   if (!a || !out || !numer || !den_a || (b && !den_b)) return DIS_ERR_NULL_POINTER;
   if (n == 0) return DIS_OK;
   return combine2(a, b, out, n, numer, den_a, den_b, eps, as_stream(stream));
+}
+
+int dis_geometric_grad_combine(const float* const* planes, const int* frame_of, int n_terms, const float* scale,
+                               const float* disp, float baseline_focal, float* grad_disp, int tl, int bs, int H, int W,
+                               void* stream) {
+  if (!disp || !grad_disp || (n_terms > 0 && (!planes || !frame_of || !scale))) return DIS_ERR_NULL_POINTER;
+  if (tl < 1 || bs < 0 || H < 1 || W < 1 || n_terms < 0) return DIS_ERR_BAD_SHAPE;
+  if (bs == 0) return DIS_OK;
+  return geometric_grad_combine(planes, frame_of, n_terms, scale, disp, baseline_focal, grad_disp, tl,
+                                (size_t)bs * H * W, as_stream(stream));
 }
 
 int dis_conv3d_out_size(int n, int ksize, int stride) {

@@ -39,6 +39,54 @@ def _merge(x):
     return x.contiguous().view(-1, *x.shape[-3:]) if x.dim() == 5 else x
 
 
+class _GeometricTerms(torch.autograd.Function):
+    """All flow-consistency terms of one track batch (the pair loop of the workers) as ONE autograd node on the
+    disparity maps: forward = DispToDepth + two fused launches per frame pair, backward = one launch that scales and
+    sums the 4 gradient planes of every pair into d/d disp of the frames they belong to, DispToDepth's derivative
+    included.  Autograd would otherwise run, per step, 12 two-plane combines, the zero-fills / strided copies of the
+    `depth[i]` indexing, 10 gradient accumulations and DispToDepth's backward."""
+
+    @staticmethod
+    def forward(ctx, disp_tl, primary_disp, R, t, amb, K, ray, clamp, multi_frame, bf, weight, *flows):
+        ctx.set_materialize_grads(False)
+        tl = disp_tl.shape[0]
+        disp_tl = disp_tl.contiguous()
+        depth = bf / (torch.relu(disp_tl) + 1e-12)                     # DispToDepth, reference model/networks.py:311-319
+        primary = bf / (torch.relu(primary_disp) + 1e-12) if multi_frame else None
+        need = ctx.needs_input_grad[0]
+        vals, planes, frame_of, dens = [], [], [], []
+        k = 0
+        for i in range(tl):
+            for j in range(i + 1, tl):
+                f_ij, f_ji = flows[2 * k], flows[2 * k + 1]
+                k += 1
+                a3, _, _, gA0, gA1 = _ops.flow_consistency_dir(depth[i], depth[j], R[i], t[i], R[j], t[j], f_ij, f_ji, amb[i],
+                                                               amb[j], K, ray, clamp, primary[j] if multi_frame else None,
+                                                               False, False, need, need)
+                b3, _, _, gB1, gB0 = _ops.flow_consistency_dir(depth[j], depth[i], R[j], t[j], R[i], t[i], f_ji, f_ij, amb[j],
+                                                               amb[i], K, ray, clamp, primary[i] if multi_frame else None,
+                                                               False, False, need, need)
+                vals.append((a3[0] / (a3[1] + 1e-8) + b3[0] / (b3[1] + 1e-8)) * weight)   # :599 / :653, times 0.2 / #pairs
+                if need:
+                    planes += [gA0, gA1, gB1, gB0]
+                    frame_of += [i, j, j, i]
+                    dens += [a3[1], a3[1], b3[1], b3[1]]
+        ctx.frame_of, ctx.bf, ctx.weight, ctx.n_pairs = frame_of, bf, weight, k
+        ctx.save_for_backward(disp_tl, torch.stack(dens) if dens else disp_tl.new_zeros(0), *planes)
+        return tuple(vals)
+
+    @staticmethod
+    def backward(ctx, *g_vals):
+        disp_tl, dens, *planes = ctx.saved_tensors
+        if not planes:
+            return (None,) * (11 + 2 * ctx.n_pairs)
+        zero = dens.new_zeros(())
+        g = torch.stack([zero if gv is None else gv.reshape(()) for gv in g_vals])       # [pairs]
+        scale = (g.repeat_interleave(4) * ctx.weight / (dens + 1e-8)).contiguous()        # one factor per gradient plane
+        grad = _ops.geometric_grad_combine(planes, ctx.frame_of, scale, disp_tl, ctx.bf)
+        return (grad,) + (None,) * (10 + 2 * ctx.n_pairs)
+
+
 class _HotPathLoss(torch.nn.Module):
     smooth_weight = None
 
@@ -59,20 +107,16 @@ class _HotPathLoss(torch.nn.Module):
         """The pair loop of the workers (single_frame_worker.py:127-149, multi_frame_worker.py:128-157):
         every unordered frame pair of a track, weight 0.2 / (tl (tl-1) / 2)."""
         tl = disp_tl.shape[0]
-        depth = self.d2d(disp_tl)
-        primary = self.d2d(primary_disp) if primary_disp is not None else None
         ge_num = tl * (tl - 1) / 2
-        vals = []
+        multi_frame = primary_disp is not None
+        K, ray = self.ge_loss._consts(disp_tl)
+        flows = []
         for i in range(tl):
             for j in range(i + 1, tl):
-                args = (depth[i], depth[j], R[i], t[i], R[j], t[j], flow_out[f'flow_{i}{j}'], flow_out[f'flow_{j}{i}'],
-                        amb[i], amb[j])
-                if primary is not None:
-                    val = self.ge_loss(*args, primary[i], primary[j])
-                else:
-                    val = self.ge_loss(*args)[0]
-                vals.append(val * 0.2 / ge_num)
-        return vals
+                flows += [flow_out[f'flow_{i}{j}'].detach(), flow_out[f'flow_{j}{i}'].detach()]
+        clamp = -1.0 if multi_frame else self.ge_loss.clamp        # the multi-frame variant never clamps (:564-601)
+        return list(_GeometricTerms.apply(disp_tl, primary_disp.detach() if multi_frame else None, R, t, amb.detach(), K, ray,
+                                          float(clamp), multi_frame, self.d2d.baseline_focal_length, 0.2 / ge_num, *flows))
 
 
     # ---- fused value + gradient (no autograd graph, no scaling passes) -------------------------------------------------

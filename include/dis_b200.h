@@ -220,6 +220,17 @@ DIS_API int dis_flow_consistency_forward(const float* depth0, const float* depth
 DIS_API int dis_combine2(const float* a, const float* b, float* out, size_t n, const float* numer,
                          const float* den_a, const float* den_b, float eps, void* stream);
 
+/* Gradient of ALL geometric terms of the loss assembly (the pair loops of single_frame_worker.py:127-149 /
+ * multi_frame_worker.py:128-157) w.r.t. the disparity maps, in one pass, DispToDepth (model/networks.py:311-319)
+ * included:   grad_disp[f] = d depth/d disp(f) * sum_{k: frame_of[k] == f} scale[k] * planes[k]
+ *   planes    HOST array of n_terms device pointers: the grad_depth0 / grad_depth1 outputs of
+ *             dis_flow_consistency_forward ([bs,1,H,W] each); frame_of: HOST int[n_terms], the frame each belongs to
+ *   scale     DEVICE float[n_terms]: upstream * weight / (den + 1e-8) of the term the plane came from
+ *   disp, grad_disp  [tl,bs,1,H,W] (tl <= 8, at most 16 planes per frame); depth = baseline_focal / (max(disp,0) + 1e-12) */
+DIS_API int dis_geometric_grad_combine(const float* const* planes, const int* frame_of, int n_terms,
+                                       const float* scale, const float* disp, float baseline_focal,
+                                       float* grad_disp, int tl, int bs, int H, int W, void* stream);
+
 /* ---- (next) neighbour selection + gather of FuseNet's Conv3D, model/multi_frame_networks.py:469-501 -------
  * xyz [tl,bs,3,h,w], feat [tl,bs,C,h,w], mask [tl,bs,1,h,w] -> for each of the M = bs*oh*ow output pixels
  * (ksize x ksize window, zero padding (ksize-1)/2, given stride) the `neighbors` candidates (of ksize^2*tl <= 64)
