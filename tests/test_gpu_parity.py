@@ -681,7 +681,7 @@ def test_gather_warped_matches_reference_composition(mods, tl, tidx, C):
     assert torch.equal(mf.gather_warped([x[i].detach() for i in range(tl)], flow, tidx), out)
 
 
-@pytest.mark.parametrize("tl,C,hw", [(4, 32, (64, 54)), (3, 5, (37, 50)), (2, 2, (16, 9)), (1, 3, (8, 8))])
+@pytest.mark.parametrize("tl,C,hw", [(4, 32, (64, 54)), (3, 5, (37, 50)), (2, 2, (16, 9)), (1, 3, (8, 8)), (8, 2, (9, 12))])
 def test_gather_warped_all_equals_per_frame_gathers(mods, tl, C, hw):
     """dis_flow_warp_gather_all_* == the tidx loop of Block2D3D.fwd_3d_1 (reference :376-389): forward bit for bit,
     backward == autograd through tl separate gathers (sum of their gradients)."""
