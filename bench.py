@@ -377,6 +377,33 @@ def run_ours(args):
     achieved = KERNEL_ALGO_BYTES_PER_FRAME * P * n / (kernel_ms * 1e-3) / 1e9
     step_gbs = ALGO_BYTES_PER_FRAME * P * (value / world) / 1e9
 
+    # ---- DIS-MF hot path (BASELINE configs[2]) on this GPU, reported beside the headline (N = 1 only) ----
+    mf_line = None
+    if world == 1 and not args.no_mf:
+        try:
+            del disps, im, amb
+            torch.cuda.empty_cache()
+            sys.path.insert(0, os.path.join(ROOT, "tools"))
+            import bench_mf
+            w = bench_mf.build(32, dev)
+            for _ in range(3):
+                bench_mf.step(w)
+            m0, m1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize()
+            m0.record()
+            for _ in range(args.steps):
+                bench_mf.step(w)
+            m1.record()
+            torch.cuda.synchronize()
+            mf_ms = m0.elapsed_time(m1) / args.steps
+            mf_line = {"value": 128 / (mf_ms * 1e-3), "unit": UNIT, "ms_per_step": mf_ms, "frames_per_step": 128,
+                       "workload": "BASELINE configs[2] on one GPU: DIS-MF hot path, bs 32 x tl 4 (copy_data LCN, 24 xyz/flow + 96 C=32 "
+                                   "feature warps fwd/recompute/bwd, 1-scale census_sad + smoothness + 12 flow-consistency terms + L1), "
+                                   "see tools/bench_mf.py"}
+            del w
+        except Exception as e:
+            mf_line = f"unavailable: {type(e).__name__}: {e}"[:200]
+
     if rank == 0:
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
@@ -399,6 +426,7 @@ def run_ours(args):
             "e2e": {"value": e2e_value, "unit": UNIT,
                     "h2d_bytes_per_step": int((2 + N_SCALES) * 4 * P * n), "d2h_bytes_per_step": 4},
             "gpu_launches": launches, "cuda_graph_ms_per_step": graph_ms, "autograd_modules_ms_per_step": autograd_ms,
+            "dis_mf": mf_line,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": measured_traffic("pattern_multi_kernel<census_sad, R=4, 4 scales, grad>", n),
                          "algorithmic_bytes": KERNEL_ALGO_BYTES_PER_FRAME * P * n,
@@ -422,6 +450,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--frames-per-gpu", type=int, default=FRAMES_PER_GPU)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-mf", action="store_true", help="skip the DIS-MF side measurement")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
     if args.impl == "reference":
