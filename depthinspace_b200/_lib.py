@@ -35,6 +35,7 @@ SIGNATURES = {
     "dis_pattern_loss_multi_forward": [_c.POINTER(_c.c_void_p), _i, _f, _f, _f, _c.POINTER(_c.c_void_p), _f, _i, _i, _i, _i, _i, _fl, _st],
     "dis_pattern_loss_multi_forward_scaled": [_c.POINTER(_c.c_void_p), _i, _f, _f, _f, _c.POINTER(_c.c_void_p), _f, _f, _i, _i, _i, _i, _i, _fl, _st],
     "dis_scale_by_device_scalar": [_f, _f, _sz, _f, _f, _st],
+    "dis_masked_l1_forward": [_f, _f, _f, _fl, _f, _f, _sz, _st],
     "dis_mul": [_f, _f, _f, _sz, _st],
     "dis_l1_num_partials": [_sz],
     "dis_l1_forward": [_f, _f, _f, _f, _sz, _st],

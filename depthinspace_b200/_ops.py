@@ -214,6 +214,27 @@ def l1_forward(a, b, want_grad):
     return out3, sgn
 
 
+def masked_l1_forward(a, b, noise, threshold, want_grad):
+    """-> (out3 [sum |a - b + noise| * valid, sum valid, ratio], sign * valid | None), valid = (b > threshold)"""
+    a, b = _chk(a, "a", None), _chk(b, "b", None)
+    if a.shape != b.shape:
+        b = b.expand_as(a).contiguous()
+    if noise is not None:
+        noise = _chk(noise, "noise", None)
+        if noise.shape != a.shape:
+            raise ValueError("noise must have the shape of a")
+    sgn = torch.empty_like(a) if want_grad else None
+    out3 = torch.empty(3, dtype=torch.float32, device=a.device)
+    with _on(a) as lib:
+        npart = lib.dis_l1_num_partials(a.numel())
+        partials = torch.empty(2 * npart, dtype=torch.float32, device=a.device)
+        s = _stream(a)
+        _lib.check(lib.dis_masked_l1_forward(_ptr(a), _ptr(b), _ptr(noise), float(threshold), _ptr(sgn), _ptr(partials),
+                                             a.numel(), s))
+        _lib.check(lib.dis_reduce_pairs(_ptr(partials), npart, _ptr(out3), s))
+    return out3, sgn
+
+
 def mul(a, b):
     a, b = a.contiguous(), b.contiguous()
     out = torch.empty_like(a)

@@ -24,6 +24,7 @@ int scale_by_device_scalar(const float*, float*, size_t, const float*, const flo
 int mul(const float*, const float*, float*, size_t, cudaStream_t);
 int l1_num_partials(size_t);
 int l1_forward(const float*, const float*, float*, float*, size_t, cudaStream_t);
+int masked_l1_forward(const float*, const float*, const float*, float, float*, float*, size_t, cudaStream_t);
 int smooth_loss_num_partials(int, int, int);
 int smooth_loss_forward(const float*, const float*, float*, float*, int, int, int, float, int, cudaStream_t);
 int sobel_forward(const float*, float*, int, int, int, int, cudaStream_t);
@@ -327,6 +328,13 @@ int dis_l1_forward(const float* a, const float* b, float* sign_out, float* parti
   if (!a || !partials) return DIS_ERR_NULL_POINTER;   // b == NULL: sum |a|
   if (n == 0) return DIS_ERR_BAD_SHAPE;
   return l1_forward(a, b, sign_out, partials, n, as_stream(stream));
+}
+
+int dis_masked_l1_forward(const float* a, const float* b, const float* noise, float threshold, float* sign_out,
+                          float* partials, size_t n, void* stream) {
+  if (!a || !b || !partials) return DIS_ERR_NULL_POINTER;
+  if (n == 0) return DIS_ERR_BAD_SHAPE;
+  return masked_l1_forward(a, b, noise, threshold, sign_out, partials, n, as_stream(stream));
 }
 
 int dis_mul(const float* a, const float* b, float* out, size_t n, void* stream) {

@@ -100,6 +100,28 @@ __global__ void __launch_bounds__(256) l1_kernel(const float* __restrict__ a, co
   if (threadIdx.x == 0) { partials[2 * blockIdx.x] = s; partials[2 * blockIdx.x + 1] = c; }
 }
 
+// Masked L1 with additive noise, the SGM warm-up term of the single-frame worker (single_frame_worker.py:158-163):
+//   valid = (b > threshold);  d = a - b + noise;  partials = (sum |d| * valid, sum valid);  sgn = sign(d) * valid
+// (the reference evaluates a - b first and adds the noise to the difference: same order here)
+__global__ void __launch_bounds__(256) masked_l1_kernel(const float* __restrict__ a, const float* __restrict__ b,
+                                                        const float* __restrict__ noise, float threshold,
+                                                        float* __restrict__ sgn, float* __restrict__ partials, size_t n) {
+  __shared__ float red[16];
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  float s = 0.f, c = 0.f;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const float bv = __ldcs(b + i);
+    const float valid = bv > threshold ? 1.0f : 0.0f;
+    float d = __ldcs(a + i) - bv;
+    if (noise) d += __ldcs(noise + i);
+    s = fmaf(fabsf(d), valid, s);
+    c += valid;
+    if (sgn) __stcs(sgn + i, sign0(d) * valid);
+  }
+  block_sum2<256>(s, c, red);
+  if (threadIdx.x == 0) { partials[2 * blockIdx.x] = s; partials[2 * blockIdx.x + 1] = c; }
+}
+
 inline int stream_grid(size_t work_items, int threads) {
   const size_t want = (work_items + threads - 1) / threads;
   const size_t cap = 148 * 16;  // 16 resident 256-thread CTAs x 148 SMs is plenty for a streaming loop
@@ -136,6 +158,12 @@ int l1_forward(const float* a, const float* b, float* sgn, float* partials, size
   const bool vec = ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b) | reinterpret_cast<uintptr_t>(sgn)) & 15) == 0;
   // the grid must match l1_num_partials(n) whatever the alignment: scalar fallback keeps the same grid
   l1_kernel<<<l1_num_partials(n), 256, 0, s>>>(a, b, sgn, partials, vec ? n / 4 : 0, n);
+  return check_launch();
+}
+
+int masked_l1_forward(const float* a, const float* b, const float* noise, float threshold, float* sgn, float* partials,
+                      size_t n, cudaStream_t s) {
+  masked_l1_kernel<<<l1_num_partials(n), 256, 0, s>>>(a, b, noise, threshold, sgn, partials, n);
   return check_launch();
 }
 

@@ -34,6 +34,32 @@ def l1_mean(o, target):
     return _L1Mean.apply(o.contiguous(), target.detach())
 
 
+class _MaskedL1Mean(torch.autograd.Function):
+    """sum(|o - target + noise| * valid) / sum(valid), valid = (target > threshold): the SGM warm-up term
+    (reference model/single_frame_worker.py:158-163), value and gradient w.r.t. o from one pass."""
+
+    @staticmethod
+    def forward(ctx, o, target, noise, threshold, group):
+        out3, sgn = _ops.masked_l1_forward(o, target, noise, threshold, want_grad=ctx.needs_input_grad[0])
+        if group is not None:
+            from .parallel import all_reduce_sum_
+            nd = out3[:2].contiguous()
+            all_reduce_sum_(nd, group)
+            out3 = torch.cat((nd, (nd[0] / nd[1]).reshape(1)))
+        ctx.save_for_backward(sgn, out3)
+        return out3[2].clone()
+
+    @staticmethod
+    def backward(ctx, g):
+        sgn, out3 = ctx.saved_tensors
+        return _ops.scale_by_device_scalar(sgn, g, out3[1:2]).view_as(sgn), None, None, None, None
+
+
+def masked_l1_mean(o, target, noise=None, threshold=30.0, process_group=None):
+    return _MaskedL1Mean.apply(o.contiguous(), target.detach(), None if noise is None else noise.detach(), float(threshold),
+                               process_group)
+
+
 def _merge(x):
     """[tl,bs,C,H,W] -> [tl*bs,C,H,W] (model/multi_frame_networks.py:36-37); 4-D tensors pass through."""
     return x.contiguous().view(-1, *x.shape[-3:]) if x.dim() == 5 else x
@@ -196,7 +222,11 @@ class SingleFrameLoss(_HotPathLoss):
     ge_class = Single_Frame_Flow_Consistency_Loss
     smooth_weight = 0.4
 
-    def forward(self, out, im_lcn, std, ambient, pseudo_gt=None, R=None, t=None, flow_out=None):
+    def forward(self, out, im_lcn, std, ambient, pseudo_gt=None, R=None, t=None, flow_out=None, sgm_disp=None,
+                sgm_noise=None):
+        """sgm_disp: adds the warm-up term of the first epochs on real data (:158-163), one per scale, weight 0.1:
+        sum(|o - sgm + noise| * (sgm > 30)) / sum(sgm > 30).  sgm_noise: list of per-scale noise tensors; when omitted
+        1.5 * randn is drawn on the device (the reference draws on the CPU generator: a different stream, same law)."""
         if not isinstance(out, (tuple, list)):
             out = [out]
         im, std, amb = _merge(im_lcn)[:, 0:1], _merge(std), _merge(ambient)
@@ -208,6 +238,10 @@ class SingleFrameLoss(_HotPathLoss):
         if pseudo_gt is not None:                                     # :152-155 (DIS-FTSF)
             for s, o in enumerate(out):
                 vals.append(l1_mean(o, pseudo_gt) * 0.1 / (2 ** s))
+        if sgm_disp is not None:                                      # :158-163 (warm-up, real data)
+            for s, o in enumerate(out):
+                noise = sgm_noise[s] if sgm_noise is not None else 1.5 * torch.randn_like(o)
+                vals.append(masked_l1_mean(o, sgm_disp, noise, 30.0, self.ph_loss.process_group) * 0.1)
         return vals
 
     def value_and_grad(self, out, im_lcn, std, ambient, pseudo_gt=None, global_frames=None):

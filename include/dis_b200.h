@@ -141,6 +141,11 @@ DIS_API int dis_scale_by_device_scalar(const float* in, float* out, size_t n, co
 DIS_API int dis_l1_num_partials(size_t n);
 DIS_API int dis_l1_forward(const float* a, const float* b, float* sign_out, float* partials, size_t n, void* stream);
 /* b may be NULL (treated as 0): sum |a|, e.g. the sigma normaliser of the photometric terms. */
+/* SGM warm-up term of the single-frame worker (model/single_frame_worker.py:158-163):
+ *   valid = (b > threshold);  partials = (sum |a - b + noise| * valid, sum valid);  sign_out = sign(a - b + noise) * valid
+ * noise may be NULL; partials sized like dis_l1_forward's. */
+DIS_API int dis_masked_l1_forward(const float* a, const float* b, const float* noise, float threshold,
+                                  float* sign_out, float* partials, size_t n, void* stream);
 /* out[i] = a[i] * b[i] */
 DIS_API int dis_mul(const float* a, const float* b, float* out, size_t n, void* stream);
 

@@ -159,6 +159,13 @@ def single_frame_loss(disps, im_lcn, std, ambient, pattern, chunk=None, pseudo_g
     return vals
 
 
+def sgm_warmup_term(o, sgm_disp, noise):
+    """The warm-up term of the first epochs on real data (model/single_frame_worker.py:158-163), with the reference's
+    `1.5 * torch.randn(o.size()).cuda()` passed in as `noise`:  sum(|o - sgm + noise| * valid) / sum(valid) * 0.1."""
+    valid_mask = (sgm_disp > 30).to(o.dtype)
+    return torch.sum(torch.abs(o - sgm_disp + noise) * valid_mask) / torch.sum(valid_mask) * 0.1
+
+
 def multi_frame_loss(disp, im_lcn, std, ambient, pattern, chunk=None, primary_disp=None):
     """Photometric + smoothness part of multi_frame_worker.Worker.loss_forward
     (model/multi_frame_worker.py:103-126, 160-165): smoothness weight 0.8."""

@@ -1130,3 +1130,30 @@ def test_conv3d_gather_more_configurations(mods, k, tl, C, stride, hw):
     (ga(feat_nb, order_a) * wf * sel).sum().backward()
     (ga(r_feat, order_b) * wf * sel).sum().backward()
     assert_close(f1.grad, f2.grad, 1e-6, "grad feat")
+
+
+def test_sgm_warmup_term_matches_reference_formula(mods):
+    """single_frame_worker.py:158-163 with the noise made explicit: value and gradient of every scale."""
+    from depthinspace_b200 import losses
+    hw, tl, bs = (40, 56), 2, 2
+    d, im_l, im_s, pat = _frames(tl * bs, hw, "real", seed=9, scales=2)
+    view = lambda a: dev(a).view(tl, bs, *a.shape[1:])
+    gen = torch.Generator(device="cuda").manual_seed(1)
+    sgm = view((d["disp_gt"] * 1.2).astype(np.float32))             # part of it above, part below the 30 px threshold
+    assert 0.05 < float((sgm > 30).float().mean()) < 0.95
+    noise = [1.5 * torch.randn(tl, bs, 1, *hw, device="cuda", generator=gen) for _ in range(2)]
+    loss = losses.SingleFrameLoss(hw[0], hw[1], dev(np.repeat(pat, 3, axis=1)))
+    outs = [view(p).requires_grad_(True) for p in d["disp_pred"]]
+    im_cat = torch.cat((view(im_l), view(d["im"])), dim=2)
+    vals = loss(outs, im_cat, view(im_s), view(d["ambient"]), sgm_disp=sgm, sgm_noise=noise)
+    assert len(vals) == 2 + 1 + 2
+    sum(vals[3:]).backward()
+    refs = [view(p).double().requires_grad_(True) for p in d["disp_pred"]]
+    rvals = [torch_port.sgm_warmup_term(r, sgm.double(), n.double()) for r, n in zip(refs, noise)]
+    sum(rvals).backward()
+    for s in range(2):
+        assert_scalar_close(vals[3 + s].item(), rvals[s].item(), name=f"warm-up term {s}")
+        assert_close(outs[s].grad, refs[s].grad, 1e-6, f"warm-up gradient {s}")
+    # without explicit noise the term is drawn on the device and still finite / differentiable
+    v2 = loss([o.detach().requires_grad_(True) for o in outs], im_cat, view(im_s), view(d["ambient"]), sgm_disp=sgm)
+    assert all(torch.isfinite(v) for v in v2)
