@@ -255,7 +255,8 @@ class MultiFrameLoss(_HotPathLoss):
     ge_class = Multi_Frame_Flow_Consistency_Loss
     smooth_weight = 0.8
 
-    def forward(self, out, im_lcn, std, ambient, primary_disp=None, R=None, t=None, flow_out=None, warmup=True):
+    def forward(self, out, im_lcn, std, ambient, primary_disp=None, R=None, t=None, flow_out=None, warmup=True,
+                sgm_disp=None, sgm_noise=None):
         if not isinstance(out, (tuple, list)):
             out = [out]
         im, std, amb = _merge(im_lcn)[:, 0:1], _merge(std), _merge(ambient)
@@ -266,4 +267,7 @@ class MultiFrameLoss(_HotPathLoss):
             vals += self._geometric_terms(out[0], R, t, ambient, flow_out, primary_disp=primary_disp)
         if primary_disp is not None and warmup:                       # :160-165 (first two epochs)
             vals.append(l1_mean(out[0], primary_disp) * 0.1)
+        if sgm_disp is not None:                                      # :167-173 (warm-up on real data, scale 0 only)
+            noise = sgm_noise if sgm_noise is not None else 1.5 * torch.randn_like(out[0])
+            vals.append(masked_l1_mean(out[0], sgm_disp, noise, 30.0, self.ph_loss.process_group) * 0.1)
         return vals

@@ -1157,3 +1157,9 @@ def test_sgm_warmup_term_matches_reference_formula(mods):
     # without explicit noise the term is drawn on the device and still finite / differentiable
     v2 = loss([o.detach().requires_grad_(True) for o in outs], im_cat, view(im_s), view(d["ambient"]), sgm_disp=sgm)
     assert all(torch.isfinite(v) for v in v2)
+    # multi-frame worker: the same term on scale 0 only (multi_frame_worker.py:167-173)
+    mloss = losses.MultiFrameLoss(hw[0], hw[1], dev(np.repeat(pat, 3, axis=1)))
+    o0 = view(d["disp_pred"][0]).requires_grad_(True)
+    mv = mloss(o0, im_cat, view(im_s), view(d["ambient"]), sgm_disp=sgm, sgm_noise=noise[0])
+    assert len(mv) == 3
+    assert_scalar_close(mv[2].item(), rvals[0].item(), name="multi-frame warm-up term")
