@@ -378,7 +378,7 @@ def run_ours(args):
     step_gbs = ALGO_BYTES_PER_FRAME * P * (value / world) / 1e9
 
     # ---- DIS-MF hot path (BASELINE configs[2]) on this GPU, reported beside the headline (N = 1 only) ----
-    mf_line = None
+    mf_line, sfg_line = None, None
     if world == 1 and not args.no_mf:
         try:
             del disps, im, amb
@@ -401,8 +401,28 @@ def run_ours(args):
                                    "feature warps fwd/recompute/bwd, 1-scale census_sad + smoothness + 12 flow-consistency terms + L1), "
                                    "see tools/bench_mf.py"}
             del w
+            torch.cuda.empty_cache()
+            # the DIS-SF assembly INCLUDING its 12 flow-consistency terms (the headline follows SURVEY 8(d): 144P, without)
+            w = bench_mf.build_sf(64, dev)
+            for _ in range(3):
+                bench_mf.step_sf(w)
+            torch.cuda.synchronize()
+            m0.record()
+            for _ in range(args.steps):
+                bench_mf.step_sf(w)
+            m1.record()
+            torch.cuda.synchronize()
+            sfg_ms = m0.elapsed_time(m1) / args.steps
+            sfg_line = {"value": 256 / (sfg_ms * 1e-3), "unit": UNIT, "ms_per_step": sfg_ms, "frames_per_step": 256,
+                        "workload": "DIS-SF loss assembly with its geometric terms (single_frame_worker.py:101-149): copy_data LCN + "
+                                    "4 x census_sad 9x9 + smoothness + 6 pairs x 2 directions of the flow-consistency loss, "
+                                    "module/autograd path, see tools/bench_mf.py --sf"}
+            del w
         except Exception as e:
-            mf_line = f"unavailable: {type(e).__name__}: {e}"[:200]
+            if mf_line is None:
+                mf_line = f"unavailable: {type(e).__name__}: {e}"[:200]
+            else:
+                sfg_line = f"unavailable: {type(e).__name__}: {e}"[:200]
 
     if rank == 0:
         cpu = None
@@ -426,7 +446,7 @@ def run_ours(args):
             "e2e": {"value": e2e_value, "unit": UNIT,
                     "h2d_bytes_per_step": int((2 + N_SCALES) * 4 * P * n), "d2h_bytes_per_step": 4},
             "gpu_launches": launches, "cuda_graph_ms_per_step": graph_ms, "autograd_modules_ms_per_step": autograd_ms,
-            "dis_mf": mf_line,
+            "dis_mf": mf_line, "dis_sf_with_geometric_terms": sfg_line,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": measured_traffic("pattern_multi_kernel<census_sad, R=4, 4 scales, grad>", n),
                          "algorithmic_bytes": KERNEL_ALGO_BYTES_PER_FRAME * P * n,
