@@ -54,11 +54,12 @@ SIGNATURES = {
     "dis_flow_consistency_forward": [_f] * 10 + [_i, _f, _f, _f, _fl, _fl, _f, _f, _f, _f, _f, _i, _i, _i, _st],
     "dis_geometric_grad_combine": [_c.POINTER(_c.c_void_p), _c.POINTER(_c.c_int), _i, _f, _f, _fl, _f, _i, _i, _i, _i, _st],
     "dis_conv3d_out_size": [_i, _i, _i],
+    "dis_conv3d_scratch_elems": [_i, _i, _i, _i],
     "dis_conv3d_gather_forward": [_f, _f, _f, _f, _f, _f, _f, _i, _i, _i, _i, _i, _i, _i, _i, _st],
     "dis_conv3d_gather_backward": [_f, _f, _f, _f, _f, _i, _i, _i, _i, _i, _i, _i, _i, _st],
     "dis_combine2": [_f, _f, _f, _sz, _f, _f, _f, _fl, _st],
 }
-_RESTYPE = {"dis_status_string": _c.c_char_p, "dis_last_cuda_error": _c.c_char_p}
+_RESTYPE = {"dis_status_string": _c.c_char_p, "dis_last_cuda_error": _c.c_char_p, "dis_conv3d_scratch_elems": _c.c_size_t}
 OPTIONAL = set()
 
 _lib = None

@@ -485,10 +485,10 @@ def conv3d_gather_forward(xyz, feat, mask, ksize, stride, neighbors):
         xyz_nb = torch.empty((M, neighbors, 3), dtype=torch.float32, device=xyz.device)
         feat_nb = torch.empty((M, neighbors, C), dtype=torch.float32, device=xyz.device)
         idx = torch.empty((M, neighbors), dtype=torch.uint8, device=xyz.device)
-        scratch = torch.empty(1, dtype=torch.float32, device=xyz.device)
+        scratch = torch.empty(lib.dis_conv3d_scratch_elems(tl, bs, h, w), dtype=torch.float32, device=xyz.device)
         _lib.check(lib.dis_conv3d_gather_forward(_ptr(xyz), _ptr(feat), _ptr(mask), _ptr(xyz_nb), _ptr(feat_nb), _ptr(idx),
                                                  _ptr(scratch), tl, bs, C, h, w, int(ksize), int(stride), int(neighbors),
-                                                 _stream(xyz)), launches=3)
+                                                 _stream(xyz)), launches=4)
     return xyz_nb, feat_nb, idx, (oh, ow)
 
 

@@ -46,6 +46,7 @@ int geometric_grad_combine(const float* const*, const int*, int, const float*, c
                            cudaStream_t);
 
 int conv3d_out_size(int, int, int);
+size_t conv3d_scratch_elems(int, int, int, int);
 int conv3d_gather_forward(const float*, const float*, const float*, float*, float*, uint8_t*, float*, int, int, int, int,
                           int, int, int, int, cudaStream_t);
 int conv3d_gather_backward(const float*, const float*, const uint8_t*, float*, float*, int, int, int, int, int, int, int,
@@ -117,7 +118,7 @@ using namespace dis;
 
 extern "C" {
 
-int dis_abi_version(void) { return 1; }
+int dis_abi_version(void) { return 2; }
 
 const char* dis_status_string(int status) {
   switch (status) {
@@ -473,6 +474,11 @@ int dis_geometric_grad_combine(const float* const* planes, const int* frame_of, 
 int dis_conv3d_out_size(int n, int ksize, int stride) {
   if (n < 1 || ksize < 1 || (ksize & 1) == 0 || stride < 1) return DIS_ERR_BAD_SHAPE;
   return conv3d_out_size(n, ksize, stride);
+}
+
+size_t dis_conv3d_scratch_elems(int tl, int bs, int h, int w) {
+  if (tl < 1 || bs < 0 || h < 1 || w < 1) return 0;
+  return conv3d_scratch_elems(tl, bs, h, w);
 }
 
 static int check_conv3d(int tl, int bs, int C, int h, int w, int ksize, int stride, int neighbors) {

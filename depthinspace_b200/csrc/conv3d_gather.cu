@@ -19,7 +19,7 @@ constexpr int MAX_KK = 64;   // window positions k*k (api.cu admits k*k*tl <= 64
 
 struct C3Args {
   const float* xyz; const float* feat; const float* mask;
-  float* xyz_nb; float* feat_nb; uint8_t* idx; float* gmax;
+  float* xyz_nb; float* feat_nb; uint8_t* idx; float* gmax; float* plane;
   int tl, bs, C, h, w, k, stride, nb, oh, ow;
 };
 
@@ -38,15 +38,38 @@ __device__ __forceinline__ void load_xyz(const C3Args& a, int t, int b, int y, i
   v[0] = __ldg(p); v[1] = __ldg(p + hw); v[2] = __ldg(p + 2 * hw);
 }
 
-// plane = xyz / (z + 1e-12)  (:489);  returns sum_c (plane_c - centre_plane_c)^2  (:493-495)
+// plane = xyz / (z + 1e-12)  (:489), once per source element instead of once per (output pixel, candidate): every
+// element is a candidate of up to k*k output pixels and both ranking passes need it (IEEE divisions: ~10 instructions
+// each).  Zero-padded candidates have xyz = 0, i.e. plane = 0 / 1e-12 = 0 exactly, and need no storage.
+__global__ void __launch_bounds__(256) conv3d_plane_kernel(const float* __restrict__ xyz, float* __restrict__ plane,
+                                                           size_t hw, size_t total) {
+  for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < total; i += (size_t)gridDim.x * 256) {
+    const size_t tb = i / hw, pix = i - tb * hw;
+    const float* p = xyz + tb * 3 * hw + pix;
+    float* o = plane + tb * 3 * hw + pix;
+    const float x = __ldg(p), y = __ldg(p + hw), z = __ldg(p + 2 * hw);
+    const float den = z + 1e-12f;
+    o[0] = __fdiv_rn(x, den); o[hw] = __fdiv_rn(y, den); o[2 * hw] = __fdiv_rn(z, den);
+  }
+}
+
+__device__ __forceinline__ void load_plane(const C3Args& a, int t, int b, int y, int x, bool inside, float v[3]) {
+  if (!inside) { v[0] = v[1] = v[2] = 0.f; return; }
+  const size_t hw = (size_t)a.h * a.w;
+  const float* p = a.plane + ((size_t)(t * a.bs + b) * 3) * hw + (size_t)y * a.w + x;
+  v[0] = __ldg(p); v[1] = __ldg(p + hw); v[2] = __ldg(p + 2 * hw);
+}
+
+// sum_c (plane_c - centre_plane_c)^2  (:493-495)
 __device__ __forceinline__ float plane_sq(const float v[3], const float cpl[3]) {
-  const float den = v[2] + 1e-12f;
-  const float d0 = __fdiv_rn(v[0], den) - cpl[0], d1 = __fdiv_rn(v[1], den) - cpl[1], d2 = __fdiv_rn(v[2], den) - cpl[2];
+  const float d0 = v[0] - cpl[0], d1 = v[1] - cpl[1], d2 = v[2] - cpl[2];
   return __fmaf_rn(d2, d2, __fmaf_rn(d1, d1, __fmul_rn(d0, d0)));
 }
 
-// FIXED: the reference configuration (3 x 3 window, 4 frames = 36 candidates) with every loop unrolled, so that the
-// keys live in registers instead of a local-memory array
+// FIXED: the reference configuration (3 x 3 window, 4 frames = 36 candidates, 9 neighbours), every loop unrolled.
+// The winners are kept as a sorted list in registers: a candidate is inserted behind every entry whose key is <= its
+// own (compare-and-select per slot, no branches) -- "ascending key, ties -> lowest candidate index", because candidates
+// arrive in index order.
 template <bool SELECT, bool FIXED>
 __global__ void __launch_bounds__(128) conv3d_rank_kernel(C3Args a) {
   const int m = blockIdx.x * blockDim.x + threadIdx.x;
@@ -56,15 +79,19 @@ __global__ void __launch_bounds__(128) conv3d_rank_kernel(C3Args a) {
     const int b = m / (a.oh * a.ow), r = m - b * a.oh * a.ow, oy = r / a.ow, ox = r - oy * a.ow;
     const int kw = FIXED ? 3 : a.k, tl = FIXED ? 4 : a.tl;
     const int ncand = FIXED ? 36 : a.k * a.k * a.tl;
+    const int nb = FIXED ? 9 : a.nb;
     const int pad = (kw - 1) / 2;
-    // centre candidate: (ky, kx) = (pad, pad), t = 0   (tidx = (k*k // 2) * tl, :491)
+    // centre candidate: (ky, kx) = (pad, pad), t = 0   (tidx = (k*k // 2) * tl, :491); always inside the image
     int cy, cx; bool cin;
     cand_pos(a, oy, ox, pad, pad, cy, cx, cin);
-    float cxyz[3];
-    load_xyz(a, 0, b, cy, cx, cin, cxyz);
-    const float cden = cxyz[2] + 1e-12f;
-    const float cpl[3] = {__fdiv_rn(cxyz[0], cden), __fdiv_rn(cxyz[1], cden), __fdiv_rn(cxyz[2], cden)};
-    float key[FIXED ? 36 : MAX_CAND];
+    float cpl[3];
+    load_plane(a, 0, b, cy, cx, cin, cpl);
+    constexpr int NBMAX = FIXED ? 9 : 16;
+    constexpr float SENTINEL = 3.402823466e38f;       // FLT_MAX: above every key (keys are <= global max + 1)
+    float bestk[NBMAX];
+    int besti[NBMAX];
+#pragma unroll
+    for (int j = 0; j < NBMAX; ++j) { bestk[j] = SENTINEL; besti[j] = 0; }
     const float big = SELECT ? __ldg(a.gmax) + 1.0f : 0.f;
     const size_t hw = (size_t)a.h * a.w;
 #pragma unroll (FIXED ? 36 : 1)
@@ -73,32 +100,41 @@ __global__ void __launch_bounds__(128) conv3d_rank_kernel(C3Args a) {
       int y, x; bool in;
       cand_pos(a, oy, ox, ky, kx, y, x, in);
       float v[3];
-      load_xyz(a, t, b, y, x, in, v);
+      load_plane(a, t, b, y, x, in, v);
       const float sq = plane_sq(v, cpl);
       if (SELECT) {
         const float mk = in ? __ldg(a.mask + (size_t)(t * a.bs + b) * hw + (size_t)y * a.w + x) : 0.f;
-        key[c] = __fmaf_rn(mk, sq, __fmul_rn(1.0f - mk, big));     // mask*sq + (1-mask)*(max+1), :497
+        const float key = __fmaf_rn(mk, sq, __fmul_rn(1.0f - mk, big));     // mask*sq + (1-mask)*(max+1), :497
+        {   // branch-free insertion (an early "not better than the current worst" exit saved < 10 %)
+          bool lt[NBMAX];
+#pragma unroll
+          for (int j = 0; j < NBMAX; ++j) lt[j] = key < bestk[j];           // monotone: the list is sorted
+#pragma unroll
+          for (int j = NBMAX - 1; j >= 1; --j) {                           // descending: reads the old neighbours
+            bestk[j] = lt[j - 1] ? bestk[j - 1] : (lt[j] ? key : bestk[j]);
+            besti[j] = lt[j - 1] ? besti[j - 1] : (lt[j] ? c : besti[j]);
+          }
+          bestk[0] = lt[0] ? key : bestk[0];
+          besti[0] = lt[0] ? c : besti[0];
+        }
       } else {
         local_max = fmaxf(local_max, sq);
       }
     }
     if (SELECT) {
-      uint64_t taken = 0;
-      for (int j = 0; j < a.nb; ++j) {
-        int best = -1; float bk = 0.f;
-#pragma unroll (FIXED ? 36 : 1)
-        for (int c = 0; c < ncand; ++c) {
-          const bool better = !((taken >> c) & 1) && (best < 0 || key[c] < bk);   // ties: lowest index wins
-          if (better) { best = c; bk = key[c]; }
-        }
-        taken |= (uint64_t)1 << best;
-        a.idx[(size_t)m * a.nb + j] = (uint8_t)best;
+      float cxyz[3];
+      load_xyz(a, 0, b, cy, cx, cin, cxyz);
+#pragma unroll
+      for (int j = 0; j < NBMAX; ++j) {
+        if (j >= nb) break;
+        const int best = besti[j];
+        a.idx[(size_t)m * nb + j] = (uint8_t)best;
         const int t = best % tl, kk = best / tl, ky = kk / kw, kx = kk - ky * kw;
         int y, x; bool in;
         cand_pos(a, oy, ox, ky, kx, y, x, in);
         float v[3];
         load_xyz(a, t, b, y, x, in, v);
-        float* o = a.xyz_nb + ((size_t)m * a.nb + j) * 3;
+        float* o = a.xyz_nb + ((size_t)m * nb + j) * 3;
         o[0] = v[0] - cxyz[0]; o[1] = v[1] - cxyz[1]; o[2] = v[2] - cxyz[2];     // xyz_local, :492
       }
     }
@@ -297,14 +333,20 @@ inline int flat_grid(size_t total, int threads) {
 
 int conv3d_out_size(int n, int k, int stride) { return (n + 2 * ((k - 1) / 2) - k) / stride + 1; }
 
+size_t conv3d_scratch_elems(int tl, int bs, int h, int w) { return 4 + (size_t)tl * bs * 3 * h * w; }
+
+// scratch: [0] = global max of the squared plane distances, [4 ...] = plane coordinates [tl,bs,3,h,w]
 int conv3d_gather_forward(const float* xyz, const float* feat, const float* mask, float* xyz_nb, float* feat_nb,
-                          uint8_t* idx, float* gmax, int tl, int bs, int C, int h, int w, int k, int stride, int nb,
+                          uint8_t* idx, float* scratch, int tl, int bs, int C, int h, int w, int k, int stride, int nb,
                           cudaStream_t s) {
-  C3Args a{xyz, feat, mask, xyz_nb, feat_nb, idx, gmax, tl, bs, C, h, w, k, stride, nb,
+  float* gmax = scratch;
+  C3Args a{xyz, feat, mask, xyz_nb, feat_nb, idx, gmax, scratch + 4, tl, bs, C, h, w, k, stride, nb,
            conv3d_out_size(h, k, stride), conv3d_out_size(w, k, stride)};
   const int M = bs * a.oh * a.ow;
   cudaError_t e = cudaMemsetAsync(gmax, 0, sizeof(float), s);
   if (e != cudaSuccess) { set_last_cuda_error(e); return DIS_ERR_CUDA_LAUNCH; }
+  const size_t n_src = (size_t)tl * bs * h * w;
+  conv3d_plane_kernel<<<flat_grid(n_src, 256), 256, 0, s>>>(xyz, a.plane, (size_t)h * w, n_src);
   if (k == 3 && tl == 4) {
     conv3d_rank_kernel<false, true><<<(M + 127) / 128, 128, 0, s>>>(a);
     conv3d_rank_kernel<true, true><<<(M + 127) / 128, 128, 0, s>>>(a);

@@ -241,9 +241,12 @@ DIS_API int dis_geometric_grad_combine(const float* const* planes, const int* fr
  * (ksize x ksize window, zero padding (ksize-1)/2, given stride) the `neighbors` candidates (of ksize^2*tl <= 64)
  * closest to the centre ray in the normalised image plane:
  *   xyz_nb [M,neighbors,3] = xyz_local, feat_nb [M,neighbors,C], idx [M,neighbors] uint8 candidate index
- *   ((ky*ksize + kx)*tl + t, ascending key, ties -> lowest index); scratch: 1 float on the device.
+ *   ((ky*ksize + kx)*tl + t, ascending key, ties -> lowest index);
+ *   scratch: dis_conv3d_scratch_elems(tl, bs, h, w) floats on the device (global maximum + the normalised image-plane
+ *   coordinates xyz / (z + 1e-12), computed once per source element).   [ABI 2: was 1 float in ABI 1]
  * backward: deterministic gather; g_xyz / g_feat may be NULL. */
 DIS_API int dis_conv3d_out_size(int n, int ksize, int stride);
+DIS_API size_t dis_conv3d_scratch_elems(int tl, int bs, int h, int w);
 DIS_API int dis_conv3d_gather_forward(const float* xyz, const float* feat, const float* mask, float* xyz_nb,
                                       float* feat_nb, uint8_t* idx, float* scratch, int tl, int bs, int C, int h,
                                       int w, int ksize, int stride, int neighbors, void* stream);
