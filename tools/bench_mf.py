@@ -31,6 +31,7 @@ HW = synth.DATASET_HW
 FEAT = ((HW[0] // 2, HW[1] // 2), (HW[0] // 4, HW[1] // 4))   # 256x216, 128x108
 C_FEAT, BLOCKS = 32, 4
 ALL_FRAMES = True
+CONV3D = False
 
 
 def build(bs, dev):
@@ -68,9 +69,20 @@ def build(bs, dev):
         grads.append(torch.randn(TL, bs, C_FEAT, h, w, device=dev, generator=gen))
         grads_all.append(grads[-1][None].expand(TL, -1, -1, -1, -1, -1).contiguous())
     xyz = torch.randn(TL, bs, 3, *FEAT[0], device=dev, generator=gen)
+    xyz_lvl, mask_lvl, g_nb = [], [], []
+    if CONV3D:
+        for (h, w) in FEAT:
+            v, u = torch.meshgrid(torch.arange(h, device=dev, dtype=torch.float32), torch.arange(w, device=dev, dtype=torch.float32), indexing="ij")
+            xl = torch.empty(TL, bs, 3, h, w, device=dev)
+            for fr_i in range(TL):
+                z = 1.5 + 0.2 * torch.sin(u / 40 + fr_i) * torch.cos(v / 55) + 0.002 * torch.randn(bs, h, w, device=dev, generator=gen)
+                xl[fr_i, :, 0], xl[fr_i, :, 1], xl[fr_i, :, 2] = (u - w / 2 + 0.3 * fr_i) / (1.3 * w) * z, (v - h / 2 - 0.2 * fr_i) / (1.3 * w) * z, z
+            xyz_lvl.append(xl)
+            mask_lvl.append((torch.rand(TL, bs, 1, h, w, device=dev, generator=gen) > 0.1).float())
+            g_nb.append(torch.randn(bs * h * w, 9, C_FEAT, device=dev, generator=gen))
     im_bt = view(im).transpose(0, 1).contiguous()      # the DataLoader hands frames over as [bs, tl, 1, H, W]
     return dict(im=view(im), im_bt=im_bt, amb=view(amb), disp=view(disp), prim=view(dgt + 0.3), R=R, t=t, flow=flow, loss=loss, lcn=lcn,
-                feats=feats, flows_lr=flows_lr, grads=grads, grads_all=grads_all, xyz=xyz, bs=bs)
+                feats=feats, flows_lr=flows_lr, grads=grads, grads_all=grads_all, xyz=xyz, bs=bs, xyz_lvl=xyz_lvl, mask_lvl=mask_lvl, g_nb=g_nb)
 
 
 class Sections:
@@ -112,8 +124,21 @@ def step(w):
         for _ in range(BLOCKS):
             if ALL_FRAMES:       # one gather for all target frames (the tidx loop of fwd_3d_1 / fwd_3d_2 as one op)
                 with torch.no_grad():
-                    mfn.gather_warped_all(x, fl)
-                mfn.gather_warped_all(x, fl).backward(w["grads_all"][lvl])
+                    warped = mfn.gather_warped_all(x, fl)
+                    if CONV3D:   # Conv3D's neighbour selection + gather on every target frame (checkpointed forward)
+                        for tidx in range(TL):
+                            mfn.conv3d_gather(w["xyz_lvl"][lvl], warped[tidx], w["mask_lvl"][lvl], 3, 1, 9)
+                warped = mfn.gather_warped_all(x, fl)
+                if CONV3D:
+                    g_acc = torch.zeros_like(warped)
+                    for tidx in range(TL):
+                        wf = warped[tidx].detach().requires_grad_(True)
+                        _, feat_nb, _ = mfn.conv3d_gather(w["xyz_lvl"][lvl], wf, w["mask_lvl"][lvl], 3, 1, 9)
+                        feat_nb.backward(w["g_nb"][lvl])
+                        g_acc[tidx] = wf.grad
+                    warped.backward(g_acc)
+                else:
+                    warped.backward(w["grads_all"][lvl])
                 continue
             for tidx in range(TL):
                 with torch.no_grad():
@@ -143,7 +168,7 @@ def build_sf(bs, dev):
     K = torch.from_numpy(g["K"].astype(np.float64))
     w["loss"] = losses.SingleFrameLoss(HW[0], HW[1], pattern, K=K, Ki=torch.linalg.inv(K), focal_length=float(g["K"][0, 0]),
                                        baseline=0.075).to(dev)
-    for k in ("feats", "flows_lr", "grads", "grads_all", "xyz"):
+    for k in ("feats", "flows_lr", "grads", "grads_all", "xyz", "xyz_lvl", "mask_lvl", "g_nb"):
         w.pop(k)
     return w
 
@@ -166,10 +191,13 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--per-frame-gathers", action="store_true", help="one gather call per target frame (reference loop shape)")
+    ap.add_argument("--conv3d", action="store_true", help="also run Conv3D's neighbour selection + gather (SURVEY 8(f) row 3) on every "
+                    "gathered stack: forward, checkpoint recompute and backward")
     ap.add_argument("--sf", action="store_true", help="time the DIS-SF loss WITH its 12 flow-consistency terms instead (bs 64 = 256 frames)")
     a = ap.parse_args()
-    global ALL_FRAMES
+    global ALL_FRAMES, CONV3D
     ALL_FRAMES = not a.per_frame_gathers
+    CONV3D = a.conv3d
     dev = torch.device("cuda")
     run_step = step_sf if a.sf else step
     if a.sf and a.bs == [4, 32]:
@@ -196,7 +224,7 @@ def main():
                 "BASELINE configs[2]: DIS-MF hot path (copy_data LCN + 24 xyz/flow warps + 96 C=32 feature warps "
                 "fwd/recompute/bwd + 1-scale census_sad loss + smoothness + 12 flow-consistency terms + L1), fwd+bwd")
         print(json.dumps({"workload": name,
-                          "gather": "all frames per call" if ALL_FRAMES else "one call per target frame", "bs": bs, "tl": TL, "frames": n, "ms_per_step": round(ms, 3), "frames_per_s": round(n / (ms * 1e-3), 1),
+                          "gather": "all frames per call" if ALL_FRAMES else "one call per target frame", "conv3d_gather": CONV3D, "bs": bs, "tl": TL, "frames": n, "ms_per_step": round(ms, 3), "frames_per_s": round(n / (ms * 1e-3), 1),
                           "gpu_launches_per_step": launches, "sections": SEC.summary(a.steps), "loss": float(total.detach())}), flush=True)
         del w
         torch.cuda.empty_cache()
