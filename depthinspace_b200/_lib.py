@@ -29,6 +29,7 @@ SIGNATURES = {
     "dis_pattern_warp_forward": [_f, _f, _f, _f, _f, _f, _i, _i, _i, _st],
     "dis_pattern_loss_num_partials": [_i, _i, _i],
     "dis_pattern_loss_forward": [_f, _f, _f, _f, _f, _f, _f, _f, _i, _i, _i, _i, _i, _fl, _st],
+    "dis_pattern_loss_forward_scaled": [_f, _f, _f, _f, _f, _f, _f, _f, _f, _i, _i, _i, _i, _i, _fl, _st],
     "dis_reduce_pairs": [_f, _i, _f, _st],
     "dis_reduce_pairs_batched": [_f, _i, _i, _f, _st],
     "dis_pattern_loss_multi_num_partials": [_i, _i, _i],

@@ -115,8 +115,9 @@ def pattern_warp(disp, pattern, want_dproj=False, want_corners=False):
     return proj, dproj, cx, cy
 
 
-def pattern_loss_forward(disp, im, std, pattern, block_size, type, eps, want_proj, want_diff, want_grad):
-    """-> (out3 [num, den, num/den], proj|None, diff|None, grad_num|None)"""
+def pattern_loss_forward(disp, im, std, pattern, block_size, type, eps, want_proj, want_diff, want_grad, grad_scale=None):
+    """-> (out3 [num, den, num/den], proj|None, diff|None, grad_num|None); grad_scale: optional one-element device
+    tensor the stored gradient is multiplied by inside the kernel."""
     disp, im = _chk(disp, "disp0"), _chk(im, "im")
     N, C, H, W = disp.shape
     if C != 1 or tuple(im.shape) != (N, 1, H, W):
@@ -137,9 +138,11 @@ def pattern_loss_forward(disp, im, std, pattern, block_size, type, eps, want_pro
         npart = lib.dis_pattern_loss_num_partials(N, H, W)
         partials = torch.empty(2 * max(npart, 1), dtype=torch.float32, device=disp.device)
         s = _stream(disp)
-        _lib.check(lib.dis_pattern_loss_forward(_ptr(disp), _ptr(im), _ptr(std), _ptr(pattern), _ptr(proj), _ptr(diff),
-                                                _ptr(gnum), _ptr(partials), N, H, W, int(block_size),
-                                                loss_type_id(type), float(eps), s))
+        if grad_scale is not None:
+            grad_scale = _chk(grad_scale, "grad_scale", 1)
+        _lib.check(lib.dis_pattern_loss_forward_scaled(_ptr(disp), _ptr(im), _ptr(std), _ptr(pattern), _ptr(proj), _ptr(diff),
+                                                       _ptr(gnum), _ptr(grad_scale), _ptr(partials), N, H, W,
+                                                       int(block_size), loss_type_id(type), float(eps), s))
         _lib.check(lib.dis_reduce_pairs(_ptr(partials), npart, _ptr(out3), s))
     return out3, proj, diff, gnum
 

@@ -228,6 +228,13 @@ int dis_pattern_loss_num_partials(int N, int H, int W) {
 int dis_pattern_loss_forward(const float* disp, const float* im, const float* std_in, const float* pattern,
                              float* proj, float* diff, float* grad_num, float* partials, int N, int H, int W,
                              int block_size, int type, float eps, void* stream) {
+  return dis_pattern_loss_forward_scaled(disp, im, std_in, pattern, proj, diff, grad_num, nullptr, partials, N, H, W,
+                                         block_size, type, eps, stream);
+}
+
+int dis_pattern_loss_forward_scaled(const float* disp, const float* im, const float* std_in, const float* pattern,
+                                    float* proj, float* diff, float* grad_num, const float* grad_scale, float* partials,
+                                    int N, int H, int W, int block_size, int type, float eps, void* stream) {
   if (int rc = check_block(block_size, type)) return rc;
   if (!disp || !im || !pattern || !partials) return DIS_ERR_NULL_POINTER;
   if (N < 0 || H < 2 || W < 2) return DIS_ERR_BAD_SHAPE;
@@ -240,6 +247,7 @@ int dis_pattern_loss_forward(const float* disp, const float* im, const float* st
     a.pattern = pattern;
     a.proj = proj ? proj + n0 * hw : nullptr; a.diff = diff ? diff + n0 * hw : nullptr;
     a.grad_num = grad_num ? grad_num + n0 * hw : nullptr;
+    a.grad_scale = grad_scale;
     a.partials = partials + (size_t)2 * n0 * per_frame;
     a.N = N - n0 < MAX_GRID_Z ? N - n0 : MAX_GRID_Z; a.H = H; a.W = W;
     a.eps = eps; a.inv_k2 = 1.0f / (float)(block_size * block_size);

@@ -226,6 +226,7 @@ __global__ void __launch_bounds__(NTHREADS, 3) box_pattern_loss_kernel(PatternLo
   float acc[2][4];
   box_cols<R>(hS, tx, ty, acc);
 
+  const float gk = (GRAD && a.grad_scale) ? a.inv_k2 * __ldg(a.grad_scale) : a.inv_k2;
   float num = 0.0f, den = 0.0f;
 #pragma unroll
   for (int r = 0; r < 2; ++r) {
@@ -239,7 +240,7 @@ __global__ void __launch_bounds__(NTHREADS, 3) box_pattern_loss_kernel(PatternLo
       d[i] = acc[r][i] * a.inv_k2;
       if (valid) { num = fmaf(wc, d[i], num); den += wc; }
       ev[i] = sE[(2 * ty + r) * TW + 4 * tx + i];
-      if (GRAD) gv[i] = sF[(2 * ty + r) * TW + 4 * tx + i] * gsum[r][i] * a.inv_k2;
+      if (GRAD) gv[i] = sF[(2 * ty + r) * TW + 4 * tx + i] * gsum[r][i] * gk;
     }
     if (a.diff) store_quad(a.diff + (size_t)n * hw, gy, x0 + 4 * tx, a.H, a.W, a.vec_ok, d[0], d[1], d[2], d[3]);
     if (a.proj) store_quad(a.proj + (size_t)n * hw, gy, x0 + 4 * tx, a.H, a.W, a.vec_ok, ev[0], ev[1], ev[2], ev[3]);

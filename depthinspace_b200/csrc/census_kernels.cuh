@@ -266,6 +266,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) census_pattern_loss_kernel(Patter
     __syncthreads();
   }
   const float fs = fwd_scale<TYPE>() * a.inv_k2;
+  const float gk = (GRAD && a.grad_scale) ? a.inv_k2 * __ldg(a.grad_scale) : a.inv_k2;
   float num = 0.0f, den = 0.0f;
 #pragma unroll
   for (int r = 0; r < 2; ++r) {
@@ -283,7 +284,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) census_pattern_loss_kernel(Patter
           const int slot = border_slot(2 * ty + r, 4 * tx + i, gy, gx, a.H, a.W);
           if (slot >= 0) g = fix[slot];
         }
-        gv[i] = finish_grad<TYPE>(g, ec[r][i], tc[r][i], a.eps) * a.inv_k2 * sdd[(2 * ty + r) * TW + 4 * tx + i];
+        gv[i] = finish_grad<TYPE>(g, ec[r][i], tc[r][i], a.eps) * gk * sdd[(2 * ty + r) * TW + 4 * tx + i];
       }
     }
     if (a.diff) store_quad(a.diff + (size_t)n * hw, gy, x0 + 4 * tx, a.H, a.W, a.vec_ok, d[0], d[1], d[2], d[3]);

@@ -20,6 +20,7 @@ struct PhotoArgs {
 struct PatternLossArgs {
   const float* disp; const float* im; const float* std_in; const float* pattern;
   float* proj; float* diff; float* grad_num; float* partials;
+  const float* grad_scale;   // optional device scalar: grad_num is multiplied by it (final gradient, no scaling pass)
   int N, H, W;
   float eps, inv_k2, inv_w, inv_h;
   int vec_ok;

@@ -161,8 +161,8 @@ class _HotPathLoss(torch.nn.Module):
         ph = self.ph_loss
         type_id = _ops.loss_type_id(ph.loss_type)
         S = len(out)
-        if type_id < 2 or S not in (2, 4):
-            raise ValueError("value_and_grad covers the census losses with 2 or 4 scales; use forward() otherwise")
+        if S not in (1, 2, 4) or (type_id < 2 and S != 1):
+            raise ValueError("value_and_grad covers 1 scale (any loss type) or 2 / 4 scales (census types); use forward() otherwise")
         im, std_m, amb = _merge(im_lcn)[:, 0:1].contiguous(), _merge(std), _merge(ambient)
         disps = [_merge(o).detach() for o in out]
         dev, group = im.device, ph.process_group
@@ -187,8 +187,14 @@ class _HotPathLoss(torch.nn.Module):
         if getattr(self, "_w_ph_key", None) != key:      # constant weights 1 / 2^s, uploaded once
             self._w_ph, self._w_ph_key = torch.tensor([1.0 / 2 ** s for s in range(S)], device=dev), key
         w_ph = self._w_ph
-        out3, grads = _ops.pattern_loss_multi_forward(disps, im, std_m, ph.pattern, ph.block_size, type_id, ph.loss_eps, True,
-                                                      grad_scale=(w_ph / den).contiguous())
+        scale = (w_ph / den).contiguous()
+        if S == 1:
+            o3, _, _, g0 = _ops.pattern_loss_forward(disps[0], im, std_m, ph.pattern, ph.block_size, type_id, ph.loss_eps,
+                                                     False, False, True, grad_scale=scale)
+            out3, grads = o3.unsqueeze(0), [g0]
+        else:
+            out3, grads = _ops.pattern_loss_multi_forward(disps, im, std_m, ph.pattern, ph.block_size, type_id, ph.loss_eps, True,
+                                                          grad_scale=scale)
         num = out3[:, 0].contiguous()
         if group is not None:
             all_reduce_sum_(num, group)
@@ -271,3 +277,9 @@ class MultiFrameLoss(_HotPathLoss):
             noise = sgm_noise if sgm_noise is not None else 1.5 * torch.randn_like(out[0])
             vals.append(masked_l1_mean(out[0], sgm_disp, noise, 30.0, self.ph_loss.process_group) * 0.1)
         return vals
+
+    def value_and_grad(self, out, im_lcn, std, ambient, primary_disp=None, warmup=True, global_frames=None):
+        """Photometric + smoothness (+ primary-disparity L1) terms of forward() and d(sum)/d out, see _value_and_grad;
+        the geometric terms stay on forward()."""
+        tgt = primary_disp if (primary_disp is not None and warmup) else None
+        return self._value_and_grad(out, im_lcn, std, ambient, tgt, [(0, 0.1)], global_frames)

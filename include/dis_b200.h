@@ -103,6 +103,11 @@ DIS_API int dis_pattern_loss_forward(const float* disp, const float* im, const f
                                      const float* pattern, float* proj, float* diff, float* grad_num,
                                      float* partials, int N, int H, int W, int block_size, int type,
                                      float eps, void* stream);
+/* Same with grad_num already multiplied by the DEVICE scalar *grad_scale (weight / sum(sigma)): final gradient. */
+DIS_API int dis_pattern_loss_forward_scaled(const float* disp, const float* im, const float* std_in,
+                                            const float* pattern, float* proj, float* diff, float* grad_num,
+                                            const float* grad_scale, float* partials, int N, int H, int W,
+                                            int block_size, int type, float eps, void* stream);
 
 /* Deterministic fixed-order reduction of n (a,b) pairs: out = {sum a, sum b, sum a / sum b}. */
 DIS_API int dis_reduce_pairs(const float* partials, int n, float* out3, void* stream);

@@ -1163,3 +1163,24 @@ def test_sgm_warmup_term_matches_reference_formula(mods):
     mv = mloss(o0, im_cat, view(im_s), view(d["ambient"]), sgm_disp=sgm, sgm_noise=noise[0])
     assert len(mv) == 3
     assert_scalar_close(mv[2].item(), rvals[0].item(), name="multi-frame warm-up term")
+
+
+@pytest.mark.parametrize("lt", ["census_sad", "mse"])
+def test_multi_frame_value_and_grad_equals_autograd(mods, lt):
+    """MultiFrameLoss.value_and_grad (single-scale kernel with the final gradient, dis_pattern_loss_forward_scaled) ==
+    forward() + autograd for the photometric, smoothness and primary-disparity terms."""
+    from depthinspace_b200 import losses
+    hw, tl, bs = (52, 76), 2, 2
+    d, im_l, im_s, pat = _frames(tl * bs, hw, "default", seed=17)
+    view = lambda a: dev(a).view(tl, bs, *a.shape[1:])
+    im_cat = torch.cat((view(im_l), view(d["im"])), dim=2)
+    prim = view((d["disp_gt"] + 0.3).astype(np.float32))
+    loss = losses.MultiFrameLoss(hw[0], hw[1], dev(np.repeat(pat, 3, axis=1)), loss_type=lt)
+    o = view(d["disp_pred"][0]).requires_grad_(True)
+    vals = loss(o, im_cat, view(im_s), view(d["ambient"]), primary_disp=prim)
+    sum(vals).backward()
+    fvals, grads = loss.value_and_grad(o.detach(), im_cat, view(im_s), view(d["ambient"]), primary_disp=prim)
+    assert len(fvals) == len(vals) == 3 and len(grads) == 1
+    for k, (a, b) in enumerate(zip(fvals, vals)):
+        assert_scalar_close(a.item(), b.item(), 2e-6, f"term {k}")
+    assert_close(grads[0], o.grad, 2e-6, "gradient")
