@@ -52,10 +52,16 @@ struct PatternMultiArgs {
   int vec_ok;                    // W even and grad pointers 8-byte aligned
 };
 
+// For the widest windows (R >= 6, 4 scales) the d proj / d disp plane would push a CTA past half of the SM's shared
+// memory and halve the occupancy; there it is re-derived in the epilogue instead (a few % more arithmetic).
+template <int R, int NPAIR>
+__host__ __device__ constexpr bool multi_recompute_dd() { return R >= 6 && NPAIR == 2; }
+
 template <int R, int NPAIR>
 constexpr size_t pattern_multi_smem_bytes() {
   using G = MultiGeom<R>;
-  return sizeof(float) * ((size_t)2 * NPAIR * G::PLANE + 2 * G::PLANE + 2 * NPAIR * MTH * MTW + 2 * NPAIR * MFIX + 64) +
+  return sizeof(float) * ((size_t)2 * NPAIR * G::PLANE + 2 * G::PLANE +
+                          (multi_recompute_dd<R, NPAIR>() ? 0 : 2 * NPAIR * MTH * MTW) + 2 * NPAIR * MFIX + 64) +
          sizeof(WarpRow) * G::ROWS;
 }
 
@@ -88,12 +94,13 @@ __global__ void __launch_bounds__(256, 2) pattern_multi_kernel(PatternMultiArgs 
   static_assert(TYPE == CENSUS_MSE || TYPE == CENSUS_SAD, "multi-scale path is for the census types");
   using G = MultiGeom<R>;
   constexpr int S = 2 * NPAIR;
+  constexpr bool RDD = multi_recompute_dd<R, NPAIR>();
   extern __shared__ __align__(16) float smem[];
   float2* se = reinterpret_cast<float2*>(smem);              // [NPAIR][ROWS][PITCH] float2 = (scale 2p, scale 2p+1)
   float* st = smem + 2 * NPAIR * G::PLANE;                   // LCN image, replicate-clamped
   float* sw = st + G::PLANE;                                 // sigma (or 1), zero outside the image
   float* sdd = sw + G::PLANE;                                // [S][MTH][MTW] d proj / d disp of own pixels
-  float* fix = sdd + S * MTH * MTW;                          // [S][MFIX]
+  float* fix = sdd + (RDD ? 0 : S * MTH * MTW);              // [S][MFIX]
   float* red = fix + S * MFIX;                               // block-reduction scratch
   WarpRow* srow = reinterpret_cast<WarpRow*>(red + 64);      // y half of the pattern warp, one entry per tile row
   const int tx = threadIdx.x, ty = threadIdx.y, tid = ty * 32 + tx;
@@ -123,7 +130,7 @@ __global__ void __launch_bounds__(256, 2) pattern_multi_kernel(PatternMultiArgs 
     const float tv = __ldg(imp + g);
     const float wv = inside ? (sdp ? __ldg(sdp + g) : 1.0f) : 0.0f;
     const WarpRow row = srow[j];
-    const bool own = GRAD && j >= R && j < R + MTH && i >= R && i < R + MTW;
+    const bool own = GRAD && !RDD && j >= R && j < R + MTH && i >= R && i < R + MTW;
     float ev[S], dd[S];
 #pragma unroll
     for (int s = 0; s < S; ++s) ev[s] = warp_col_sample(a.pattern, row, dv[s], cx, a.W, a.inv_w, own ? &dd[s] : nullptr);
@@ -259,6 +266,13 @@ __global__ void __launch_bounds__(256, 2) pattern_multi_kernel(PatternMultiArgs 
       const int gx = x0 + 2 * tx + i;
       const bool valid = gy < a.H && gx < a.W;
       if (valid) den += wc[i];
+      float ddv[S];
+      if (GRAD && RDD) {
+        const WarpRow row = srow[ly + R];
+        const int cy = min(gy, a.H - 1), cx = min(gx, a.W - 1);
+#pragma unroll
+        for (int s = 0; s < S; ++s) warp_col_sample(a.pattern, row, __ldg(dptr[s] + cy * a.W + cx), cx, a.W, a.inv_w, &ddv[s]);
+      }
       int slot = -1;
       if (GRAD && edge_tile && valid) {
         if (gx == 0) slot = ly;
@@ -281,7 +295,7 @@ __global__ void __launch_bounds__(256, 2) pattern_multi_kernel(PatternMultiArgs 
         for (int h = 0; h < 2; ++h) {
           const int s = 2 * p + h;
           if (valid) num[s] = fmaf(wc[i], acc[p][i][h] * fs, num[s]);
-          if (GRAD) gout[s][i] = (h ? g1 : g0) * gss[s] * sdd[(s * MTH + ly) * MTW + 2 * tx + i];
+          if (GRAD) gout[s][i] = (h ? g1 : g0) * gss[s] * (RDD ? ddv[s] : sdd[(s * MTH + ly) * MTW + 2 * tx + i]);
         }
       }
     }

@@ -416,7 +416,7 @@ def test_flow_warp_golden(mods, golden):
 # ----------------------------------------------------------------------------- multi-scale kernel + loss assembly (a8)
 @pytest.mark.parametrize("lt", ["census_sad", "census_mse"])
 @pytest.mark.parametrize("S", [2, 4])
-@pytest.mark.parametrize("hw,k", [((70, 150), 9), ((33, 47), 5), ((64, 96), 13)])
+@pytest.mark.parametrize("hw,k", [((70, 150), 9), ((33, 47), 5), ((64, 96), 13), ((40, 70), 15), ((33, 65), 1)])
 def test_pattern_loss_multi_scale_kernel(mods, lt, S, hw, k):
     """Packed fp32x2 multi-scale kernel against the fp64 / fp32 oracle and against the single-scale kernel."""
     net, _, _ = mods
