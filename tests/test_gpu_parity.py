@@ -1184,3 +1184,47 @@ def test_multi_frame_value_and_grad_equals_autograd(mods, lt):
     for k, (a, b) in enumerate(zip(fvals, vals)):
         assert_scalar_close(a.item(), b.item(), 2e-6, f"term {k}")
     assert_close(grads[0], o.grad, 2e-6, "gradient")
+
+
+def test_batches_beyond_the_grid_z_limit(mods):
+    """More than 65 535 frames in one call: the entry points split the batch over several launches (gridDim.z limit);
+    results must equal the sum / concatenation of two half-batch calls."""
+    from depthinspace_b200 import _ops
+    net, ext, _ = mods
+    n, hw = 66000, (6, 10)
+    gen = torch.Generator(device="cuda").manual_seed(8)
+    r = lambda *s: torch.rand(*s, device="cuda", generator=gen)
+    es, ta = r(n, 1, *hw), r(n, 1, *hw)
+    out = _ops.photometric_loss_forward(es, ta, 3, "census_sad", 0.5)
+    half = n // 2
+    ref = torch.cat([_ops.photometric_loss_forward(es[:half].contiguous(), ta[:half].contiguous(), 3, "census_sad", 0.5),
+                     _ops.photometric_loss_forward(es[half:].contiguous(), ta[half:].contiguous(), 3, "census_sad", 0.5)])
+    assert torch.equal(out, ref)
+    go = r(n, 1, *hw)
+    g = _ops.photometric_loss_backward(es, ta, go, 3, "census_sad", 0.5)
+    gref = torch.cat([_ops.photometric_loss_backward(es[:half].contiguous(), ta[:half].contiguous(), go[:half].contiguous(), 3, "census_sad", 0.5),
+                      _ops.photometric_loss_backward(es[half:].contiguous(), ta[half:].contiguous(), go[half:].contiguous(), 3, "census_sad", 0.5)])
+    assert torch.equal(g, gref)
+    # fused pattern loss (single and multi scale), smoothness, LCN
+    disp = [r(n, 1, *hw) * 4 for _ in range(2)]
+    pat = r(1, 1, *hw)
+    sig = 0.1 + r(n, 1, *hw)
+    o3, _, _, gn = _ops.pattern_loss_forward(disp[0], ta, sig, pat, 3, "census_sad", 0.5, False, False, True)
+    parts = [_ops.pattern_loss_forward(disp[0][s].contiguous(), ta[s].contiguous(), sig[s].contiguous(), pat, 3, "census_sad", 0.5, False, False, True)
+             for s in (slice(0, half), slice(half, n))]
+    assert_scalar_close(o3[0].item(), (parts[0][0][0] + parts[1][0][0]).item(), 2e-6, "num")
+    assert_scalar_close(o3[1].item(), (parts[0][0][1] + parts[1][0][1]).item(), 2e-6, "den")
+    assert torch.equal(gn, torch.cat([parts[0][3], parts[1][3]]))
+    m3, mg = _ops.pattern_loss_multi_forward(disp, ta, sig, pat, 3, "census_sad", 0.5, True)
+    mparts = [_ops.pattern_loss_multi_forward([d[s].contiguous() for d in disp], ta[s].contiguous(), sig[s].contiguous(), pat, 3, "census_sad", 0.5, True)
+              for s in (slice(0, half), slice(half, n))]
+    for k in range(2):
+        assert_scalar_close(m3[k, 0].item(), (mparts[0][0][k, 0] + mparts[1][0][k, 0]).item(), 2e-6, f"multi num {k}")
+        assert torch.equal(mg[k], torch.cat([mparts[0][1][k], mparts[1][1][k]]))
+    s3, sg = _ops.smooth_loss_forward(disp[0], ta, True)
+    sparts = [_ops.smooth_loss_forward(disp[0][s].contiguous(), ta[s].contiguous(), True) for s in (slice(0, half), slice(half, n))]
+    assert_scalar_close(s3[0].item(), (sparts[0][0][0] + sparts[1][0][0]).item(), 2e-6, "smooth sum")
+    assert torch.equal(sg, torch.cat([sparts[0][1], sparts[1][1]]))
+    l, sd = _ops.lcn_forward(es, 2, 0.05)
+    l2, sd2 = _ops.lcn_forward(es[half:].contiguous(), 2, 0.05)
+    assert torch.equal(l[half:], l2) and torch.equal(sd[half:], sd2)
