@@ -12,6 +12,10 @@ namespace dis {
 namespace {
 
 constexpr int STW = 64, STH = 32, SNT = 256;
+#ifndef DIS_SMOOTH_FILL_UNROLL
+#define DIS_SMOOTH_FILL_UNROLL 4
+#endif
+constexpr int kSmoothFillUnroll = DIS_SMOOTH_FILL_UNROLL;   // staging loads in flight per thread (the phase is latency-bound)
 constexpr int IN_H = STH + 8, IN_W = STW + 8, IN_P = IN_W;      // inputs with halo 4 (replicate-clamped)
 constexpr int U_H = STH + 4, U_W = STW + 4, U_P = U_W;          // u with halo 2 (zero outside the image)
 
@@ -117,6 +121,7 @@ __global__ void __launch_bounds__(SNT) smooth_loss_kernel(const float* __restric
   const size_t hw = (size_t)H * W;
   const float* d = disp + (size_t)n * hw;
   const float* a = im + (size_t)n * hw;
+#pragma unroll kSmoothFillUnroll
   for (int idx = tid; idx < IN_H * IN_W; idx += SNT) {
     const int j = idx / IN_W, i = idx - j * IN_W;
     const int g = clampi(y0 - 4 + j, 0, H - 1) * W + clampi(x0 - 4 + i, 0, W - 1);
