@@ -13,6 +13,11 @@
 
 namespace dis {
 
+#ifndef DIS_CENSUS_FILL_UNROLL
+#define DIS_CENSUS_FILL_UNROLL 3
+#endif
+constexpr int kCensusFillUnroll = DIS_CENSUS_FILL_UNROLL;   // pattern-warp staging positions in flight per thread
+
 template <int TYPE, bool FWD, bool BWD>
 __device__ __forceinline__ void census_tap2(u64 etc, u64 etq, float wq, u64 eps2, float& acc, float& ga, float& gb) {
   const u64 d2 = sub2(etq, etc);                 // (de, dt)
@@ -235,7 +240,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) census_pattern_loss_kernel(Patter
   const float* disp = a.disp + (size_t)n * hw;
   const float* im = a.im + (size_t)n * hw;
   const float* sd = a.std_in ? a.std_in + (size_t)n * hw : nullptr;
-#pragma unroll 2
+#pragma unroll kCensusFillUnroll
   for (int idx = tid; idx < G::ROWS * G::COLS; idx += NTHREADS) {
     const int j = idx / G::COLS, i = idx - j * G::COLS;
     const int gy = y0 - R + j, gx = x0 - R + i;
