@@ -31,3 +31,22 @@ def test_reference_arm_other_ranks_exit_quietly():
     r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "0"],
                        capture_output=True, text=True, timeout=120, cwd=ROOT, env=env)
     assert r.returncode == 0 and not [l for l in r.stdout.splitlines() if l.startswith("{")]
+
+
+import pytest
+
+
+@pytest.mark.gpu
+def test_gpu_arm_prints_the_contract_line():
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "2", "--warmup", "3", "--no-cpu-baseline", "--no-mf",
+                        "--frames-per-gpu", "64"], capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1, r.stdout[-2000:]
+    d = json.loads(lines[0])
+    assert (BASE_KEYS - {"cpu_baseline"}) | {"clocks", "gpu_launches", "roofline"} <= set(d)
+    assert "impl" not in d and d["value"] > 0 and d["gpu_launches"] > 0 and d["dtype"] == "f32"
+    assert d["e2e"]["value"] > 0 and d["e2e"]["h2d_bytes_per_step"] == 6 * 4 * 512 * 432 * 64 and d["e2e"]["d2h_bytes_per_step"] == 4
+    rf = d["roofline"]
+    assert rf["bound"] == "hbm" and rf["unit"] == "GB/s" and abs(rf["frac"] - rf["achieved"] / rf["peak"]) < 1e-9
+    assert {"sm_mhz", "sm_max_mhz", "reasons"} <= set(d["clocks"])
