@@ -4,6 +4,8 @@
 #include <string.h>
 #include "photometric_kernels.cuh"
 #include "pattern_multi.cuh"
+#include "pattern_march.cuh"
+#include <stdlib.h>
 
 namespace dis {
 
@@ -111,7 +113,83 @@ int dispatch_pattern_multi(int R, const PatternMultiArgs& a, int S, int type, cu
   return DIS_ERR_UNSUPPORTED_BLOCK_SIZE;
 }
 
+int dispatch_pattern_march(int R, const PatternMarchArgs& a, const MarchPlan& plan, int S, int type, cudaStream_t s) {
+  switch (R) {
+    case 1: return launch_pattern_march<1>(a, plan, S, type, s);
+    case 2: return launch_pattern_march<2>(a, plan, S, type, s);
+    case 3: return launch_pattern_march<3>(a, plan, S, type, s);
+    case 4: return launch_pattern_march<4>(a, plan, S, type, s);
+    case 5: return launch_pattern_march<5>(a, plan, S, type, s);
+    case 6: return launch_pattern_march<6>(a, plan, S, type, s);
+    case 7: return launch_pattern_march<7>(a, plan, S, type, s);
+  }
+  return DIS_ERR_UNSUPPORTED_BLOCK_SIZE;
+}
+
+// Tuning / A-B knobs, read per call (no cached state): DIS_MULTI_IMPL=tile selects the round-1 tile kernel,
+// DIS_MARCH_BAND_ROWS / DIS_MARCH_WARPS override the band plan.
+int env_int(const char* name, int dflt) {
+  const char* v = getenv(name);
+  return (v && *v) ? atoi(v) : dflt;
+}
+bool use_march(int R) {
+  if (R < 1) return false;
+  const char* v = getenv("DIS_MULTI_IMPL");
+  return !(v && strcmp(v, "tile") == 0);
+}
+
 }  // namespace
+
+// Column bands: the CTA width (warps) that wastes the fewest lanes over the extended width W + 2R; row bands: the
+// count that minimises (waves of CTAs) x (rows marched per CTA, including the R halo rows recomputed per band).
+MarchPlan march_plan(int N, int H, int W, int R) {
+  const int EW = W + 2 * R, EH = H + 2 * R;
+  const int RH = ((R + MV - 1) / MV) * MV;
+  MarchPlan best{};
+  long best_lanes = -1;
+  const int force_w = env_int("DIS_MARCH_WARPS", 0);
+  for (int nw = 1; nw <= MARCH_MAX_WARPS; ++nw) {
+    if (force_w && nw != force_w) continue;
+    const int LW = 32 * nw, own = LW - 2 * R;
+    if (own < 8) continue;
+    const int ncb = EW <= LW ? 1 : 1 + (EW - LW + own - 1) / own;
+    const long lanes = (long)ncb * LW;
+    if (best_lanes < 0 || lanes <= best_lanes) {   // ties: the wider CTA
+      best_lanes = lanes;
+      best.nwarps = nw;
+      best.ncb = ncb;
+    }
+  }
+  const int slots = 148 * MARCH_CTAS_PER_SM;
+  const int min_rows = 2 * RH + 2 * MV;
+  int band_rows = env_int("DIS_MARCH_BAND_ROWS", 0);
+  if (band_rows <= 0) {
+    double best_cost = 0.0;
+    for (int nrb = 1; nrb <= 64; ++nrb) {
+      int rows = (EH + nrb - 1) / nrb;
+      rows = ((rows + MV - 1) / MV) * MV;
+      if (rows < min_rows) break;
+      const long ctas = (long)N * best.ncb * nrb;
+      const double waves = (double)((ctas + slots - 1) / slots);
+      // a partially filled last wave costs a full band; 0.25 of a band models launch + tail skew per wave
+      const double cost = waves * (rows + RH + 0.25 * rows / (nrb > 0 ? 1 : 1));
+      if (band_rows <= 0 || cost < best_cost) {
+        best_cost = cost;
+        band_rows = rows;
+      }
+    }
+    if (band_rows <= 0) band_rows = ((EH + MV - 1) / MV) * MV;
+  }
+  band_rows = ((band_rows + MV - 1) / MV) * MV;
+  if (band_rows < min_rows) band_rows = min_rows;
+  int nrb = (EH + band_rows - 1) / band_rows;
+  // the last band must own image row H-1 together with the virtual rows below it
+  while (nrb > 1 && EH - (nrb - 1) * band_rows < R + 1) --nrb;
+  best.nrb = nrb;
+  best.band_rows = band_rows;
+  return best;
+}
+
 }  // namespace dis
 
 using namespace dis;
@@ -273,7 +351,13 @@ int dis_reduce_pairs_batched(const float* partials, int n, int count, float* out
 
 int dis_pattern_loss_multi_num_partials(int N, int H, int W) {
   if (N < 0 || H < 1 || W < 1) return DIS_ERR_BAD_SHAPE;
-  return N * ((H + MTH - 1) / MTH) * ((W + MTW - 1) / MTW);
+  long most = (long)N * ((H + MTH - 1) / MTH) * ((W + MTW - 1) / MTW);   // tile kernel (1 x 1 windows, A/B runs)
+  for (int R = 1; R <= MAX_R; ++R) {                                        // marching kernel: depends on the window
+    const MarchPlan p = march_plan(N, H, W, R);
+    const long n = (long)N * p.ncb * p.nrb;
+    if (n > most) most = n;
+  }
+  return most > INT_MAX ? DIS_ERR_BAD_SHAPE : (int)most;
 }
 
 int dis_pattern_loss_multi_forward(const float* const* disps, int S, const float* im, const float* std_in,
@@ -302,7 +386,37 @@ int dis_pattern_loss_multi_forward_scaled(const float* const* disps, int S, cons
   if (N < 0 || H < 2 || W < 2) return DIS_ERR_BAD_SHAPE;
   if (N == 0) return DIS_OK;
   const size_t hw = (size_t)H * W;
+  if (use_march(block_size / 2)) {
+    const int R = block_size / 2;
+    const MarchPlan plan = march_plan(N, H, W, R);
+    const int num_blocks = dis_pattern_loss_multi_num_partials(N, H, W);
+    if (num_blocks < 0) return num_blocks;
+    const int per_frame = plan.ncb * plan.nrb;
+    for (int n0 = 0; n0 < N; n0 += MAX_GRID_Z) {
+      PatternMarchArgs a{};
+      for (int s = 0; s < S; ++s) {
+        a.disp[s] = disps[s] + n0 * hw;
+        a.grad[s] = any_grad ? grad_nums[s] + n0 * hw : nullptr;
+      }
+      a.im = im + n0 * hw; a.std_in = std_in ? std_in + n0 * hw : nullptr; a.pattern = pattern;
+      a.partials = partials;
+      a.grad_scale = grad_scale;
+      a.N = N - n0 < MAX_GRID_Z ? N - n0 : MAX_GRID_Z; a.H = H; a.W = W;
+      a.ncb = plan.ncb; a.nrb = plan.nrb; a.band_rows = plan.band_rows;
+      a.num_blocks = num_blocks; a.total_blocks = N * per_frame; a.block_offset = n0 * per_frame;
+      a.eps = eps; a.inv_k2 = 1.0f / (float)(block_size * block_size);
+      a.inv_w = 1.0f / (float)(W - 1); a.inv_h = 1.0f / (float)(H - 1);
+      if (int rc = dispatch_pattern_march(R, a, plan, S, type, as_stream(stream))) return rc;
+    }
+    return DIS_OK;
+  }
   const int per_frame = ((H + MTH - 1) / MTH) * ((W + MTW - 1) / MTW);
+  const int num_blocks_all = dis_pattern_loss_multi_num_partials(N, H, W);
+  if (num_blocks_all < 0) return num_blocks_all;
+  if (num_blocks_all > N * per_frame) {   // slots this kernel does not write must read as zero
+    const cudaError_t e = cudaMemsetAsync(partials, 0, sizeof(float) * 2 * S * (size_t)num_blocks_all, as_stream(stream));
+    if (e != cudaSuccess) { set_last_cuda_error(e); return DIS_ERR_CUDA_LAUNCH; }
+  }
   for (int n0 = 0; n0 < N; n0 += MAX_GRID_Z) {
     PatternMultiArgs a{};
     uintptr_t align = 0;
@@ -315,7 +429,7 @@ int dis_pattern_loss_multi_forward_scaled(const float* const* disps, int S, cons
     a.partials = partials;
     a.grad_scale = grad_scale;
     a.N = N - n0 < MAX_GRID_Z ? N - n0 : MAX_GRID_Z; a.H = H; a.W = W;
-    a.num_blocks = N * per_frame; a.block_offset = n0 * per_frame;
+    a.num_blocks = num_blocks_all; a.block_offset = n0 * per_frame;
     a.eps = eps; a.inv_k2 = 1.0f / (float)(block_size * block_size);
     a.inv_w = 1.0f / (float)(W - 1); a.inv_h = 1.0f / (float)(H - 1);
     a.vec_ok = (W % 2 == 0) && (align & 7) == 0;

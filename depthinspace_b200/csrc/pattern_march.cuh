@@ -1,0 +1,466 @@
+// Pair-symmetric, column-marching fused pattern loss (soft census types): every unordered pixel pair of the
+// k x k windows is evaluated ONCE and serves the forward value and the gradient of both of its pixels.
+//
+// reference: the photometric loop of single_frame_worker.Worker.loss_forward
+// (model/single_frame_worker.py:108-115) -> RectifiedPatternSimilarityLoss.tforward (model/networks.py:354-377)
+// -> ext_functions.photometric_loss(..., 'census_sad' / 'census_mse') (model/ext_functions.py:156-183).
+//
+// Maths.  With g(d) = d / sqrt(d^2 + eps) the per-tap term is f(p,o) = F(g(e(p+o) - e(p)) - g(t(p+o) - t(p))) with
+// F even, so f(p,o) = f(p+o,-o), and its derivative u(p,o) w.r.t. the neighbour is odd: u(p,o) = -u(p+o,-o).
+// Hence, over the "forward" half window (dy > 0, or dy == 0 and dx > 0), one evaluation per unordered pair {p,q}:
+//     numerator  += f * (w(p) + w(q))
+//     G(p)       += v,   G(q) -= v,        v = (w(p) + w(q)) * u(p,o)
+// Replicate padding (model/ext_functions.py:158-159) is handled by making the padded plane THE image: the
+// (H + 2R) x (W + 2R) extended image carries the clamped e / t values and weight 0 on its R virtual border
+// rows / columns; the gradient collected by a virtual pixel is folded onto the border pixel it replicates
+// (= the backward of F.pad).  Clamp multiplicities come out exactly, with no special border pass.
+//
+// Organisation.  A CTA owns a band of the extended image: up to 7 warps side by side (lane = column), marching
+// down the band MV = 2 rows per step.  Per step a thread owns pixels p0 = (row, col), p1 = (row + 1, col) and
+// visits the cells q of rows row .. row + R + 1: the values of q are loaded once for both pairs (p0,q), (p1,q).
+// The p side of the gradient stays in registers; the q side goes into a WARP-PRIVATE strip of shared-memory
+// accumulators (RING rows x (32 + 2R) cells, all scales of a cell in one 128-bit word), one read-modify-write per
+// cell.  Strips of neighbouring warps are merged in a fixed order when a row retires: no atomics, bitwise
+// reproducible.  Staged planes (warped pattern of every scale, LCN image, sigma) live in a ring of RING rows;
+// every pixel of the band is staged exactly once (halo: R rows at the top of a band, R columns between column
+// bands).  d proj / d disp is parked in the gradient output buffer at staging time and read back (L2 hit) when
+// the row retires, instead of occupying shared memory for R + 2 rows.
+//
+// Cost per unordered pair for 4 scales: 5 MUFU.RSQ and ~46 issue slots (the tile kernel in pattern_multi.cuh
+// pays 43 slots and 5 MUFU per ORDERED pair, i.e. twice).
+#pragma once
+#include <type_traits>
+#include "window.cuh"
+
+namespace dis {
+
+constexpr int MV = 2;                  // rows per thread per step
+constexpr int MARCH_MAX_WARPS = 7;     // CTA <= 224 threads: three CTAs of 96-register threads per SM
+constexpr int MARCH_CTAS_PER_SM = 3;
+
+template <int R>
+struct MarchGeom {
+  static constexpr int RH = ((R + MV - 1) / MV) * MV;  // halo rows recomputed at the top of a band
+  static constexpr int RING = MV + R;                   // live rows of the staged planes and of the strips
+  static constexpr int SW = 32 + 2 * R;                 // strip cells per row
+};
+
+struct PatternMarchArgs {
+  const float* disp[4];
+  float* grad[4];          // all NULL => forward only
+  const float* im;
+  const float* std_in;
+  const float* pattern;
+  const float* grad_scale; // optional device float[S]
+  float* partials;         // [S][num_blocks][2] = (num_s, den)
+  int N, H, W;
+  int ncb, nrb;            // column / row bands per frame
+  int band_rows;           // extended rows owned by a row band (multiple of MV); the last band takes the rest
+  int num_blocks;          // partial slots per scale (>= total_blocks; the tail is zero-filled)
+  int total_blocks;        // CTAs of the whole call
+  int block_offset;        // first CTA index of this launch (batch chunking)
+  float eps, inv_k2, inv_w, inv_h;
+};
+
+// shared memory: ring of staged rows (estimate pairs, (t, w)), per-warp accumulator strips, reduction scratch
+template <int R, int NPAIR>
+__host__ __device__ constexpr size_t pattern_march_smem_bytes(int nwarps) {
+  using G = MarchGeom<R>;
+  const size_t pitch = 32 * (size_t)nwarps + 2 * R;
+  return G::RING * pitch * NPAIR * 8 + G::RING * pitch * 8 + (size_t)nwarps * G::RING * G::SW * NPAIR * 8 +
+         (size_t)nwarps * (2 * NPAIR + 1) * 8;
+}
+
+template <int NPAIR>
+struct MCell {  // all scales of one pixel: NPAIR packed fp32x2 values
+  u64 v[NPAIR];
+};
+template <int NPAIR>
+__device__ __forceinline__ MCell<NPAIR> mcell_load(const u64* p) {
+  MCell<NPAIR> c;
+  if (NPAIR == 2) {
+    const ulonglong2 q = *reinterpret_cast<const ulonglong2*>(p);
+    c.v[0] = q.x;
+    c.v[NPAIR - 1] = q.y;
+  } else {
+    c.v[0] = *p;
+  }
+  return c;
+}
+template <int NPAIR>
+__device__ __forceinline__ void mcell_store(u64* p, const MCell<NPAIR>& c) {
+  if (NPAIR == 2) *reinterpret_cast<ulonglong2*>(p) = make_ulonglong2(c.v[0], c.v[NPAIR - 1]);
+  else *p = c.v[0];
+}
+
+// One unordered pair {p (centre), q}: forward accumulators `acc`, p-side gradient `gp`, running q-cell sum `cell`.
+template <int TYPE, int NPAIR, bool GRAD, bool FIRST>
+__device__ __forceinline__ void march_pair(const MCell<NPAIR>& ec, float tc, float wc, const MCell<NPAIR>& eq, float tq,
+                                           float wq, float eps, u64 eps2, float (&acc)[2 * NPAIR], MCell<NPAIR>& gp,
+                                           MCell<NPAIR>& cell) {
+  // target side, shared by all scales: gt = dt * rt (rounded) and its exact rounding residual
+  const float dt = tq - tc;
+  const float rt = rsqrt_fast(fmaf(dt, dt, eps));
+  const float gt = __fmul_rn(dt, rt);
+  const float rest = __fmaf_rn(dt, rt, -gt);
+  const float ws = wq + wc;
+#pragma unroll
+  for (int p = 0; p < NPAIR; ++p) {
+    const u64 de = sub2(eq.v[p], ec.v[p]);
+    const u64 xe = fma2(de, de, eps2);
+    float x0f, x1f;
+    upk2(xe, x0f, x1f);
+    const u64 re = pk2(rsqrt_fast(x0f), rsqrt_fast(x1f));
+    // diff = (de*re - gt) - (dt*rt - gt): both products enter through an exact FMA residual, so e == t gives
+    // exactly 0 (the reference's |.| has subgradient 0 there)
+    const u64 diff = sub2(fma2(de, re, bc2(-gt)), bc2(rest));
+    float d0, d1;
+    upk2(diff, d0, d1);
+    if (TYPE == CENSUS_SAD) {
+      acc[2 * p] = fmaf(fabsf(d0), ws, acc[2 * p]);
+      acc[2 * p + 1] = fmaf(fabsf(d1), ws, acc[2 * p + 1]);
+    } else {
+      acc[2 * p] = fmaf(d0 * d0, ws, acc[2 * p]);
+      acc[2 * p + 1] = fmaf(d1 * d1, ws, acc[2 * p + 1]);
+    }
+    if (GRAD) {
+      const u64 r3 = mul2(mul2(re, re), re);
+      u64 u;
+      if (TYPE == CENSUS_SAD) {
+        float q0, q1;
+        upk2(r3, q0, q1);
+        u = pk2(signed_mag(q0, d0), signed_mag(q1, d1));
+      } else {
+        u = mul2(diff, r3);
+      }
+      const u64 v = mul2(u, bc2(ws));
+      gp.v[p] = add2(gp.v[p], v);
+      cell.v[p] = FIRST ? v : add2(cell.v[p], v);
+    }
+  }
+}
+
+// Sum of everything the strips hold for CTA-lane position P of strip row rq (own strip, then the halo cells of the
+// left and of the right neighbour warp: fixed order); the cells are zeroed for their next use.
+template <int R, int NPAIR>
+__device__ __forceinline__ MCell<NPAIR> strip_collect(u64* strips, int P, int rq, int nwarps) {
+  using G = MarchGeom<R>;
+  const int w = P >> 5, l = P & 31;
+  MCell<NPAIR> zero;
+#pragma unroll
+  for (int p = 0; p < NPAIR; ++p) zero.v[p] = 0ull;
+  u64* own = strips + ((size_t)(w * G::RING + rq) * G::SW + l + R) * NPAIR;
+  MCell<NPAIR> t = mcell_load<NPAIR>(own);
+  mcell_store<NPAIR>(own, zero);
+  if (l < R && w > 0) {
+    u64* h = strips + ((size_t)((w - 1) * G::RING + rq) * G::SW + 32 + R + l) * NPAIR;
+    const MCell<NPAIR> c = mcell_load<NPAIR>(h);
+    mcell_store<NPAIR>(h, zero);
+#pragma unroll
+    for (int p = 0; p < NPAIR; ++p) t.v[p] = add2(t.v[p], c.v[p]);
+  }
+  if (l >= 32 - R && w < nwarps - 1) {
+    u64* h = strips + ((size_t)((w + 1) * G::RING + rq) * G::SW + l - 32 + R) * NPAIR;
+    const MCell<NPAIR> c = mcell_load<NPAIR>(h);
+    mcell_store<NPAIR>(h, zero);
+#pragma unroll
+    for (int p = 0; p < NPAIR; ++p) t.v[p] = add2(t.v[p], c.v[p]);
+  }
+  return t;
+}
+
+template <int TYPE, int R, int NPAIR, bool GRAD>
+__global__ void __launch_bounds__(32 * MARCH_MAX_WARPS, MARCH_CTAS_PER_SM) pattern_march_kernel(PatternMarchArgs a) {
+  static_assert(TYPE == CENSUS_MSE || TYPE == CENSUS_SAD, "pair symmetry is a property of the census types");
+  static_assert(R >= 1, "a 1 x 1 window has no pairs");
+  using G = MarchGeom<R>;
+  constexpr int S = 2 * NPAIR;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int LW = blockDim.x, nwarps = LW >> 5;
+  const int PITCH = LW + 2 * R;
+  extern __shared__ __align__(16) unsigned char march_smem[];
+  u64* ring_e = reinterpret_cast<u64*>(march_smem);                                  // [RING][PITCH][NPAIR]
+  float2* ring_tw = reinterpret_cast<float2*>(ring_e + (size_t)G::RING * PITCH * NPAIR);  // [RING][PITCH] (t, w)
+  u64* strips = reinterpret_cast<u64*>(ring_tw + (size_t)G::RING * PITCH);           // [nwarps][RING][SW][NPAIR]
+  double* red = reinterpret_cast<double*>(strips + (size_t)nwarps * G::RING * G::SW * NPAIR);  // [nwarps][S+1]
+
+  const int H = a.H, W = a.W;
+  const int EH = H + 2 * R, EW = W + 2 * R;
+  const int cb = blockIdx.x, rb = blockIdx.y, n = blockIdx.z;
+  // ---- my column ---------------------------------------------------------------------------------------
+  const int c0 = cb * (LW - 2 * R);
+  const int ec = c0 + tid;                                   // extended column of this thread
+  const int own_c0 = c0 + (cb > 0 ? R : 0);
+  const int own_c1 = (cb == a.ncb - 1) ? EW : c0 + LW - R;
+  const bool col_own = ec >= own_c0 && ec < own_c1;          // (implies ec < EW)
+  const bool col_in = ec >= R && ec < EW - R;                // a real image column
+  const bool out_lane = col_own && col_in;
+  const int x = clampi(ec - R, 0, W - 1);
+  // ---- my rows -----------------------------------------------------------------------------------------
+  const int own_r0 = rb * a.band_rows;
+  const int own_r1 = (rb == a.nrb - 1) ? EH : own_r0 + a.band_rows;
+  const int row_start = rb > 0 ? own_r0 - G::RH : 0;
+  const int nsteps = (own_r1 - row_start + MV - 1) / MV;
+
+  const size_t hw = (size_t)H * W;
+  const size_t fo = (size_t)n * hw;
+  const float* dptr[S];
+  float* gptr[S];
+#pragma unroll
+  for (int s = 0; s < S; ++s) {
+    dptr[s] = a.disp[s] + fo;
+    gptr[s] = GRAD ? a.grad[s] + fo : nullptr;
+  }
+  const float* imp = a.im + fo;
+  const float* sdp = a.std_in ? a.std_in + fo : nullptr;
+
+  const float gs = -0.5f * a.eps * a.inv_k2;
+  float gss[S];            // census chain-rule constant x the caller's per-scale factor
+#pragma unroll
+  for (int s = 0; s < S; ++s) gss[s] = (GRAD && a.grad_scale) ? gs * __ldg(a.grad_scale + s) : gs;
+  const u64 eps2 = bc2(a.eps);
+
+  // ---- one-time initialisation: zero strips, finite zero-weight padding cells of the ring --------------------
+  for (int i = tid; i < nwarps * G::RING * G::SW * NPAIR; i += LW) strips[i] = 0ull;
+  for (int i = tid; i < G::RING * 2 * R; i += LW) {
+    const int r = i / (2 * R), k = i - r * 2 * R;
+    const int slot = r * PITCH + (k < R ? k : LW + k);
+#pragma unroll
+    for (int p = 0; p < NPAIR; ++p) ring_e[(size_t)slot * NPAIR + p] = 0ull;
+    ring_tw[slot] = make_float2(0.0f, 0.0f);
+  }
+
+  // stage one extended row: pattern warp of every scale, LCN image, sigma (0 outside the image)
+  auto stage_row = [&](int er) {
+    const int y = clampi(er - R, 0, H - 1);
+    const bool inside = col_in && er >= R && er < EH - R;
+    const size_t g = (size_t)y * W + x;
+    float dv[S];
+#pragma unroll
+    for (int s = 0; s < S; ++s) dv[s] = __ldg(dptr[s] + g);
+    const float tv = __ldg(imp + g);
+    const float wv = inside ? (sdp ? __ldg(sdp + g) : 1.0f) : 0.0f;
+    const WarpRow row = warp_row_setup(y, H, W, a.inv_h);
+    const bool want_dd = GRAD && inside && col_own && er >= own_r0 && er < own_r1;
+    float ev[S], dd[S];
+#pragma unroll
+    for (int s = 0; s < S; ++s) ev[s] = warp_col_sample(a.pattern, row, dv[s], x, W, a.inv_w, want_dd ? &dd[s] : nullptr);
+    int rq = er % G::RING;
+    const int slot = rq * PITCH + R + tid;
+#pragma unroll
+    for (int p = 0; p < NPAIR; ++p) ring_e[(size_t)slot * NPAIR + p] = pk2(ev[2 * p], ev[2 * p + 1]);
+    ring_tw[slot] = make_float2(tv, wv);
+    if (want_dd) {
+#pragma unroll
+      for (int s = 0; s < S; ++s) gptr[s][g] = dd[s] * gss[s];   // parked; multiplied by G(p) when the row retires
+    }
+  };
+
+  for (int er = row_start; er < row_start + G::RING - MV; ++er) stage_row(er);
+
+  double numd[S], dend = 0.0;
+#pragma unroll
+  for (int s = 0; s < S; ++s) numd[s] = 0.0;
+  MCell<NPAIR> vacc, bacc;   // vertical fold: top virtual rows -> image row 0; image row H-1 + bottom virtual rows
+#pragma unroll
+  for (int p = 0; p < NPAIR; ++p) vacc.v[p] = bacc.v[p] = 0ull;
+
+#pragma unroll 1
+  for (int step = 0; step < nsteps; ++step) {
+    const int ys = row_start + step * MV;
+    // ---- A: stage the MV new rows this step needs ---------------------------------------------------------
+#pragma unroll
+    for (int i = 0; i < MV; ++i) stage_row(ys + R + i);
+    __syncthreads();
+
+    // ---- C: pairs -------------------------------------------------------------------------------------------
+    const int r0 = ys % G::RING;
+    MCell<NPAIR> pe[MV], gp[MV];
+    float ptc[MV], pwc[MV];
+    float acc[S];
+#pragma unroll
+    for (int s = 0; s < S; ++s) acc[s] = 0.0f;
+#pragma unroll
+    for (int i = 0; i < MV; ++i) {
+      int rq = r0 + i;
+      if (rq >= G::RING) rq -= G::RING;
+      const int slot = rq * PITCH + R + tid;
+      pe[i] = mcell_load<NPAIR>(ring_e + (size_t)slot * NPAIR);
+      const float2 tw = ring_tw[slot];
+      ptc[i] = tw.x;
+      pwc[i] = tw.y;
+#pragma unroll
+      for (int p = 0; p < NPAIR; ++p) gp[i].v[p] = 0ull;
+    }
+    u64* my_strip = strips + (size_t)wid * G::RING * G::SW * NPAIR;
+
+    // one cell q = (row ys + j, column + dx); P0 / P1: which of my two pixels pair with it
+    auto cell = [&](int rq, int dx, auto p0_tag, auto p1_tag) {
+      constexpr bool P0 = decltype(p0_tag)::value, P1 = decltype(p1_tag)::value;
+      const int slot = rq * PITCH + R + tid + dx;
+      const MCell<NPAIR> eq = mcell_load<NPAIR>(ring_e + (size_t)slot * NPAIR);
+      const float2 tw = ring_tw[slot];
+      MCell<NPAIR> cs;
+      if (P0) march_pair<TYPE, NPAIR, GRAD, true>(pe[0], ptc[0], pwc[0], eq, tw.x, tw.y, a.eps, eps2, acc, gp[0], cs);
+      if (P1) {
+        if (P0) march_pair<TYPE, NPAIR, GRAD, false>(pe[1], ptc[1], pwc[1], eq, tw.x, tw.y, a.eps, eps2, acc, gp[1], cs);
+        else march_pair<TYPE, NPAIR, GRAD, true>(pe[1], ptc[1], pwc[1], eq, tw.x, tw.y, a.eps, eps2, acc, gp[1], cs);
+      }
+      if (GRAD) {
+        u64* c = my_strip + ((size_t)rq * G::SW + lane + R + dx) * NPAIR;
+        MCell<NPAIR> cur = mcell_load<NPAIR>(c);
+#pragma unroll
+        for (int p = 0; p < NPAIR; ++p) cur.v[p] = sub2(cur.v[p], cs.v[p]);
+        mcell_store<NPAIR>(c, cur);
+        __syncwarp();   // the next cell of this lane is the previous cell of its neighbour
+      }
+    };
+    using T_ = std::true_type;
+    using F_ = std::false_type;
+    {  // j = 0: dy = 0 for p0 (dx > 0 only)
+#pragma unroll
+      for (int dx = 1; dx <= R; ++dx) cell(r0, dx, T_{}, F_{});
+    }
+    {  // j = 1: dy = 1 for p0 (all dx), dy = 0 for p1 (dx > 0)
+      int rq = r0 + 1;
+      if (rq >= G::RING) rq -= G::RING;
+#pragma unroll
+      for (int dx = -R; dx <= 0; ++dx) cell(rq, dx, T_{}, F_{});
+#pragma unroll
+      for (int dx = 1; dx <= R; ++dx) cell(rq, dx, T_{}, T_{});
+    }
+#pragma unroll 1
+    for (int j = 2; j <= R; ++j) {  // both pixels, all dx
+      int rq = r0 + j;
+      if (rq >= G::RING) rq -= G::RING;
+#pragma unroll
+      for (int dx = -R; dx <= R; ++dx) cell(rq, dx, T_{}, T_{});
+    }
+    {  // j = R + 1: dy = R for p1 only
+      int rq = r0 + R + 1;
+      if (rq >= G::RING) rq -= G::RING;
+#pragma unroll
+      for (int dx = -R; dx <= R; ++dx) cell(rq, dx, F_{}, T_{});
+    }
+    if (GRAD) {  // my own pixels' p-side sums join the strip (own cells: no other lane touches them now)
+#pragma unroll
+      for (int i = 0; i < MV; ++i) {
+        int rq = r0 + i;
+        if (rq >= G::RING) rq -= G::RING;
+        u64* c = my_strip + ((size_t)rq * G::SW + lane + R) * NPAIR;
+        MCell<NPAIR> cur = mcell_load<NPAIR>(c);
+#pragma unroll
+        for (int p = 0; p < NPAIR; ++p) cur.v[p] = add2(cur.v[p], gp[i].v[p]);
+        mcell_store<NPAIR>(c, cur);
+      }
+    }
+    if (ys >= own_r0) {  // pairs are counted by the band that owns p (halo steps only feed the strips)
+#pragma unroll
+      for (int s = 0; s < S; ++s) numd[s] += (double)acc[s];
+    }
+    __syncthreads();
+
+    // ---- E: rows ys, ys + 1 retire: merge strips, fold virtual pixels, write the gradient ------------------------
+    if (out_lane) {
+#pragma unroll
+      for (int i = 0; i < MV; ++i) {
+        const int er = ys + i;
+        int rq = r0 + i;
+        if (rq >= G::RING) rq -= G::RING;
+        const bool row_own = er >= own_r0 && er < own_r1;
+        if (row_own) dend += (double)ring_tw[rq * PITCH + R + tid].y;
+        if (GRAD) {
+          MCell<NPAIR> t = strip_collect<R, NPAIR>(strips, tid, rq, nwarps);
+          if (ec == R) {  // left border column: virtual columns 0 .. R-1 fold onto it
+            for (int k = 0; k < R; ++k) {
+              const MCell<NPAIR> c = strip_collect<R, NPAIR>(strips, tid - R + k, rq, nwarps);
+#pragma unroll
+              for (int p = 0; p < NPAIR; ++p) t.v[p] = add2(t.v[p], c.v[p]);
+            }
+          }
+          if (ec == EW - R - 1) {  // right border column
+            for (int k = 1; k <= R; ++k) {
+              const MCell<NPAIR> c = strip_collect<R, NPAIR>(strips, tid + k, rq, nwarps);
+#pragma unroll
+              for (int p = 0; p < NPAIR; ++p) t.v[p] = add2(t.v[p], c.v[p]);
+            }
+          }
+          if (row_own) {
+            bool emit = true;
+            int y = er - R;
+            if (er < R) {                      // top virtual row
+#pragma unroll
+              for (int p = 0; p < NPAIR; ++p) vacc.v[p] = add2(vacc.v[p], t.v[p]);
+              emit = false;
+            } else if (er >= EH - R - 1) {     // image row H-1 and the virtual rows below it
+#pragma unroll
+              for (int p = 0; p < NPAIR; ++p) bacc.v[p] = add2(bacc.v[p], t.v[p]);
+              emit = (er == EH - 1);
+              t = bacc;
+              y = H - 1;
+            } else if (er == R) {              // image row 0
+#pragma unroll
+              for (int p = 0; p < NPAIR; ++p) t.v[p] = add2(t.v[p], vacc.v[p]);
+            }
+            if (emit) {
+              const size_t g = (size_t)y * W + x;
+#pragma unroll
+              for (int p = 0; p < NPAIR; ++p) {
+                float t0, t1;
+                upk2(t.v[p], t0, t1);
+                gptr[2 * p][g] = t0 * gptr[2 * p][g];
+                gptr[2 * p + 1][g] = t1 * gptr[2 * p + 1][g];
+              }
+            }
+          }
+        }
+      }
+    }
+    // (no barrier here: stage_row of the next step overwrites ring rows ys, ys+1, which every warp finished
+    //  reading before the barrier above; strip rows are next written after the barrier that follows staging)
+  }
+
+  // ---- CTA reduction of S numerators + the denominator (fixed order) ------------------------------------------
+  const double fs = (double)(fwd_scale<TYPE>() * a.inv_k2);
+#pragma unroll
+  for (int s = 0; s < S; ++s) {
+    double v = col_own ? numd[s] * fs : 0.0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == 0) red[wid * (S + 1) + s] = v;
+  }
+  {
+    double v = dend;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == 0) red[wid * (S + 1) + S] = v;
+  }
+  __syncthreads();
+  if (tid < S) {
+    double num = 0.0, den = 0.0;
+    for (int w = 0; w < nwarps; ++w) {
+      num += red[w * (S + 1) + tid];
+      den += red[w * (S + 1) + S];
+    }
+    const size_t blocks_per_frame = (size_t)a.ncb * a.nrb;
+    const size_t b = (size_t)a.block_offset + (size_t)n * blocks_per_frame + (size_t)rb * a.ncb + cb;
+    float* out = a.partials + (size_t)tid * a.num_blocks * 2;
+    out[b * 2] = (float)num;
+    out[b * 2 + 1] = (float)den;
+    for (size_t z = (size_t)a.total_blocks + b; z < (size_t)a.num_blocks; z += a.total_blocks) {
+      out[z * 2] = 0.0f;
+      out[z * 2 + 1] = 0.0f;
+    }
+  }
+}
+
+// Band plan for one call (host side): warps per CTA / column bands minimising idle lanes, row bands balancing the
+// halo re-computation against the number of CTA waves.
+struct MarchPlan {
+  int nwarps, ncb, nrb, band_rows;
+};
+MarchPlan march_plan(int N, int H, int W, int R);
+
+template <int R> int launch_pattern_march(const PatternMarchArgs& a, const MarchPlan& plan, int S, int type, cudaStream_t s);
+
+}  // namespace dis

@@ -4,6 +4,7 @@
 #include <mutex>
 #include "photometric_kernels.cuh"
 #include "pattern_multi.cuh"
+#include "pattern_march.cuh"
 #include "box_kernels.cuh"
 #include "census_kernels.cuh"
 
@@ -111,7 +112,33 @@ int pattern_multi_t(const PatternMultiArgs& a, cudaStream_t s) {
   return check_launch();
 }
 
+#if DIS_R >= 1
+template <int TYPE, int R, int NPAIR>
+int pattern_march_t(const PatternMarchArgs& a, const MarchPlan& plan, cudaStream_t s) {
+  const dim3 block(32 * plan.nwarps);
+  const dim3 grid(plan.ncb, plan.nrb, a.N);
+  const size_t smem = pattern_march_smem_bytes<R, NPAIR>(plan.nwarps);
+  if (a.grad[0]) {
+    if (int rc = prepare(pattern_march_kernel<TYPE, R, NPAIR, true>, smem)) return rc;
+    pattern_march_kernel<TYPE, R, NPAIR, true><<<grid, block, smem, s>>>(a);
+  } else {
+    if (int rc = prepare(pattern_march_kernel<TYPE, R, NPAIR, false>, smem)) return rc;
+    pattern_march_kernel<TYPE, R, NPAIR, false><<<grid, block, smem, s>>>(a);
+  }
+  return check_launch();
+}
+#endif
+
 }  // namespace
+
+template <>
+int launch_pattern_march<DIS_R>(const PatternMarchArgs& a, const MarchPlan& plan, int S, int type, cudaStream_t s) {
+#if DIS_R >= 1
+  if (type == CENSUS_SAD) return S == 4 ? pattern_march_t<CENSUS_SAD, DIS_R, 2>(a, plan, s) : pattern_march_t<CENSUS_SAD, DIS_R, 1>(a, plan, s);
+  if (type == CENSUS_MSE) return S == 4 ? pattern_march_t<CENSUS_MSE, DIS_R, 2>(a, plan, s) : pattern_march_t<CENSUS_MSE, DIS_R, 1>(a, plan, s);
+#endif
+  return DIS_ERR_UNSUPPORTED_COMBINATION;
+}
 
 template <>
 int launch_pattern_multi<DIS_R>(const PatternMultiArgs& a, int S, int type, cudaStream_t s) {
