@@ -221,6 +221,33 @@ __device__ __forceinline__ float warp_col_sample(const float* __restrict__ patte
   return acc;
 }
 
+// Same value as warp_col_sample() without the per-corner within_bounds_2d() predicates: after the border clip the
+// source coordinates lie in [0, W-1] x [0, H-1], so the only corners that can fall outside the image are x0+1 == W
+// (ix == W-1, weight wx1 == 0) and y0+1 == H (weight wy1 == 0).  Reading the clamped neighbour instead of skipping
+// the corner adds v * 0 for a finite pattern value v: the same sum (the sign of a zero result may differ; the
+// values compare equal), and d proj / d disp is masked by mult == 0 there.  Needs a finite pattern.
+__device__ __forceinline__ float warp_col_sample_clamped(const float* __restrict__ row0, const float* __restrict__ row1,
+                                                         float wy0, float wy1, float disp, int w, int W, float inv_w,
+                                                         float* dproj) {
+  float mult;
+  const float ix = border_source_index(normalize_coord(fsub((float)w, disp), inv_w), W, mult);
+  const int x0 = (int)floorf(ix);
+  const float wx0 = fsub((float)(x0 + 1), ix), wx1 = fsub(ix, (float)x0);
+  const int c1 = min(x0 + 1, W - 1);
+  const float vnw = __ldg(row0 + x0), vne = __ldg(row0 + c1);
+  const float vsw = __ldg(row1 + x0), vse = __ldg(row1 + c1);
+  float acc = __fmaf_rn(vnw, fmul(wx0, wy0), 0.0f);
+  acc = __fmaf_rn(vne, fmul(wx1, wy0), acc);
+  acc = __fmaf_rn(vsw, fmul(wx0, wy1), acc);
+  acc = __fmaf_rn(vse, fmul(wx1, wy1), acc);
+  if (dproj) {
+    float g = 0.0f;   // grid_sampler_2d_backward: gix
+    g -= vnw * wy0; g += vne * wy0; g -= vsw * wy1; g += vse * wy1;
+    *dproj = -(((mult * g) * 2.0f) * inv_w);
+  }
+  return acc;
+}
+
 // ---- reductions -----------------------------------------------------------------------
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

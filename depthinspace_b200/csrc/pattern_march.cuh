@@ -35,8 +35,19 @@
 namespace dis {
 
 constexpr int MV = 2;                  // rows per thread per step
-constexpr int MARCH_MAX_WARPS = 7;     // CTA <= 224 threads: three CTAs of 96-register threads per SM
+constexpr int MARCH_MAX_WARPS = 8;     // CTA <= 256 threads
 constexpr int MARCH_CTAS_PER_SM = 3;
+#ifndef DIS_MARCH_UNROLL
+#define DIS_MARCH_UNROLL 9
+#endif
+#ifndef DIS_MARCH_PREFETCH
+#define DIS_MARCH_PREFETCH 0     // streaming loads of the next step's rows issued one step ahead
+#endif
+#ifndef DIS_MARCH_STASH_EARLY
+#define DIS_MARCH_STASH_EARLY 0  // read-back of the parked d proj / d disp issued before the barrier
+#endif
+constexpr int MARCH_UNROLL = DIS_MARCH_UNROLL;   // cells per iteration of the rolled cell loops
+constexpr int MARCH_MAX_REGS = 80;      // 6 warps per SM sub-partition (16 K registers each): 3 CTAs of 7 warps
 
 template <int R>
 struct MarchGeom {
@@ -68,7 +79,7 @@ __host__ __device__ constexpr size_t pattern_march_smem_bytes(int nwarps) {
   using G = MarchGeom<R>;
   const size_t pitch = 32 * (size_t)nwarps + 2 * R;
   return G::RING * pitch * NPAIR * 8 + G::RING * pitch * 8 + (size_t)nwarps * G::RING * G::SW * NPAIR * 8 +
-         (size_t)nwarps * (2 * NPAIR + 1) * 8;
+         (size_t)nwarps * (2 * NPAIR + 1) * 8 + (size_t)(2 * NPAIR + 1) * 32 * nwarps * 8;
 }
 
 template <int NPAIR>
@@ -93,17 +104,29 @@ __device__ __forceinline__ void mcell_store(u64* p, const MCell<NPAIR>& c) {
   else *p = c.v[0];
 }
 
-// One unordered pair {p (centre), q}: forward accumulators `acc`, p-side gradient `gp`, running q-cell sum `cell`.
+// Accesses to the accumulator strips: volatile, so that the read-modify-write sequences of consecutive cells keep
+// their program order (the next cell of a lane is the previous cell of its neighbour lane; the warp runs them in
+// lockstep and the LSU executes a warp's shared-memory operations in order), while the plain loads of the staged
+// planes stay free to be scheduled early.
+template <int NPAIR>
+__device__ __forceinline__ MCell<NPAIR> strip_ld(unsigned addr) {
+  MCell<NPAIR> c;
+  if (NPAIR == 2) asm volatile("ld.volatile.shared.v2.u64 {%0, %1}, [%2];" : "=l"(c.v[0]), "=l"(c.v[NPAIR - 1]) : "r"(addr));
+  else asm volatile("ld.volatile.shared.u64 %0, [%1];" : "=l"(c.v[0]) : "r"(addr));
+  return c;
+}
+template <int NPAIR>
+__device__ __forceinline__ void strip_st(unsigned addr, const MCell<NPAIR>& c) {
+  if (NPAIR == 2) asm volatile("st.volatile.shared.v2.u64 [%0], {%1, %2};" ::"r"(addr), "l"(c.v[0]), "l"(c.v[NPAIR - 1]));
+  else asm volatile("st.volatile.shared.u64 [%0], %1;" ::"r"(addr), "l"(c.v[0]));
+}
+
+// Estimate side of one unordered pair {p (centre), q} for all scales, given the target side (ngt = -(dt * rt) rounded,
+// rest = the exact rounding residual of dt * rt) and the pair weight ws = w(p) + w(q).
+// acc: forward accumulators, gp: p-side gradient, cell: running sum for q's cell.
 template <int TYPE, int NPAIR, bool GRAD, bool FIRST>
-__device__ __forceinline__ void march_pair(const MCell<NPAIR>& ec, float tc, float wc, const MCell<NPAIR>& eq, float tq,
-                                           float wq, float eps, u64 eps2, float (&acc)[2 * NPAIR], MCell<NPAIR>& gp,
-                                           MCell<NPAIR>& cell) {
-  // target side, shared by all scales: gt = dt * rt (rounded) and its exact rounding residual
-  const float dt = tq - tc;
-  const float rt = rsqrt_fast(fmaf(dt, dt, eps));
-  const float gt = __fmul_rn(dt, rt);
-  const float rest = __fmaf_rn(dt, rt, -gt);
-  const float ws = wq + wc;
+__device__ __forceinline__ void march_scales(const MCell<NPAIR>& ec, const MCell<NPAIR>& eq, float ngt, float rest, float ws,
+                                             u64 eps2, float (&acc)[2 * NPAIR], MCell<NPAIR>& gp, MCell<NPAIR>& cell) {
 #pragma unroll
   for (int p = 0; p < NPAIR; ++p) {
     const u64 de = sub2(eq.v[p], ec.v[p]);
@@ -113,7 +136,7 @@ __device__ __forceinline__ void march_pair(const MCell<NPAIR>& ec, float tc, flo
     const u64 re = pk2(rsqrt_fast(x0f), rsqrt_fast(x1f));
     // diff = (de*re - gt) - (dt*rt - gt): both products enter through an exact FMA residual, so e == t gives
     // exactly 0 (the reference's |.| has subgradient 0 there)
-    const u64 diff = sub2(fma2(de, re, bc2(-gt)), bc2(rest));
+    const u64 diff = sub2(fma2(de, re, bc2(ngt)), bc2(rest));
     float d0, d1;
     upk2(diff, d0, d1);
     if (TYPE == CENSUS_SAD) {
@@ -140,29 +163,63 @@ __device__ __forceinline__ void march_pair(const MCell<NPAIR>& ec, float tc, flo
   }
 }
 
+// one pair: scalar target side
+template <int TYPE, int NPAIR, bool GRAD>
+__device__ __forceinline__ void march_pair1(const MCell<NPAIR>& ec, float tc, float wc, const MCell<NPAIR>& eq, float tq,
+                                            float wq, float eps, u64 eps2, float (&acc)[2 * NPAIR], MCell<NPAIR>& gp,
+                                            MCell<NPAIR>& cell) {
+  const float dt = tq - tc;
+  const float rt = rsqrt_fast(fmaf(dt, dt, eps));
+  const float gt = __fmul_rn(dt, rt);
+  const float rest = __fmaf_rn(dt, rt, -gt);
+  march_scales<TYPE, NPAIR, GRAD, true>(ec, eq, -gt, rest, wq + wc, eps2, acc, gp, cell);
+}
+
+// both pixels of the thread against the same q: the two target sides share packed instructions
+template <int TYPE, int NPAIR, bool GRAD>
+__device__ __forceinline__ void march_pair2(const MCell<NPAIR>& ec0, const MCell<NPAIR>& ec1, u64 tc2, u64 wc2,
+                                            const MCell<NPAIR>& eq, float tq, float wq, u64 eps2, float (&acc)[2 * NPAIR],
+                                            MCell<NPAIR>& gp0, MCell<NPAIR>& gp1, MCell<NPAIR>& cell) {
+  const u64 dt = sub2(bc2(tq), tc2);
+  const u64 xt = fma2(dt, dt, eps2);
+  float x0f, x1f;
+  upk2(xt, x0f, x1f);
+  const u64 rt = pk2(rsqrt_fast(x0f), rsqrt_fast(x1f));
+  const u64 gt = mul2(dt, rt);
+  const u64 ngt = mul2(gt, bc2(-1.0f));
+  const u64 rest = fma2(dt, rt, ngt);
+  const u64 ws = add2(bc2(wq), wc2);
+  float n0, n1, r0, r1, w0, w1;
+  upk2(ngt, n0, n1);
+  upk2(rest, r0, r1);
+  upk2(ws, w0, w1);
+  march_scales<TYPE, NPAIR, GRAD, true>(ec0, eq, n0, r0, w0, eps2, acc, gp0, cell);
+  march_scales<TYPE, NPAIR, GRAD, false>(ec1, eq, n1, r1, w1, eps2, acc, gp1, cell);
+}
+
 // Sum of everything the strips hold for CTA-lane position P of strip row rq (own strip, then the halo cells of the
 // left and of the right neighbour warp: fixed order); the cells are zeroed for their next use.
 template <int R, int NPAIR>
-__device__ __forceinline__ MCell<NPAIR> strip_collect(u64* strips, int P, int rq, int nwarps) {
+__device__ __forceinline__ MCell<NPAIR> strip_collect(unsigned strips_addr, int P, int rq, int nwarps) {
   using G = MarchGeom<R>;
   const int w = P >> 5, l = P & 31;
   MCell<NPAIR> zero;
 #pragma unroll
   for (int p = 0; p < NPAIR; ++p) zero.v[p] = 0ull;
-  u64* own = strips + ((size_t)(w * G::RING + rq) * G::SW + l + R) * NPAIR;
-  MCell<NPAIR> t = mcell_load<NPAIR>(own);
-  mcell_store<NPAIR>(own, zero);
+  const unsigned own = strips_addr + (unsigned)(((w * G::RING + rq) * G::SW + l + R) * NPAIR * 8);
+  MCell<NPAIR> t = strip_ld<NPAIR>(own);
+  strip_st<NPAIR>(own, zero);
   if (l < R && w > 0) {
-    u64* h = strips + ((size_t)((w - 1) * G::RING + rq) * G::SW + 32 + R + l) * NPAIR;
-    const MCell<NPAIR> c = mcell_load<NPAIR>(h);
-    mcell_store<NPAIR>(h, zero);
+    const unsigned h = strips_addr + (unsigned)((((w - 1) * G::RING + rq) * G::SW + 32 + R + l) * NPAIR * 8);
+    const MCell<NPAIR> c = strip_ld<NPAIR>(h);
+    strip_st<NPAIR>(h, zero);
 #pragma unroll
     for (int p = 0; p < NPAIR; ++p) t.v[p] = add2(t.v[p], c.v[p]);
   }
   if (l >= 32 - R && w < nwarps - 1) {
-    u64* h = strips + ((size_t)((w + 1) * G::RING + rq) * G::SW + l - 32 + R) * NPAIR;
-    const MCell<NPAIR> c = mcell_load<NPAIR>(h);
-    mcell_store<NPAIR>(h, zero);
+    const unsigned h = strips_addr + (unsigned)((((w + 1) * G::RING + rq) * G::SW + l - 32 + R) * NPAIR * 8);
+    const MCell<NPAIR> c = strip_ld<NPAIR>(h);
+    strip_st<NPAIR>(h, zero);
 #pragma unroll
     for (int p = 0; p < NPAIR; ++p) t.v[p] = add2(t.v[p], c.v[p]);
   }
@@ -170,7 +227,7 @@ __device__ __forceinline__ MCell<NPAIR> strip_collect(u64* strips, int P, int rq
 }
 
 template <int TYPE, int R, int NPAIR, bool GRAD>
-__global__ void __launch_bounds__(32 * MARCH_MAX_WARPS, MARCH_CTAS_PER_SM) pattern_march_kernel(PatternMarchArgs a) {
+__global__ void __maxnreg__(MARCH_MAX_REGS) pattern_march_kernel(PatternMarchArgs a) {
   static_assert(TYPE == CENSUS_MSE || TYPE == CENSUS_SAD, "pair symmetry is a property of the census types");
   static_assert(R >= 1, "a 1 x 1 window has no pairs");
   using G = MarchGeom<R>;
@@ -183,6 +240,7 @@ __global__ void __launch_bounds__(32 * MARCH_MAX_WARPS, MARCH_CTAS_PER_SM) patte
   float2* ring_tw = reinterpret_cast<float2*>(ring_e + (size_t)G::RING * PITCH * NPAIR);  // [RING][PITCH] (t, w)
   u64* strips = reinterpret_cast<u64*>(ring_tw + (size_t)G::RING * PITCH);           // [nwarps][RING][SW][NPAIR]
   double* red = reinterpret_cast<double*>(strips + (size_t)nwarps * G::RING * G::SW * NPAIR);  // [nwarps][S+1]
+  double* sums = red + nwarps * (S + 1);                                             // [S+1][LW]
 
   const int H = a.H, W = a.W;
   const int EH = H + 2 * R, EW = W + 2 * R;
@@ -204,15 +262,7 @@ __global__ void __launch_bounds__(32 * MARCH_MAX_WARPS, MARCH_CTAS_PER_SM) patte
 
   const size_t hw = (size_t)H * W;
   const size_t fo = (size_t)n * hw;
-  const float* dptr[S];
-  float* gptr[S];
-#pragma unroll
-  for (int s = 0; s < S; ++s) {
-    dptr[s] = a.disp[s] + fo;
-    gptr[s] = GRAD ? a.grad[s] + fo : nullptr;
-  }
-  const float* imp = a.im + fo;
-  const float* sdp = a.std_in ? a.std_in + fo : nullptr;
+  // (plane pointers are re-derived from the parameter block at each use: they would cost 20 registers otherwise)
 
   const float gs = -0.5f * a.eps * a.inv_k2;
   float gss[S];            // census chain-rule constant x the caller's per-scale factor
@@ -230,51 +280,82 @@ __global__ void __launch_bounds__(32 * MARCH_MAX_WARPS, MARCH_CTAS_PER_SM) patte
     ring_tw[slot] = make_float2(0.0f, 0.0f);
   }
 
-  // stage one extended row: pattern warp of every scale, LCN image, sigma (0 outside the image)
-  auto stage_row = [&](int er) {
+  // Staging of one extended row in two halves: the streaming loads (issued a phase early so that their DRAM latency
+  // hides behind the pair arithmetic), then the pattern warp of every scale and the stores into the ring.
+  struct Raw {
+    float dv[S];
+    float tv, wv;
+  };
+  auto load_raw = [&](int er) __attribute__((always_inline)) {
     const int y = clampi(er - R, 0, H - 1);
     const bool inside = col_in && er >= R && er < EH - R;
     const size_t g = (size_t)y * W + x;
-    float dv[S];
+    Raw r;
 #pragma unroll
-    for (int s = 0; s < S; ++s) dv[s] = __ldg(dptr[s] + g);
-    const float tv = __ldg(imp + g);
-    const float wv = inside ? (sdp ? __ldg(sdp + g) : 1.0f) : 0.0f;
+    for (int s = 0; s < S; ++s) r.dv[s] = __ldg(a.disp[s] + fo + g);
+    r.tv = __ldg(a.im + fo + g);
+    r.wv = inside ? (a.std_in ? __ldg(a.std_in + fo + g) : 1.0f) : 0.0f;
+    return r;
+  };
+  auto finish_row = [&](int er, const Raw& r) __attribute__((always_inline)) {
+    const int y = clampi(er - R, 0, H - 1);
+    const bool inside = col_in && er >= R && er < EH - R;
     const WarpRow row = warp_row_setup(y, H, W, a.inv_h);
+    const float* prow0 = a.pattern + row.off0;
+    const float* prow1 = a.pattern + row.off1;
     const bool want_dd = GRAD && inside && col_own && er >= own_r0 && er < own_r1;
     float ev[S], dd[S];
 #pragma unroll
-    for (int s = 0; s < S; ++s) ev[s] = warp_col_sample(a.pattern, row, dv[s], x, W, a.inv_w, want_dd ? &dd[s] : nullptr);
-    int rq = er % G::RING;
-    const int slot = rq * PITCH + R + tid;
+    for (int s = 0; s < S; ++s)
+      ev[s] = warp_col_sample_clamped(prow0, prow1, row.wy0, row.wy1, r.dv[s], x, W, a.inv_w, want_dd ? &dd[s] : nullptr);
+    const int slot = (er % G::RING) * PITCH + R + tid;
 #pragma unroll
     for (int p = 0; p < NPAIR; ++p) ring_e[(size_t)slot * NPAIR + p] = pk2(ev[2 * p], ev[2 * p + 1]);
-    ring_tw[slot] = make_float2(tv, wv);
+    ring_tw[slot] = make_float2(r.tv, r.wv);
     if (want_dd) {
+      const size_t g = (size_t)y * W + x;
 #pragma unroll
-      for (int s = 0; s < S; ++s) gptr[s][g] = dd[s] * gss[s];   // parked; multiplied by G(p) when the row retires
+      for (int s = 0; s < S; ++s) a.grad[s][fo + g] = dd[s] * gss[s];   // parked; multiplied by G(p) when the row retires
     }
   };
 
-  for (int er = row_start; er < row_start + G::RING - MV; ++er) stage_row(er);
+  for (int er = row_start; er < row_start + R; ++er) finish_row(er, load_raw(er));
+  Raw raw[MV];
+  if (DIS_MARCH_PREFETCH) {
+#pragma unroll
+    for (int i = 0; i < MV; ++i) raw[i] = load_raw(row_start + R + i);
+  }
 
-  double numd[S], dend = 0.0;
+  // per-thread fp64 running sums (S numerators + the denominator) live in shared memory, not in 10 registers
+  double* my_sums = sums + tid;
 #pragma unroll
-  for (int s = 0; s < S; ++s) numd[s] = 0.0;
-  MCell<NPAIR> vacc, bacc;   // vertical fold: top virtual rows -> image row 0; image row H-1 + bottom virtual rows
+  for (int s = 0; s <= S; ++s) my_sums[s * LW] = 0.0;
+  // vertical fold: first the top virtual rows (added to image row 0, then reset), later image row H-1 plus the
+  // virtual rows below it -- never both at once (H >= 2), so one accumulator serves both
+  MCell<NPAIR> facc;
 #pragma unroll
-  for (int p = 0; p < NPAIR; ++p) vacc.v[p] = bacc.v[p] = 0ull;
+  for (int p = 0; p < NPAIR; ++p) facc.v[p] = 0ull;
+  const unsigned strips_addr = (unsigned)__cvta_generic_to_shared(strips);
+  const unsigned my_strip = strips_addr + (unsigned)((wid * G::RING * G::SW + lane + R) * NPAIR * 8);
+  constexpr unsigned STRIP_ROW_BYTES = G::SW * NPAIR * 8;
 
 #pragma unroll 1
   for (int step = 0; step < nsteps; ++step) {
     const int ys = row_start + step * MV;
-    // ---- A: stage the MV new rows this step needs ---------------------------------------------------------
-#pragma unroll
-    for (int i = 0; i < MV; ++i) stage_row(ys + R + i);
-    __syncthreads();
-
-    // ---- C: pairs -------------------------------------------------------------------------------------------
     const int r0 = ys % G::RING;
+    // ---- the MV new rows of this step enter the ring (their streaming loads were issued a step ago) --------------
+    if (!DIS_MARCH_PREFETCH) {
+#pragma unroll
+      for (int i = 0; i < MV; ++i) raw[i] = load_raw(ys + R + i);
+    }
+#pragma unroll
+    for (int i = 0; i < MV; ++i) finish_row(ys + R + i, raw[i]);
+    __syncthreads();
+    if (DIS_MARCH_PREFETCH && step + 1 < nsteps) {
+#pragma unroll
+      for (int i = 0; i < MV; ++i) raw[i] = load_raw(ys + MV + R + i);
+    }
+
     MCell<NPAIR> pe[MV], gp[MV];
     float ptc[MV], pwc[MV];
     float acc[S];
@@ -292,75 +373,94 @@ __global__ void __launch_bounds__(32 * MARCH_MAX_WARPS, MARCH_CTAS_PER_SM) patte
 #pragma unroll
       for (int p = 0; p < NPAIR; ++p) gp[i].v[p] = 0ull;
     }
-    u64* my_strip = strips + (size_t)wid * G::RING * G::SW * NPAIR;
+    const u64 tc2 = pk2(ptc[0], ptc[1]), wc2 = pk2(pwc[0], pwc[1]);
+    float stash[MV][S];     // d proj / d disp x constants of my two pixels, parked in the gradient buffer at staging
+    int stash_at[MV];
 
-    // one cell q = (row ys + j, column + dx); P0 / P1: which of my two pixels pair with it
-    auto cell = [&](int rq, int dx, auto p0_tag, auto p1_tag) {
+    // one cell q = (row ys + j, column + dx); P0 / P1: which of my two pixels pair with it.  The cell loops are kept
+    // rolled (MARCH_UNROLL cells per iteration): the fully unrolled step is ~70 KB of code and 21 warps at different
+    // places in it thrash the instruction cache (ncu: 34 % "no instruction" stalls in the staging phase).
+    auto cell = [&](int rq, int dx, auto p0_tag, auto p1_tag) __attribute__((always_inline)) {
       constexpr bool P0 = decltype(p0_tag)::value, P1 = decltype(p1_tag)::value;
       const int slot = rq * PITCH + R + tid + dx;
+      const unsigned c = my_strip + (unsigned)rq * STRIP_ROW_BYTES + dx * (NPAIR * 8);
+      MCell<NPAIR> cur;
+      if (GRAD) cur = strip_ld<NPAIR>(c);     // issued first: its latency hides behind the pair arithmetic
       const MCell<NPAIR> eq = mcell_load<NPAIR>(ring_e + (size_t)slot * NPAIR);
       const float2 tw = ring_tw[slot];
       MCell<NPAIR> cs;
-      if (P0) march_pair<TYPE, NPAIR, GRAD, true>(pe[0], ptc[0], pwc[0], eq, tw.x, tw.y, a.eps, eps2, acc, gp[0], cs);
-      if (P1) {
-        if (P0) march_pair<TYPE, NPAIR, GRAD, false>(pe[1], ptc[1], pwc[1], eq, tw.x, tw.y, a.eps, eps2, acc, gp[1], cs);
-        else march_pair<TYPE, NPAIR, GRAD, true>(pe[1], ptc[1], pwc[1], eq, tw.x, tw.y, a.eps, eps2, acc, gp[1], cs);
-      }
+      if (P0 && P1) march_pair2<TYPE, NPAIR, GRAD>(pe[0], pe[1], tc2, wc2, eq, tw.x, tw.y, eps2, acc, gp[0], gp[1], cs);
+      else if (P0) march_pair1<TYPE, NPAIR, GRAD>(pe[0], ptc[0], pwc[0], eq, tw.x, tw.y, a.eps, eps2, acc, gp[0], cs);
+      else march_pair1<TYPE, NPAIR, GRAD>(pe[1], ptc[1], pwc[1], eq, tw.x, tw.y, a.eps, eps2, acc, gp[1], cs);
       if (GRAD) {
-        u64* c = my_strip + ((size_t)rq * G::SW + lane + R + dx) * NPAIR;
-        MCell<NPAIR> cur = mcell_load<NPAIR>(c);
 #pragma unroll
         for (int p = 0; p < NPAIR; ++p) cur.v[p] = sub2(cur.v[p], cs.v[p]);
-        mcell_store<NPAIR>(c, cur);
-        __syncwarp();   // the next cell of this lane is the previous cell of its neighbour
+        strip_st<NPAIR>(c, cur);
       }
     };
     using T_ = std::true_type;
     using F_ = std::false_type;
-    {  // j = 0: dy = 0 for p0 (dx > 0 only)
-#pragma unroll
-      for (int dx = 1; dx <= R; ++dx) cell(r0, dx, T_{}, F_{});
-    }
-    {  // j = 1: dy = 1 for p0 (all dx), dy = 0 for p1 (dx > 0)
-      int rq = r0 + 1;
-      if (rq >= G::RING) rq -= G::RING;
-#pragma unroll
-      for (int dx = -R; dx <= 0; ++dx) cell(rq, dx, T_{}, F_{});
-#pragma unroll
-      for (int dx = 1; dx <= R; ++dx) cell(rq, dx, T_{}, T_{});
-    }
+    auto ring_row = [&](int j) {
+      const int rq = r0 + j;
+      return rq >= G::RING ? rq - G::RING : rq;
+    };
+    // p0 alone: row ys (dy = 0: dx > 0) and the left half of row ys + 1 (dy = 1; p1 joins for dx > 0)
 #pragma unroll 1
-    for (int j = 2; j <= R; ++j) {  // both pixels, all dx
-      int rq = r0 + j;
-      if (rq >= G::RING) rq -= G::RING;
-#pragma unroll
-      for (int dx = -R; dx <= R; ++dx) cell(rq, dx, T_{}, T_{});
+    for (int j = 0; j < 2; ++j) {
+      const int rq = ring_row(j);
+      const int lo = j == 0 ? 1 : -R, hi = j == 0 ? R : 0;
+#pragma unroll 1
+      for (int dx = lo; dx <= hi; ++dx) cell(rq, dx, T_{}, F_{});
     }
-    {  // j = R + 1: dy = R for p1 only
-      int rq = r0 + R + 1;
-      if (rq >= G::RING) rq -= G::RING;
+    // both pixels: right half of row ys + 1, then rows ys + 2 .. ys + R in full
+#pragma unroll 1
+    for (int j = 1; j <= R; ++j) {
+      const int rq = ring_row(j);
+      if (MARCH_UNROLL >= 2 * R + 1 && j == 1) {   // (fully unrolled variant: keep immediate offsets)
 #pragma unroll
+        for (int dx = 1; dx <= R; ++dx) cell(rq, dx, T_{}, T_{});
+      } else {
+#pragma unroll MARCH_UNROLL
+        for (int dx = (MARCH_UNROLL >= 2 * R + 1 || j != 1) ? -R : 1; dx <= R; ++dx) cell(rq, dx, T_{}, T_{});
+      }
+    }
+    {  // p1 alone: row ys + R + 1 (dy = R)
+      const int rq = ring_row(R + 1);
+#pragma unroll MARCH_UNROLL
       for (int dx = -R; dx <= R; ++dx) cell(rq, dx, F_{}, T_{});
     }
-    if (GRAD) {  // my own pixels' p-side sums join the strip (own cells: no other lane touches them now)
+    if (GRAD) {  // my own pixels' p-side sums join the strip
 #pragma unroll
       for (int i = 0; i < MV; ++i) {
         int rq = r0 + i;
         if (rq >= G::RING) rq -= G::RING;
-        u64* c = my_strip + ((size_t)rq * G::SW + lane + R) * NPAIR;
-        MCell<NPAIR> cur = mcell_load<NPAIR>(c);
+        const unsigned c = my_strip + (unsigned)rq * STRIP_ROW_BYTES;
+        MCell<NPAIR> cur = strip_ld<NPAIR>(c);
 #pragma unroll
         for (int p = 0; p < NPAIR; ++p) cur.v[p] = add2(cur.v[p], gp[i].v[p]);
-        mcell_store<NPAIR>(c, cur);
+        strip_st<NPAIR>(c, cur);
       }
     }
+    auto load_stash = [&]() __attribute__((always_inline)) {
+#pragma unroll
+      for (int i = 0; i < MV; ++i) {
+        const int er = ys + i;
+        const int y = er >= EH - R - 1 ? H - 1 : max(er - R, 0);
+        stash_at[i] = y * W + x;
+#pragma unroll
+        for (int s = 0; s < S; ++s)
+          stash[i][s] = (out_lane && er >= own_r0 && er < own_r1 && er >= R) ? a.grad[s][fo + stash_at[i]] : 0.0f;
+      }
+    };
+    if (GRAD && DIS_MARCH_STASH_EARLY) load_stash();   // L2 hits, in flight across the barrier
     if (ys >= own_r0) {  // pairs are counted by the band that owns p (halo steps only feed the strips)
 #pragma unroll
-      for (int s = 0; s < S; ++s) numd[s] += (double)acc[s];
+      for (int s = 0; s < S; ++s) my_sums[s * LW] += (double)acc[s];
     }
     __syncthreads();
 
-    // ---- E: rows ys, ys + 1 retire: merge strips, fold virtual pixels, write the gradient ------------------------
+    // ---- rows ys, ys + 1 retire: merge strips, fold virtual pixels, write the gradient ------------------------
+    if (GRAD && !DIS_MARCH_STASH_EARLY) load_stash();
     if (out_lane) {
 #pragma unroll
       for (int i = 0; i < MV; ++i) {
@@ -368,69 +468,69 @@ __global__ void __launch_bounds__(32 * MARCH_MAX_WARPS, MARCH_CTAS_PER_SM) patte
         int rq = r0 + i;
         if (rq >= G::RING) rq -= G::RING;
         const bool row_own = er >= own_r0 && er < own_r1;
-        if (row_own) dend += (double)ring_tw[rq * PITCH + R + tid].y;
+        if (row_own) my_sums[S * LW] += (double)ring_tw[rq * PITCH + R + tid].y;
         if (GRAD) {
-          MCell<NPAIR> t = strip_collect<R, NPAIR>(strips, tid, rq, nwarps);
+          MCell<NPAIR> t = strip_collect<R, NPAIR>(strips_addr, tid, rq, nwarps);
           if (ec == R) {  // left border column: virtual columns 0 .. R-1 fold onto it
             for (int k = 0; k < R; ++k) {
-              const MCell<NPAIR> c = strip_collect<R, NPAIR>(strips, tid - R + k, rq, nwarps);
+              const MCell<NPAIR> c = strip_collect<R, NPAIR>(strips_addr, tid - R + k, rq, nwarps);
 #pragma unroll
               for (int p = 0; p < NPAIR; ++p) t.v[p] = add2(t.v[p], c.v[p]);
             }
           }
           if (ec == EW - R - 1) {  // right border column
             for (int k = 1; k <= R; ++k) {
-              const MCell<NPAIR> c = strip_collect<R, NPAIR>(strips, tid + k, rq, nwarps);
+              const MCell<NPAIR> c = strip_collect<R, NPAIR>(strips_addr, tid + k, rq, nwarps);
 #pragma unroll
               for (int p = 0; p < NPAIR; ++p) t.v[p] = add2(t.v[p], c.v[p]);
             }
           }
           if (row_own) {
             bool emit = true;
-            int y = er - R;
             if (er < R) {                      // top virtual row
 #pragma unroll
-              for (int p = 0; p < NPAIR; ++p) vacc.v[p] = add2(vacc.v[p], t.v[p]);
+              for (int p = 0; p < NPAIR; ++p) facc.v[p] = add2(facc.v[p], t.v[p]);
               emit = false;
             } else if (er >= EH - R - 1) {     // image row H-1 and the virtual rows below it
 #pragma unroll
-              for (int p = 0; p < NPAIR; ++p) bacc.v[p] = add2(bacc.v[p], t.v[p]);
+              for (int p = 0; p < NPAIR; ++p) facc.v[p] = add2(facc.v[p], t.v[p]);
               emit = (er == EH - 1);
-              t = bacc;
-              y = H - 1;
+              t = facc;
             } else if (er == R) {              // image row 0
 #pragma unroll
-              for (int p = 0; p < NPAIR; ++p) t.v[p] = add2(t.v[p], vacc.v[p]);
+              for (int p = 0; p < NPAIR; ++p) {
+                t.v[p] = add2(t.v[p], facc.v[p]);
+                facc.v[p] = 0ull;
+              }
             }
             if (emit) {
-              const size_t g = (size_t)y * W + x;
 #pragma unroll
               for (int p = 0; p < NPAIR; ++p) {
                 float t0, t1;
                 upk2(t.v[p], t0, t1);
-                gptr[2 * p][g] = t0 * gptr[2 * p][g];
-                gptr[2 * p + 1][g] = t1 * gptr[2 * p + 1][g];
+                a.grad[2 * p][fo + stash_at[i]] = t0 * stash[i][2 * p];
+                a.grad[2 * p + 1][fo + stash_at[i]] = t1 * stash[i][2 * p + 1];
               }
             }
           }
         }
       }
     }
-    // (no barrier here: stage_row of the next step overwrites ring rows ys, ys+1, which every warp finished
-    //  reading before the barrier above; strip rows are next written after the barrier that follows staging)
+    // (no barrier here: the next step's new rows go into the ring rows of ys, ys+1, which every warp finished reading
+    //  before the barrier above; strip rows ys, ys+1 are written again only after the barrier that follows the next staging)
   }
 
   // ---- CTA reduction of S numerators + the denominator (fixed order) ------------------------------------------
   const double fs = (double)(fwd_scale<TYPE>() * a.inv_k2);
 #pragma unroll
   for (int s = 0; s < S; ++s) {
-    double v = col_own ? numd[s] * fs : 0.0;
+    double v = col_own ? my_sums[s * LW] * fs : 0.0;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     if (lane == 0) red[wid * (S + 1) + s] = v;
   }
   {
-    double v = dend;
+    double v = my_sums[S * LW];
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     if (lane == 0) red[wid * (S + 1) + S] = v;

@@ -118,11 +118,12 @@ int pattern_march_t(const PatternMarchArgs& a, const MarchPlan& plan, cudaStream
   const dim3 block(32 * plan.nwarps);
   const dim3 grid(plan.ncb, plan.nrb, a.N);
   const size_t smem = pattern_march_smem_bytes<R, NPAIR>(plan.nwarps);
+  const size_t smem_max = pattern_march_smem_bytes<R, NPAIR>(MARCH_MAX_WARPS);   // the opt-in is made once per kernel
   if (a.grad[0]) {
-    if (int rc = prepare(pattern_march_kernel<TYPE, R, NPAIR, true>, smem)) return rc;
+    if (int rc = prepare(pattern_march_kernel<TYPE, R, NPAIR, true>, smem_max)) return rc;
     pattern_march_kernel<TYPE, R, NPAIR, true><<<grid, block, smem, s>>>(a);
   } else {
-    if (int rc = prepare(pattern_march_kernel<TYPE, R, NPAIR, false>, smem)) return rc;
+    if (int rc = prepare(pattern_march_kernel<TYPE, R, NPAIR, false>, smem_max)) return rc;
     pattern_march_kernel<TYPE, R, NPAIR, false><<<grid, block, smem, s>>>(a);
   }
   return check_launch();
