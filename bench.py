@@ -8,14 +8,22 @@ One "step" = one pass of the hot path over one batch of synthetic structured-lig
     LCN(IR)  ->  4 x RectifiedPatternSimilarityLoss (census_sad 9x9, sigma-weighted, scales 1/2^s)
              ->  DisparitySmoothLoss(scale 0) * 0.4  ->  backward to the 4 disparity maps
 i.e. BASELINE.json configs[1] "DIS-SF training step ... batch 64": 64 samples x 4 frames = 256 frames of
-512x432 per GPU (the DispNet convolutions are out of scope and stay on cuDNN; they are not in the step).
-Frames shard by sample with no data-path collective; with N > 1 ranks the only exchange is the NCCL
-all-reduce of the loss numerators / denominators.  "scaling": "weak" (256 frames per GPU).
+512x432 per GPU, the reference's own default projector pattern (the DispNet convolutions are out of scope and stay
+on cuDNN; they are not in the step).  Frames shard by sample with no data-path collective; with N > 1 ranks the
+only exchange is the NCCL all-reduce of the loss numerators / denominators.  "scaling": "weak" (256 frames per GPU).
+`value` is timed through the drop-in surface (nn.Module forward() + autograd backward()); the fused
+value_and_grad() entry of the loss assembly is reported beside it.
 
 Printed JSON (rank 0, one line): the driver contract plus
-    roofline      dominant kernel (fused pattern-loss) algorithmic bytes / CUDA-event time vs measured HBM peak
-    cpu_baseline  the oracle's torch port of the reference timed on this box's host cores (bounded sample)
-    e2e           same step through the public modules with HOST (pinned) inputs, H2D + D2H inside the timed region
+    roofline        dominant kernel (pair-symmetric fused pattern loss) algorithmic bytes / CUDA-event time vs the measured
+                    HBM peak, with the kernel's XU / issue utilisation (ncu) beside it
+    value_and_grad  the same step through SingleFrameLoss.value_and_grad (final gradients from the kernels)
+    strong          (N > 1) 256 frames IN TOTAL split over the N ranks: the strong-scaling point of configs[1]
+    dis_mf          BASELINE configs[2], bs 32 in total split over the N ranks, with its own roofline / e2e / CPU leg
+    cpu_baseline    the oracle's torch port of the reference timed on this box's host cores (bounded sample)
+    cpu_baseline_cfg0  BASELINE configs[0] (batch 8, 480x640 and 512x432, 1 scale) on the host cores: torch port and
+                    the plain-C restatement, with the GPU time of the same workload
+    e2e             same step through the public modules with HOST (pinned, NUMA-local) inputs, H2D + D2H in the timed region
 --impl reference times the reference's CPU implementation of the path (oracle port; the reference is pure
 Python and its native dependency is un-vendored, so there is no oracle/_ref binary) on rank 0 only.
 """
@@ -35,6 +43,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 METRIC = "frames/s loss+warp fwd+bwd (DIS-SF)"
+DOMINANT = "pattern_march_kernel<census_sad, R=4, 4 scales, grad>"
 UNIT = "frames/s"
 HW = (512, 432)
 N_SCALES = 4
@@ -115,11 +124,36 @@ class ClockSampler:
                 "reasons": reasons, "samples": len(self.rows)}
 
 
-def make_host_inputs(n_frames, seed):
+def bind_to_gpu_numa_node(local_rank):
+    """Pin this process to the CPUs of the NUMA node its GPU hangs off BEFORE pinned host buffers are allocated
+    (first-touch placement): without it every rank's staging memory lands on node 0 and the ranks of the other
+    socket pull their inputs across the inter-socket link.  -> description string for the JSON line."""
+    try:
+        pr = torch.cuda.get_device_properties(local_rank)
+        bdf = f"{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+        with open(f"/sys/bus/pci/devices/{bdf}/numa_node") as f:
+            node = int(f.read().strip())
+        if node < 0:
+            return "numa node unknown (single node or virtualised): not bound"
+        with open(f"/sys/devices/system/node/node{node}/cpulist") as f:
+            cpus = set()
+            for part in f.read().strip().split(","):
+                lo, _, hi = part.partition("-")
+                cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return f"numa node {node}: no allowed cpu, not bound"
+        os.sched_setaffinity(0, cpus)
+        return f"bound to numa node {node} ({len(cpus)} cpus) of GPU {bdf}"
+    except Exception as e:   # sysfs layout differs / containers: the bench still runs, just unbound
+        return f"not bound ({type(e).__name__})"
+
+
+def make_host_inputs(n_frames, seed, hw=HW, n_scales=N_SCALES, kind="default"):
     """Synthetic frames on the host: a handful of distinct frames tiled up to the batch (generation is numpy)."""
     from depthinspace_b200 import synth
     base = min(n_frames, 8)
-    d = synth.make_frames(base, HW, "default", n_scales=N_SCALES, max_disp=128.0, seed=seed)
+    d = synth.make_frames(base, hw, kind, n_scales=n_scales, max_disp=128.0, seed=seed)
     reps = (n_frames + base - 1) // base
 
     def tile(a):
@@ -175,15 +209,94 @@ def run_reference_arm(args):
 
 
 # ------------------------------------------------------------------------------------------ GPU arm
+def cuda_ms(fn, steps):
+    """Total device time of `steps` calls of fn (CUDA events on the current stream, synchronised on both sides)."""
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    out = None
+    for _ in range(steps):
+        out = fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1), out
+
+
+def pipelined_e2e(upload, compute, k):
+    """k end-to-end steps: the host->device copies of step i+1 are issued on a side stream while step i computes (the
+    way a training loop prefetches); every step copies ITS OWN inputs and reads its loss back to the host."""
+    nxt = upload()
+    out = []
+    for i in range(k):
+        bufs, ev = nxt
+        torch.cuda.current_stream().wait_event(ev)
+        if i + 1 < k:
+            nxt = upload()
+        out.append(float(compute(bufs).detach()))      # D2H read of the step's loss
+    return out
+
+
+def cpu_cfg0(threads):
+    """BASELINE configs[0] on the host cores: batch 8, 1 scale, LCN + pattern-warp census_sad 9x9 loss + smoothness,
+    fwd+bwd, at the literal 480x640 and at the dataset shape 512x432 -- the oracle's torch port (the reference's own op
+    sequence) and the plain-C restatement (oracle/dis_oracle.c, scalar code fanned out over the frames)."""
+    from oracle import c_oracle, torch_port
+    rows = []
+    for hw in ((480, 640), HW):
+        sample = make_host_inputs(8, seed=42, hw=hw, n_scales=1)
+        torch.set_num_threads(threads)
+        pat_l, _ = torch_port.lcn(torch.from_numpy(sample["pattern"]))
+        disp = torch.from_numpy(sample["disp"][0]).requires_grad_(True)
+        t0 = time.perf_counter()
+        im_l, im_s = torch_port.lcn(torch.from_numpy(sample["im"]))
+        v = torch_port.pattern_loss(disp, im_l, im_s, pat_l, chunk=1)[0] + 0.4 * torch_port.smooth_loss(disp, torch.from_numpy(sample["ambient"]))
+        v.backward()
+        t_port = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        o_l, o_s = c_oracle.lcn_forward(sample["im"], 5, 0.05, "f32")
+        o_p, _ = c_oracle.lcn_forward(sample["pattern"], 5, 0.05, "f32")
+        c_oracle.pattern_loss(sample["disp"][0], o_l, o_s, o_p, 9, 3, 0.5, True, "f32")
+        c_oracle.smooth_loss(sample["disp"][0], sample["ambient"], True, "f32")
+        t_c = time.perf_counter() - t0
+        rows.append({"shape": f"{hw[0]}x{hw[1]}", "frames": 8, "port_frames_per_s": 8 / t_port, "c_oracle_frames_per_s": 8 / t_c,
+                     "cores": threads, "c_oracle_threads": min(8, c_oracle._threads())})
+    return rows
+
+
+def gpu_cfg0(dev):
+    """The configs[0] workload (batch 8, 1 scale) on the GPU through the public modules, for the row beside cpu_cfg0."""
+    from depthinspace_b200 import losses, networks
+    rows = {}
+    for hw in ((480, 640), HW):
+        sample = make_host_inputs(8, seed=42, hw=hw, n_scales=1)
+        lcn = networks.LCN(5, 0.05)
+        pat_l, _ = lcn(torch.from_numpy(sample["pattern"]).to(dev))
+        loss = losses.SingleFrameLoss(hw[0], hw[1], torch.cat([pat_l] * 3, dim=1))
+        im, amb = torch.from_numpy(sample["im"]).to(dev), torch.from_numpy(sample["ambient"]).to(dev)
+        disp = torch.from_numpy(sample["disp"][0]).to(dev).requires_grad_(True)
+
+        def one():
+            disp.grad = None
+            im_l, im_s = lcn(im)
+            torch.stack(loss([disp], im_l, im_s, amb)).sum().backward()
+        for _ in range(3):
+            one()
+        ms, _ = cuda_ms(one, 20)
+        rows[f"{hw[0]}x{hw[1]}"] = 8 / (ms / 20 * 1e-3)
+    return rows
+
+
 def run_ours(args):
+    import ctypes
     import torch.distributed as dist
-    from depthinspace_b200 import _lib, _ops, losses, networks
+    from depthinspace_b200 import _lib, _ops, losses, networks, synth
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    numa = bind_to_gpu_numa_node(local_rank)       # before any pinned allocation
     group = None
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
@@ -204,16 +317,9 @@ def run_ours(args):
     im, amb = h_im.to(dev), h_amb.to(dev)
     disps = [p.to(dev).requires_grad_(True) for p in h_disp]
 
-    def step(im_d, amb_d, disps_d):
-        """LCN + fused loss/gradient kernels: every term of the assembly and d(total)/d(disparity map) for all 4 scales
-        (losses.SingleFrameLoss.value_and_grad; the gradients are what autograd.backward(outs, grads) feeds DispNet)."""
-        im_l, im_s = lcn(im_d)
-        vals, grads = loss.value_and_grad(disps_d, im_l, im_s, amb_d, global_frames=n * world)
-        step.grads = grads
-        return torch.stack(vals).sum()
-
-    def autograd_step(im_d, amb_d, disps_d):
-        """The same through the nn.Module / autograd surface (forward() + backward(), five gradient-scaling passes)."""
+    def module_step(im_d, amb_d, disps_d):
+        """The drop-in surface: nn.Module forward() + autograd backward() (the reference's call shape,
+        model/single_frame_worker.py:101-165 followed by loss.backward(), model/worker.py:522-524)."""
         for d in disps_d:
             d.grad = None
         im_l, im_s = lcn(im_d)
@@ -224,86 +330,82 @@ def run_ours(args):
         total.backward()
         return total
 
+    def vg_step(im_d, amb_d, disps_d, frames_global):
+        """LCN + fused loss/gradient kernels: every term of the assembly and d(total)/d(disparity map) for all 4 scales
+        (losses.SingleFrameLoss.value_and_grad; the gradients are what autograd.backward(outs, grads) feeds DispNet)."""
+        im_l, im_s = lcn(im_d)
+        vals, grads = loss.value_and_grad(disps_d, im_l, im_s, amb_d, global_frames=frames_global)
+        vg_step.grads = grads
+        return torch.stack(vals).sum()
+
     def sync_all():
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
             torch.cuda.synchronize()
 
+    def timed(fn, steps):
+        """K steps bracketed by barrier + synchronize on both sides; CUDA events on the launching stream."""
+        sync_all()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        out = None
+        for _ in range(steps):
+            out = fn()
+        e1.record()
+        sync_all()
+        return e0.elapsed_time(e1), out
+
     # the clock sampler covers warm-up + timed region (the GPU is under the same load throughout), so that
     # even a short timed region gets several 100 ms samples
     with ClockSampler(local_rank) as clocks:
         for _ in range(args.warmup):
-            step(im, amb, disps)
-        sync_all()
-
-        # ---- device-resident timing (value) ----
+            module_step(im, amb, disps)
         l0 = _lib.LAUNCHES
-        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        ev0.record()
-        for _ in range(args.steps):
-            total = step(im, amb, disps)
-        ev1.record()
-        sync_all()
+        ms, total = timed(lambda: module_step(im, amb, disps), args.steps)     # ---- headline: device-resident, module path
         launches = _lib.LAUNCHES - l0             # libdis_b200 kernels enqueued inside the timed region
-        if ev0.elapsed_time(ev1) < 400.0:      # keep the load on until nvidia-smi has reported at least a few samples
+        if ms < 400.0:      # keep the load on until nvidia-smi has reported at least a few samples
             t_end = time.perf_counter() + 0.5
             while time.perf_counter() < t_end:
-                step(im, amb, disps)
+                module_step(im, amb, disps)
             torch.cuda.synchronize()
-    ms = ev0.elapsed_time(ev1)
     loss_value = float(total.detach())
+    module_grads = [d.grad.clone() for d in disps]
 
-    # ---- the same work through the nn.Module / autograd surface (forward() + backward()) ----
+    # ---- the same work through the fused value-and-gradient entry (no scaling passes, 2 collectives per step) ----
     for _ in range(2):
-        autograd_step(im, amb, disps)
-    a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    torch.cuda.synchronize()
-    a0.record()
-    for _ in range(args.steps):
-        a_total = autograd_step(im, amb, disps)
-    a1.record()
-    torch.cuda.synchronize()
-    autograd_ms = a0.elapsed_time(a1) / args.steps
-    grad_gap = max(float((g.view_as(d) - d.grad).abs().max() / d.grad.abs().max()) for g, d in zip(step.grads, disps))
-    assert abs(float(a_total.detach()) - loss_value) <= 2e-6 * abs(loss_value) and grad_gap < 1e-5, (grad_gap, loss_value)
+        vg_step(im, amb, disps, n * world)
+    vg_total_ms, vg_total = timed(lambda: vg_step(im, amb, disps, n * world), args.steps)
+    grad_gap = max(float((g.view_as(d) - m).abs().max() / m.abs().max()) for g, d, m in zip(vg_step.grads, disps, module_grads))
+    assert abs(float(vg_total.detach()) - loss_value) <= 2e-6 * abs(loss_value) and grad_gap < 1e-5, (grad_gap, loss_value)
+    del module_grads
 
-    # ---- the same step captured once into a CUDA graph and replayed (launch gaps and Python overhead removed) ----
+    # ---- value_and_grad captured once into a CUDA graph and replayed (launch gaps and Python overhead removed) ----
     graph_ms = None
-    try:
-        side = torch.cuda.Stream()
-        side.wait_stream(torch.cuda.current_stream())
-        with torch.cuda.stream(side):
-            # fresh leaves: autograd binds a leaf's gradient accumulation to the stream of its first use, and the
-            # benchmark's own leaves were first used on the legacy default stream, which a capture may not touch
-            g_disps = [d.detach().clone().requires_grad_(True) for d in disps]
+    if world == 1:
+        try:
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                g_disps = [d.detach().clone() for d in disps]
+                for _ in range(2):
+                    vg_step(im, amb, g_disps, n)
+            torch.cuda.current_stream().wait_stream(side)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                g_total = vg_step(im, amb, g_disps, n)
             for _ in range(2):
-                step(im, amb, g_disps)
-        torch.cuda.current_stream().wait_stream(side)
-        graph = torch.cuda.CUDAGraph()
-        for d in g_disps:
-            d.grad = None
-        with torch.cuda.graph(graph):
-            g_total = step(im, amb, g_disps)
-        for _ in range(2):
-            graph.replay()
-        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        torch.cuda.synchronize()
-        g0.record()
-        for _ in range(args.steps):
-            graph.replay()
-        g1.record()
-        torch.cuda.synchronize()
-        graph_ms = g0.elapsed_time(g1) / args.steps
-        assert abs(float(g_total.detach()) - loss_value) <= 1e-6 * abs(loss_value)
-        del graph
-    except Exception as e:  # graph capture is an optimisation on top of the public API, never a requirement
-        import traceback
-        traceback.print_exc(file=sys.stderr)
-        graph_ms = f"unavailable: {type(e).__name__}: {e}"[:160]
+                graph.replay()
+            g_ms, _ = cuda_ms(graph.replay, args.steps)
+            graph_ms = g_ms / args.steps
+            assert abs(float(g_total.detach()) - loss_value) <= 2e-6 * abs(loss_value)
+            del graph, g_disps
+        except Exception as e:  # graph capture is an optimisation on top of the public API, never a requirement
+            import traceback
+            traceback.print_exc(file=sys.stderr)
+            graph_ms = f"unavailable: {type(e).__name__}: {e}"[:160]
 
-    # ---- dominant kernel alone: 4-scale fused pattern-loss (census_sad 9x9, with gradient stash) ----
-    import ctypes
+    # ---- dominant kernel alone: 4-scale fused pattern loss (census_sad 9x9, with gradients), through the C-ABI ----
     im_l, im_s = lcn(im)
     gnums = [torch.empty_like(d) for d in disps]
     lib = _lib.load()
@@ -320,20 +422,13 @@ def run_ours(args):
                                                       n, HW[0], HW[1], 9, 3, 0.5, stream))
     for _ in range(3):
         dominant()
-    k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    torch.cuda.synchronize()
     reps = max(3, min(args.steps, 10))
-    k0.record()
-    for _ in range(reps):
-        dominant()
-    k1.record()
-    torch.cuda.synchronize()
-    kernel_ms = k0.elapsed_time(k1) / reps
+    k_ms, _ = cuda_ms(dominant, reps)
+    kernel_ms = k_ms / reps
+    del gnums, partials
 
-    # ---- end to end: host (pinned) inputs -> public modules -> loss scalar back on the host ----
-    # Every step copies ITS OWN inputs (raw IR, ambient, 4 disparity maps = 1.36 GB) from pinned host memory and reads
-    # its loss back.  The copies of step i+1 are issued on a side stream while step i computes (double buffering), the
-    # way a training loop prefetches; nothing is reused across steps.
+    # ---- end to end: host (pinned, NUMA-local) inputs -> public modules -> loss scalar back on the host ----
+    # Every step copies ITS OWN inputs (raw IR, ambient, 4 disparity maps = 1.36 GB) and reads its loss back.
     copy_stream = torch.cuda.Stream()
 
     def upload():
@@ -344,32 +439,56 @@ def run_ours(args):
             ev.record(copy_stream)
         return bufs, ev
 
-    def e2e_run(k):
-        nxt = upload()
-        losses_host = []
-        for i in range(k):
-            (im_d, amb_d, disps_d), ev = nxt
-            torch.cuda.current_stream().wait_event(ev)
-            if i + 1 < k:
-                nxt = upload()
-            for t in (im_d, amb_d, *disps_d):
-                t.record_stream(torch.cuda.current_stream())
-            total = step(im_d, amb_d, [d.requires_grad_(True) for d in disps_d])
-            losses_host.append(float(total.detach()))    # D2H read of the step's loss
-        return losses_host
+    def e2e_compute(bufs):
+        im_d, amb_d, disps_d = bufs
+        for t in (im_d, amb_d, *disps_d):
+            t.record_stream(torch.cuda.current_stream())
+        return module_step(im_d, amb_d, [d.requires_grad_(True) for d in disps_d])
 
-    e2e_run(2)
+    pipelined_e2e(upload, e2e_compute, 2)
     sync_all()
     t0 = time.perf_counter()
-    e2e_run(args.steps)
+    pipelined_e2e(upload, e2e_compute, args.steps)
     sync_all()
     e2e_s = time.perf_counter() - t0
+    h2d_bytes = int((2 + N_SCALES) * 4 * P * n)
+    # raw host->device bandwidth of this rank alone and with all ranks copying at once (the e2e ceiling)
+    probe = torch.empty_like(h_im, device=dev)
+
+    def h2d_probe():
+        probe.copy_(h_im, non_blocking=True)
+    h2d_probe()
+    sync_all()
+    pm, _ = cuda_ms(h2d_probe, 5)
+    h2d_gbs = h_im.numel() * 4 * 5 / (pm * 1e-3) / 1e9
+    del probe
+
+    # ---- strong scaling point of configs[1]: 256 frames IN TOTAL, split over the ranks ----
+    strong = None
+    if world > 1 and FRAMES_PER_GPU % world == 0:
+        ns = FRAMES_PER_GPU // world
+        s_im, s_amb = im[:ns].contiguous(), amb[:ns].contiguous()
+        s_disps = [d.detach()[:ns].clone().requires_grad_(True) for d in disps]
+        for _ in range(3):
+            module_step(s_im, s_amb, s_disps)
+            vg_step(s_im, s_amb, s_disps, FRAMES_PER_GPU)
+        sm_ms, _ = timed(lambda: module_step(s_im, s_amb, s_disps), args.steps)
+        sv_ms, _ = timed(lambda: vg_step(s_im, s_amb, s_disps, FRAMES_PER_GPU), args.steps)
+        strong = (sm_ms, sv_ms, ns)
+        del s_im, s_amb, s_disps
 
     # ---- max over ranks ----
-    times = torch.tensor([ms, e2e_s * 1e3, kernel_ms], device=dev, dtype=torch.float64)
+    times = torch.tensor([ms, e2e_s * 1e3, kernel_ms, vg_total_ms, strong[0] if strong else 0.0, strong[1] if strong else 0.0],
+                         device=dev, dtype=torch.float64)
+    h2d_all = torch.tensor([h2d_gbs], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
-    ms, e2e_ms, kernel_ms = times.tolist()
+        gathered = [torch.zeros_like(h2d_all) for _ in range(world)]
+        dist.all_gather(gathered, h2d_all)
+        h2d_list = [round(float(g), 1) for g in gathered]
+    else:
+        h2d_list = [round(h2d_gbs, 1)]
+    ms, e2e_ms, kernel_ms, vg_total_ms, strong_m, strong_v = times.tolist()
     frames = n * world * args.steps
     value = frames / (ms * 1e-3)
     e2e_value = frames / (e2e_ms * 1e-3)
@@ -377,55 +496,37 @@ def run_ours(args):
     achieved = KERNEL_ALGO_BYTES_PER_FRAME * P * n / (kernel_ms * 1e-3) / 1e9
     step_gbs = ALGO_BYTES_PER_FRAME * P * (value / world) / 1e9
 
-    # ---- DIS-MF hot path (BASELINE configs[2]) on this GPU, reported beside the headline (N = 1 only) ----
+    # ---- DIS-MF hot path (BASELINE configs[2]: bs 32 IN TOTAL) at every N ----
     mf_line, sfg_line = None, None
-    if world == 1 and not args.no_mf:
+    if not args.no_mf and 32 % world == 0:
         try:
-            del disps, im, amb
+            del disps, im, amb, im_l, im_s
             torch.cuda.empty_cache()
             sys.path.insert(0, os.path.join(ROOT, "tools"))
             import bench_mf
-            w = bench_mf.build(32, dev)
-            for _ in range(3):
-                bench_mf.step(w)
-            m0, m1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            torch.cuda.synchronize()
-            m0.record()
-            for _ in range(args.steps):
-                bench_mf.step(w)
-            m1.record()
-            torch.cuda.synchronize()
-            mf_ms = m0.elapsed_time(m1) / args.steps
-            mf_line = {"value": 128 / (mf_ms * 1e-3), "unit": UNIT, "ms_per_step": mf_ms, "frames_per_step": 128,
-                       "workload": "BASELINE configs[2] on one GPU: DIS-MF hot path, bs 32 x tl 4 (copy_data LCN, 24 xyz/flow + 96 C=32 "
-                                   "feature warps fwd/recompute/bwd, 1-scale census_sad + smoothness + 12 flow-consistency terms + L1), "
-                                   "see tools/bench_mf.py"}
-            del w
-            torch.cuda.empty_cache()
-            # the DIS-SF assembly INCLUDING its 12 flow-consistency terms (the headline follows SURVEY 8(d): 144P, without)
-            w = bench_mf.build_sf(64, dev)
-            for _ in range(3):
-                bench_mf.step_sf(w)
-            torch.cuda.synchronize()
-            m0.record()
-            for _ in range(args.steps):
-                bench_mf.step_sf(w)
-            m1.record()
-            torch.cuda.synchronize()
-            sfg_ms = m0.elapsed_time(m1) / args.steps
-            sfg_line = {"value": 256 / (sfg_ms * 1e-3), "unit": UNIT, "ms_per_step": sfg_ms, "frames_per_step": 256,
-                        "workload": "DIS-SF loss assembly with its geometric terms (single_frame_worker.py:101-149): copy_data LCN + "
-                                    "4 x census_sad 9x9 + smoothness + 6 pairs x 2 directions of the flow-consistency loss, "
-                                    "module/autograd path, see tools/bench_mf.py --sf"}
-            del w
+            mf_line = bench_mf.measure(32 // world, dev, group, world, args.steps, peak, sync_all, rank == 0 and world == 1 and not args.no_cpu_baseline)
+            if world == 1:
+                # the DIS-SF assembly INCLUDING its 12 flow-consistency terms (the headline follows SURVEY 8(d): 144P, without)
+                w = bench_mf.build_sf(64, dev)
+                for _ in range(3):
+                    bench_mf.step_sf(w)
+                sfg_total, _ = cuda_ms(lambda: bench_mf.step_sf(w), args.steps)
+                sfg_ms = sfg_total / args.steps
+                sfg_line = {"value": 256 / (sfg_ms * 1e-3), "unit": UNIT, "ms_per_step": sfg_ms, "frames_per_step": 256,
+                            "workload": "DIS-SF loss assembly with its geometric terms (single_frame_worker.py:101-149): copy_data LCN + "
+                                        "4 x census_sad 9x9 + smoothness + 6 pairs x 2 directions of the flow-consistency loss, "
+                                        "module/autograd path, see tools/bench_mf.py --sf"}
+                del w
         except Exception as e:
+            import traceback
+            traceback.print_exc(file=sys.stderr)
             if mf_line is None:
                 mf_line = f"unavailable: {type(e).__name__}: {e}"[:200]
             else:
                 sfg_line = f"unavailable: {type(e).__name__}: {e}"[:200]
 
     if rank == 0:
-        cpu = None
+        cpu, cfg0 = None, None
         if world == 1 and not args.no_cpu_baseline:
             threads = os.cpu_count() or 1
             sample = make_host_inputs(2, seed=42)
@@ -433,29 +534,51 @@ def run_ours(args):
             t, _ = cpu_reference_step(sample, threads)
             cpu = {"value": 2 / t, "unit": UNIT, "cores": threads, "kind": "port",
                    "sample": "2 of the 256 frames, 1 pass, oracle torch port of the reference modules, all host threads"}
+            try:
+                torch.cuda.empty_cache()
+                gpu_rows = gpu_cfg0(dev)
+                cfg0 = {"workload": "BASELINE configs[0]: DIS-SF LCN + pattern-warp census_sad 9x9 loss + smoothness fwd+bwd, batch 8, 1 scale, "
+                                    "default pattern (procedural stand-in at 480x640: the reference defines its patterns for 512x432)",
+                        "unit": UNIT, "rows": cpu_cfg0(threads)}
+                for r in cfg0["rows"]:
+                    r["gpu_frames_per_s"] = gpu_rows[r["shape"]]
+            except Exception as e:
+                cfg0 = f"unavailable: {type(e).__name__}: {e}"[:200]
+        pipes = measured_pipes(DOMINANT) or {}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"BASELINE configs[1]: DIS-SF loss path, {n} frames/GPU (bs 64 x tl 4), {HW[0]}x{HW[1]}, "
-                                   "default pattern, LCN r5 + 4 x (pattern warp + census_sad 9x9, sigma-weighted) + smoothness, "
-                                   "loss terms + gradients w.r.t. all 4 disparity maps (SingleFrameLoss.value_and_grad)",
+                                   f"default pattern ({synth.pattern_source('default', HW)}), LCN r5 + 4 x (pattern warp + census_sad 9x9, "
+                                   "sigma-weighted) + smoothness, forward() + backward() of the drop-in modules (SingleFrameLoss)",
                        "frames_per_gpu": n, "l2": "inputs (2.7 GB/step) exceed the 126 MB L2; no flush needed",
                        "loss": loss_value},
             "clocks": clocks.summary(),
-            "e2e": {"value": e2e_value, "unit": UNIT,
-                    "h2d_bytes_per_step": int((2 + N_SCALES) * 4 * P * n), "d2h_bytes_per_step": 4},
-            "gpu_launches": launches, "cuda_graph_ms_per_step": graph_ms, "autograd_modules_ms_per_step": autograd_ms,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,
+                    "h2d_gbs_per_rank_all_ranks_copying": h2d_list, "host_buffers": numa,
+                    "h2d_bound_frames_per_s": sum(h2d_list) * 1e9 / (h2d_bytes / n)},
+            "gpu_launches": launches,
+            "value_and_grad": {"value": frames / (vg_total_ms * 1e-3), "unit": UNIT, "ms_per_step": vg_total_ms / args.steps,
+                               "cuda_graph_ms_per_step": graph_ms,
+                               "note": "SingleFrameLoss.value_and_grad: same terms and gradients, final gradients written by the kernels"},
+            "strong": None if not strong else {
+                "frames_total": FRAMES_PER_GPU, "frames_per_gpu": strong[2], "scaling": "strong",
+                "value": FRAMES_PER_GPU * args.steps / (strong_m * 1e-3), "ms_per_step": strong_m / args.steps,
+                "value_and_grad_value": FRAMES_PER_GPU * args.steps / (strong_v * 1e-3), "value_and_grad_ms_per_step": strong_v / args.steps,
+                "unit": UNIT},
             "dis_mf": mf_line, "dis_sf_with_geometric_terms": sfg_line,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": measured_traffic("pattern_multi_kernel<census_sad, R=4, 4 scales, grad>", n),
+                         "traffic": measured_traffic(DOMINANT, n),
                          "algorithmic_bytes": KERNEL_ALGO_BYTES_PER_FRAME * P * n,
-                         "kernel": "pattern_multi_kernel<census_sad, R=4, 4 scales, grad>",
-                         "kernel_ms": kernel_ms, "peak_source": peak_src,
-                         "limiter": "XU (rsqrt) + FP32 issue, not HBM: ~100 rsqrt per pixel-scale (see DESIGN.md)",
-                         "pipes_pct_of_peak": measured_pipes("pattern_multi_kernel<census_sad, R=4, 4 scales, grad>"),
+                         "kernel": DOMINANT, "kernel_ms": kernel_ms, "peak_source": peak_src,
+                         "xu_frac": pipes.get("xu", 0) / 100 if pipes else None,
+                         "issue_frac": pipes.get("issue_active", 0) / 100 if pipes else None,
+                         "limiter": "issue slots / FP32 pipe / XU (rsqrt) in balance, not HBM: 5 rsqrt + ~41 instructions per unordered "
+                                    "pixel pair for 4 scales, 40 pairs per pixel (see DESIGN.md)",
+                         "pipes_pct_of_peak": pipes or None,
                          "step_algorithmic_gbs": step_gbs, "step_frac": step_gbs / peak},
-            "cpu_baseline": cpu,
+            "cpu_baseline": cpu, "cpu_baseline_cfg0": cfg0,
         }
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -393,6 +393,36 @@ def flow_warp_gather_all_backward(flows, grad_out):
     return gx
 
 
+def resize_bilinear(tensors, size, mode=0):
+    """Bilinear align_corners=True resize of a list of equally shaped [N,C,H,W] tensors to `size` in one launch.
+    mode 0 plain, 1 flow (x / y channel rescaled by the size ratio), 2 mask (> 0.5 -> 1 / 0).  -> list of outputs"""
+    import ctypes
+    tensors = [_chk(t, f"tensor[{i}]") for i, t in enumerate(tensors)]
+    if not tensors:
+        return []
+    N, C, H, W = tensors[0].shape
+    if any(t.shape != tensors[0].shape for t in tensors):
+        raise ValueError("all tensors of one resize call must have the same shape")
+    oh, ow = int(size[0]), int(size[1])
+    outs = [torch.empty((N, C, oh, ow), dtype=t.dtype, device=t.device) for t in tensors]
+    Arr = ctypes.c_void_p * len(tensors)
+    with _on(tensors[0]) as lib:
+        _lib.check(lib.dis_resize_bilinear_forward(Arr(*[t.data_ptr() for t in tensors]), Arr(*[o.data_ptr() for o in outs]),
+                                                   len(tensors), N, C, H, W, oh, ow, int(mode), _stream(tensors[0])),
+                   launches=(len(tensors) + 55) // 56)
+    return outs
+
+
+def resize_bilinear_backward(grad_out, in_shape):
+    grad_out = _chk(grad_out, "grad_out")
+    N, C, oh, ow = grad_out.shape
+    H, W = int(in_shape[-2]), int(in_shape[-1])
+    g = torch.empty((N, C, H, W), dtype=grad_out.dtype, device=grad_out.device)
+    with _on(grad_out) as lib:
+        _lib.check(lib.dis_resize_bilinear_backward(_ptr(grad_out), _ptr(g), N, C, H, W, oh, ow, _stream(grad_out)))
+    return g
+
+
 def lcn_backward(data, lcn, std, g_lcn, g_std, radius, eps):
     data, lcn, std = _chk(data, "data"), _chk(lcn, "lcn"), _chk(std, "std")
     N, C, H, W = data.shape

@@ -47,6 +47,9 @@ int combine2(const float*, const float*, float*, size_t, const float*, const flo
 int geometric_grad_combine(const float* const*, const int*, int, const float*, const float*, float, float*, int, size_t,
                            cudaStream_t);
 
+int resize_bilinear_forward(const float* const*, float* const*, int, int, int, int, int, int, int, int, cudaStream_t);
+int resize_bilinear_backward(const float*, float*, int, int, int, int, int, int, cudaStream_t);
+
 int conv3d_out_size(int, int, int);
 size_t conv3d_scratch_elems(int, int, int, int);
 int conv3d_gather_forward(const float*, const float*, const float*, float*, float*, uint8_t*, float*, int, int, int, int,
@@ -196,7 +199,27 @@ using namespace dis;
 
 extern "C" {
 
-int dis_abi_version(void) { return 2; }
+int dis_abi_version(void) { return 3; }
+
+int dis_resize_bilinear_forward(const float* const* ins, float* const* outs, int count, int N, int C, int H, int W, int oh,
+                                int ow, int mode, void* stream) {
+  if (!ins || !outs) return DIS_ERR_NULL_POINTER;
+  if (count < 0 || N < 0 || C < 1 || H < 1 || W < 1 || oh < 1 || ow < 1 || (long)oh * ow > INT_MAX || (long)H * W > INT_MAX)
+    return DIS_ERR_BAD_SHAPE;
+  if (mode < 0 || mode > 2 || (mode == 1 && C != 2)) return DIS_ERR_UNSUPPORTED_COMBINATION;
+  for (int i = 0; i < count; ++i)
+    if (!ins[i] || !outs[i]) return DIS_ERR_NULL_POINTER;
+  if (count == 0 || N == 0) return DIS_OK;
+  return resize_bilinear_forward(ins, outs, count, N, C, H, W, oh, ow, mode, as_stream(stream));
+}
+
+int dis_resize_bilinear_backward(const float* grad_out, float* grad_in, int N, int C, int H, int W, int oh, int ow,
+                                 void* stream) {
+  if (!grad_out || !grad_in) return DIS_ERR_NULL_POINTER;
+  if (N < 0 || C < 1 || H < 1 || W < 1 || oh < 1 || ow < 1 || (long)oh * ow > INT_MAX || (long)H * W > INT_MAX) return DIS_ERR_BAD_SHAPE;
+  if (N == 0) return DIS_OK;
+  return resize_bilinear_backward(grad_out, grad_in, N, C, H, W, oh, ow, as_stream(stream));
+}
 
 const char* dis_status_string(int status) {
   switch (status) {

@@ -347,7 +347,7 @@ int conv3d_gather_forward(const float* xyz, const float* feat, const float* mask
   if (e != cudaSuccess) { set_last_cuda_error(e); return DIS_ERR_CUDA_LAUNCH; }
   const size_t n_src = (size_t)tl * bs * h * w;
   conv3d_plane_kernel<<<flat_grid(n_src, 256), 256, 0, s>>>(xyz, a.plane, (size_t)h * w, n_src);
-  if (k == 3 && tl == 4) {
+  if (k == 3 && tl == 4 && nb == 9) {   // the FIXED instantiation hard-codes 36 candidates AND 9 neighbours
     conv3d_rank_kernel<false, true><<<(M + 127) / 128, 128, 0, s>>>(a);
     conv3d_rank_kernel<true, true><<<(M + 127) / 128, 128, 0, s>>>(a);
   } else {

@@ -18,20 +18,25 @@ class _L1Mean(torch.autograd.Function):
     """torch.mean(torch.abs(o - target)) with the gradient w.r.t. o produced by the same pass."""
 
     @staticmethod
-    def forward(ctx, o, target):
+    def forward(ctx, o, target, group):
         out3, sgn = _ops.l1_forward(o, target, want_grad=ctx.needs_input_grad[0])
+        if group is not None:      # mean over the WHOLE data-parallel batch: all-reduce (sum, count), then divide
+            from .parallel import all_reduce_sum_
+            nd = out3[:2].contiguous()
+            all_reduce_sum_(nd, group)
+            out3 = torch.cat((nd, (nd[0] / nd[1]).reshape(1)))
         ctx.save_for_backward(sgn, out3)
         return out3[2].clone()
 
     @staticmethod
     def backward(ctx, g):
         sgn, out3 = ctx.saved_tensors
-        return _ops.scale_by_device_scalar(sgn, g, out3[1:2]).view_as(sgn), None
+        return _ops.scale_by_device_scalar(sgn, g, out3[1:2]).view_as(sgn), None, None
 
 
-def l1_mean(o, target):
-    """mean |o - target| (gradient to o only: the targets are data)."""
-    return _L1Mean.apply(o.contiguous(), target.detach())
+def l1_mean(o, target, process_group=None):
+    """mean |o - target| (gradient to o only: the targets are data); with a process group the mean runs over all ranks."""
+    return _L1Mean.apply(o.contiguous(), target.detach(), process_group)
 
 
 class _MaskedL1Mean(torch.autograd.Function):
@@ -61,7 +66,9 @@ def masked_l1_mean(o, target, noise=None, threshold=30.0, process_group=None):
 
 
 def _merge(x):
-    """[tl,bs,C,H,W] -> [tl*bs,C,H,W] (model/multi_frame_networks.py:36-37); 4-D tensors pass through."""
+    """[tl,bs,C,H,W] -> [tl*bs,C,H,W] (model/multi_frame_networks.py:36-37); 4-D tensors and None pass through."""
+    if x is None:
+        return None
     return x.contiguous().view(-1, *x.shape[-3:]) if x.dim() == 5 else x
 
 
@@ -73,14 +80,14 @@ class _GeometricTerms(torch.autograd.Function):
     `depth[i]` indexing, 10 gradient accumulations and DispToDepth's backward."""
 
     @staticmethod
-    def forward(ctx, disp_tl, primary_disp, R, t, amb, K, ray, clamp, multi_frame, bf, weight, *flows):
+    def forward(ctx, disp_tl, primary_disp, R, t, amb, K, ray, clamp, multi_frame, bf, weight, group, *flows):
         ctx.set_materialize_grads(False)
         tl = disp_tl.shape[0]
         disp_tl = disp_tl.contiguous()
         depth = bf / (torch.relu(disp_tl) + 1e-12)                     # DispToDepth, reference model/networks.py:311-319
         primary = bf / (torch.relu(primary_disp) + 1e-12) if multi_frame else None
         need = ctx.needs_input_grad[0]
-        vals, planes, frame_of, dens = [], [], [], []
+        planes, frame_of, nd = [], [], []
         k = 0
         for i in range(tl):
             for j in range(i + 1, tl):
@@ -92,25 +99,30 @@ class _GeometricTerms(torch.autograd.Function):
                 b3, _, _, gB1, gB0 = _ops.flow_consistency_dir(depth[j], depth[i], R[j], t[j], R[i], t[i], f_ji, f_ij, amb[j],
                                                                amb[i], K, ray, clamp, primary[i] if multi_frame else None,
                                                                False, False, need, need)
-                vals.append((a3[0] / (a3[1] + 1e-8) + b3[0] / (b3[1] + 1e-8)) * weight)   # :599 / :653, times 0.2 / #pairs
+                nd += [a3[:2], b3[:2]]
                 if need:
                     planes += [gA0, gA1, gB1, gB0]
                     frame_of += [i, j, j, i]
-                    dens += [a3[1], a3[1], b3[1], b3[1]]
+        nd = torch.stack(nd) if nd else disp_tl.new_zeros((0, 2))          # [2 * pairs, (num, den)]
+        if group is not None and k:   # the ratios run over the whole data-parallel batch: ONE all-reduce for every pair
+            from .parallel import all_reduce_sum_
+            all_reduce_sum_(nd, group)
+        ratio = (nd[:, 0] / (nd[:, 1] + 1e-8)).view(-1, 2).sum(dim=1) * weight     # :599 / :653, times 0.2 / #pairs
         ctx.frame_of, ctx.bf, ctx.weight, ctx.n_pairs = frame_of, bf, weight, k
-        ctx.save_for_backward(disp_tl, torch.stack(dens) if dens else disp_tl.new_zeros(0), *planes)
-        return tuple(vals)
+        dens = nd[:, 1].repeat_interleave(2) if need else disp_tl.new_zeros(0)     # (A, A, B, B) per pair
+        ctx.save_for_backward(disp_tl, dens, *planes)
+        return tuple(ratio.unbind(0))
 
     @staticmethod
     def backward(ctx, *g_vals):
         disp_tl, dens, *planes = ctx.saved_tensors
         if not planes:
-            return (None,) * (11 + 2 * ctx.n_pairs)
+            return (None,) * (12 + 2 * ctx.n_pairs)
         zero = dens.new_zeros(())
         g = torch.stack([zero if gv is None else gv.reshape(()) for gv in g_vals])       # [pairs]
         scale = (g.repeat_interleave(4) * ctx.weight / (dens + 1e-8)).contiguous()        # one factor per gradient plane
         grad = _ops.geometric_grad_combine(planes, ctx.frame_of, scale, disp_tl, ctx.bf)
-        return (grad,) + (None,) * (10 + 2 * ctx.n_pairs)
+        return (grad,) + (None,) * (11 + 2 * ctx.n_pairs)
 
 
 class _HotPathLoss(torch.nn.Module):
@@ -126,7 +138,9 @@ class _HotPathLoss(torch.nn.Module):
                                                       process_group=process_group)
         self.disparity_loss = DisparitySmoothLoss(process_group=process_group)
         # geometric (flow-consistency) terms are optional: they need the intrinsics and the stereo baseline
-        self.ge_loss = self.ge_class(K, Ki, im_height, im_width, clamp=ge_clamp) if K is not None else None
+        self.process_group = process_group
+        self.ge_loss = (self.ge_class(K, Ki, im_height, im_width, clamp=ge_clamp, process_group=process_group)
+                        if K is not None else None)
         self.d2d = DispToDepth(float(focal_length), float(baseline)) if focal_length is not None else None
 
     def _geometric_terms(self, disp_tl, R, t, amb, flow_out, primary_disp=None):
@@ -142,7 +156,8 @@ class _HotPathLoss(torch.nn.Module):
                 flows += [flow_out[f'flow_{i}{j}'].detach(), flow_out[f'flow_{j}{i}'].detach()]
         clamp = -1.0 if multi_frame else self.ge_loss.clamp        # the multi-frame variant never clamps (:564-601)
         return list(_GeometricTerms.apply(disp_tl, primary_disp.detach() if multi_frame else None, R, t, amb.detach(), K, ray,
-                                          float(clamp), multi_frame, self.d2d.baseline_focal_length, 0.2 / ge_num, *flows))
+                                          float(clamp), multi_frame, self.d2d.baseline_focal_length, 0.2 / ge_num,
+                                          self.process_group, *flows))
 
 
     # ---- fused value + gradient (no autograd graph, no scaling passes) -------------------------------------------------
@@ -195,29 +210,27 @@ class _HotPathLoss(torch.nn.Module):
         else:
             out3, grads = _ops.pattern_loss_multi_forward(disps, im, std_m, ph.pattern, ph.block_size, type_id, ph.loss_eps, True,
                                                           grad_scale=scale)
-        num = out3[:, 0].contiguous()
-        if group is not None:
-            all_reduce_sum_(num, group)
-        vals = list((num / den * w_ph).unbind(0))                      # reference :108-115, weights 1 / 2^s
         # smoothness on scale 0: mean over 2 * N * H * W elements (:118-124)
         per_frame = 2.0 * hw
         s3, _ = _ops.smooth_loss_forward(disps[0], amb.contiguous(), True, grad_scale=self.smooth_weight / (per_frame * n_global),
                                          accumulate_into=grads[0])
-        ssum = s3[0:1].clone()
-        if group is not None:
-            all_reduce_sum_(ssum, group)
-        vals.append(ssum[0] * (self.smooth_weight / (per_frame * n_global)))
+        sums = [out3[:, 0], s3[0:1]]                                   # S photometric numerators, the smoothness sum
+        l1_terms = []
         if l1_target is not None:                                      # pseudo-GT / primary-disparity L1 terms
             tgt = _merge(l1_target).detach()
             for s, wgt in l1_weights:
                 o3, sgn = _ops.l1_forward(disps[s], tgt, True)
-                cnt = o3[1:2].clone()
-                tot = o3[0:1].clone()
-                if group is not None:
-                    all_reduce_sum_(cnt, group)
-                    all_reduce_sum_(tot, group)
-                vals.append(tot[0] / cnt[0] * wgt)
-                grads[s].add_(_ops.scale_by_device_scalar(sgn, torch.full((1,), wgt, device=dev), cnt).view_as(grads[s]))
+                cnt = float(disps[s].numel() // n_local * n_global)    # elements of the whole batch: no reduction needed
+                sums.append(o3[0:1])
+                l1_terms.append(wgt / cnt)
+                grads[s].add_(sgn.view_as(grads[s]), alpha=wgt / cnt)
+        packed = torch.cat(sums)
+        if group is not None:          # every numerator of the step in ONE all-reduced vector (S + 1 + #L1 floats)
+            all_reduce_sum_(packed, group)
+        vals = list((packed[:S] / den * w_ph).unbind(0))              # reference :108-115, weights 1 / 2^s
+        vals.append(packed[S] * (self.smooth_weight / (per_frame * n_global)))
+        for i, f in enumerate(l1_terms):
+            vals.append(packed[S + 1 + i] * f)
         return vals, [g.view_as(o) for g, o in zip(grads, out)]
 
 
@@ -243,7 +256,7 @@ class SingleFrameLoss(_HotPathLoss):
             vals += self._geometric_terms(out[0], R, t, ambient, flow_out)
         if pseudo_gt is not None:                                     # :152-155 (DIS-FTSF)
             for s, o in enumerate(out):
-                vals.append(l1_mean(o, pseudo_gt) * 0.1 / (2 ** s))
+                vals.append(l1_mean(o, pseudo_gt, self.process_group) * 0.1 / (2 ** s))
         if sgm_disp is not None:                                      # :158-163 (warm-up, real data)
             for s, o in enumerate(out):
                 noise = sgm_noise[s] if sgm_noise is not None else 1.5 * torch.randn_like(o)
@@ -272,7 +285,7 @@ class MultiFrameLoss(_HotPathLoss):
         if flow_out is not None:                                      # :128-157 (needs primary_disp)
             vals += self._geometric_terms(out[0], R, t, ambient, flow_out, primary_disp=primary_disp)
         if primary_disp is not None and warmup:                       # :160-165 (first two epochs)
-            vals.append(l1_mean(out[0], primary_disp) * 0.1)
+            vals.append(l1_mean(out[0], primary_disp, self.process_group) * 0.1)
         if sgm_disp is not None:                                      # :167-173 (warm-up on real data, scale 0 only)
             noise = sgm_noise if sgm_noise is not None else 1.5 * torch.randn_like(out[0])
             vals.append(masked_l1_mean(out[0], sgm_disp, noise, 30.0, self.ph_loss.process_group) * 0.1)

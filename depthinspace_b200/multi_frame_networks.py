@@ -2,6 +2,7 @@
 
     warp(x, flow) -> x_prj                                     reference :83-99
     warp_with_fb_mask(flow_ji, flow_ij) -> (flow_ji warped, mask)   reference :202-209 (gather_warped_xyz)
+    resize_like / resize_flow_like / resize_flow_masks_like         reference :42-81
 
 Bilinear resampling with zeros padding and align_corners=True, bit-compatible with the reference's
 normalise -> grid_sample round trip, executed by libdis_b200.so.  Gradients flow to x (and to flow when
@@ -100,6 +101,54 @@ def gather_warped_all(x, flow):
     tl = x.shape[0]
     keys = tuple((i, j) for i in range(tl) for j in range(tl) if i != j)
     return _GatherWarpedAll.apply(x, keys, *[flow[f'flow_{i}{j}'].detach() for (i, j) in keys])
+
+
+def _target_size(target):
+    return (int(target[0]), int(target[1])) if isinstance(target, (tuple, list)) else (target.shape[-2], target.shape[-1])
+
+
+class _ResizeLike(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x4, size):
+        ctx.in_shape = tuple(x4.shape)
+        return _ops.resize_bilinear([x4], size, 0)[0]
+
+    @staticmethod
+    def backward(ctx, g):
+        return _ops.resize_bilinear_backward(g.contiguous(), ctx.in_shape), None
+
+
+def resize_like(x, target):
+    """reference model/multi_frame_networks.py:42-52: bilinear (align_corners=True) resize of the last two dims of x
+    ([..., C, H, W]) to those of `target` (a tensor, or an (h, w) pair)."""
+    size = _target_size(target)
+    lead = x.shape[:-3]
+    out = _ResizeLike.apply(x.contiguous().view(-1, *x.shape[-3:]), size)
+    return out.view(*lead, *out.shape[1:])
+
+
+def resize_flow_like(flow, target):
+    """reference :54-68: every flow of the dict resized to the target size with its x / y channel rescaled by the width /
+    height ratio -- all entries in one launch (the reference: interpolate + 2 in-place multiplies per entry).  A single
+    tensor is accepted too.  Flows are data: no gradient."""
+    size = _target_size(target)
+    with torch.no_grad():
+        if isinstance(flow, dict):
+            keys = list(flow.keys())
+            return dict(zip(keys, _ops.resize_bilinear([flow[k] for k in keys], size, 1)))
+        return _ops.resize_bilinear([flow], size, 1)[0]
+
+
+def resize_flow_masks_like(flow_masks, target):
+    """reference :70-81: (interpolate(mask) > 0.5).float() for every mask of the dict, one launch, threshold fused."""
+    size = _target_size(target)
+    with torch.no_grad():
+        if isinstance(flow_masks, dict):
+            keys = list(flow_masks.keys())
+            return dict(zip(keys, _ops.resize_bilinear([flow_masks[k] for k in keys], size, 2)))
+        lead = flow_masks.shape[:-3]
+        out = _ops.resize_bilinear([flow_masks.contiguous().view(-1, *flow_masks.shape[-3:])], size, 2)[0]
+        return out.view(*lead, *out.shape[1:])
 
 
 class _Conv3DGather(torch.autograd.Function):

@@ -274,7 +274,7 @@ class _FlowConsistency(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, depth0, depth1, R0, t0, R1, t1, flow0, flow1, amb0, amb1, primary0, primary1, K, ray, clamp,
-                multi_frame):
+                multi_frame, group=None):
         ctx.set_materialize_grads(False)
         need0, need1 = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
         # direction A: frame 0 -> 1 (direct gradient to depth0, scatter to depth1); direction B: the mirror image
@@ -284,6 +284,10 @@ class _FlowConsistency(torch.autograd.Function):
         b3, mask1, _, gB1, gB0 = _ops.flow_consistency_dir(depth1, depth0, R1, t1, R0, t0, flow1, flow0, amb1, amb0, K,
                                                            ray, clamp, primary0 if multi_frame else None,
                                                            True, False, need1, need0)
+        if group is not None:      # batch-wide ratios: all-reduce both (numerator, denominator) pairs in one vector
+            nd = torch.stack((a3[:2], b3[:2]))
+            all_reduce_sum_(nd, group)
+            a3, b3 = nd[0], nd[1]
         loss = a3[0] / (a3[1] + 1e-8) + b3[0] / (b3[1] + 1e-8)      # (diff*mask).sum() / (mask.sum() + 1e-8), :599, :653
         ctx.save_for_backward(a3, b3, gA0, gA1, gB0, gB1)
         if orig is None:
@@ -295,19 +299,20 @@ class _FlowConsistency(torch.autograd.Function):
     def backward(ctx, g_loss, *_):
         a3, b3, gA0, gA1, gB0, gB1 = ctx.saved_tensors
         if g_loss is None:
-            return (None,) * 16
+            return (None,) * 17
         g0 = _ops.combine2(gA0, gB0, g_loss, a3[1:2], b3[1:2], 1e-8) if gA0 is not None else None
         g1 = _ops.combine2(gB1, gA1, g_loss, b3[1:2], a3[1:2], 1e-8) if gB1 is not None else None
-        return (g0, g1) + (None,) * 14
+        return (g0, g1) + (None,) * 15
 
 
 class ProjectionBaseLoss(torch.nn.Module):
     """Holds K and the per-pixel rays [u, v, 1] @ Ki^T (computed in float64, stored float32 like the reference,
     model/networks.py:437-453)."""
 
-    def __init__(self, K, Ki, im_height, im_width):
+    def __init__(self, K, Ki, im_height, im_width, process_group=None):
         super().__init__()
         import numpy as np
+        self.process_group = process_group
         self.K = K.reshape(3, 3).to(torch.float32)
         self.im_height, self.im_width = im_height, im_width
         u, v = np.meshgrid(range(im_width), range(im_height))
@@ -321,19 +326,22 @@ class ProjectionBaseLoss(torch.nn.Module):
 
 
 class Single_Frame_Flow_Consistency_Loss(ProjectionBaseLoss):
-    """reference model/networks.py:609-661.  Returns (loss, mask0, mask1, orig_mask) like the reference, except that
+    """reference model/networks.py:609-661.  Returns (loss, mask0, mask1, orig_mask) like the reference.  By default
     orig_mask ([H,W], first sample) stays a device tensor: the reference's blocking `.to('cpu').numpy()` (:640)
-    stalls the stream for a value the worker never uses (single_frame_worker.py:148)."""
+    stalls the stream for a value the worker never uses (single_frame_worker.py:148); numpy_orig_mask=True returns
+    the numpy array of the reference (strict drop-in)."""
 
-    def __init__(self, *args, clamp=-1):
-        super().__init__(*args)
+    def __init__(self, *args, clamp=-1, process_group=None, numpy_orig_mask=False):
+        super().__init__(*args, process_group=process_group)
         self.clamp = clamp
+        self.numpy_orig_mask = numpy_orig_mask   # True: strict drop-in, orig_mask as a host numpy array (:640)
 
     def forward(self, depth0, depth1, R0, t0, R1, t1, flow0, flow1, amb0, amb1):
         K, ray = self._consts(depth0)
         loss, m0, m1, orig = _FlowConsistency.apply(depth0, depth1, R0, t0, R1, t1, flow0, flow1, amb0, amb1, None, None,
-                                                    K, ray, self.clamp, False)
-        return loss, m0, m1, orig[0, 0]
+                                                    K, ray, self.clamp, False, self.process_group)
+        orig = orig[0, 0]
+        return loss, m0, m1, (orig.to('cpu').numpy() if self.numpy_orig_mask else orig)
 
     tforward = forward
 
@@ -341,14 +349,15 @@ class Single_Frame_Flow_Consistency_Loss(ProjectionBaseLoss):
 class Multi_Frame_Flow_Consistency_Loss(ProjectionBaseLoss):
     """reference model/networks.py:554-607 (adds the < 1 px reprojection mask from the primary depths)."""
 
-    def __init__(self, *args, clamp=-1):
-        super().__init__(*args)
+    def __init__(self, *args, clamp=-1, process_group=None):
+        super().__init__(*args, process_group=process_group)
         self.clamp = clamp   # stored but unused, as in the reference's fwd (:564-601)
 
     def forward(self, depth0, depth1, R0, t0, R1, t1, flow0, flow1, amb0, amb1, primary_depth0, primary_depth1):
         K, ray = self._consts(depth0)
         loss, _, _, _ = _FlowConsistency.apply(depth0, depth1, R0, t0, R1, t1, flow0, flow1, amb0, amb1,
-                                               primary_depth0.detach(), primary_depth1.detach(), K, ray, -1.0, True)
+                                               primary_depth0.detach(), primary_depth1.detach(), K, ray, -1.0, True,
+                                               self.process_group)
         return loss
 
     tforward = forward

@@ -2,12 +2,17 @@
 
 Mimics what the reference's renderer produces (data/create_syn_data.py:106-144, 227, 295:
 a board plus a few objects; IR = 0.6 * warped pattern + 0.4 * ambient; sensor noise as in
-data/data_manipulation.py:170-192) without reading any reference asset: the three projector
-patterns (default / kinect / real) are regenerated procedurally as random dot fields whose
-mean intensity matches the remapped 512x432 reference patterns (0.037 / 0.183 / 0.312).
+data/data_manipulation.py:170-192).  At the dataset shape (512x432) the projector patterns are the
+REFERENCE's own default / kinect / real patterns after its read_pattern_file + remap + post_process
+pipeline (tests/golden/patterns_512x432.npz, written by oracle/gen_patterns.py from the reference's
+PNGs; intrinsics K and baseline of each pattern are stored beside them).  For any other shape (the
+reference defines its patterns for 512x432 only) or if the fixture is missing, a procedural random
+dot field with the same mean intensity (0.037 / 0.183 / 0.312) stands in.
 
 Everything is plain numpy on the host, seeded, and shape-parametric.
 """
+import os
+
 import numpy as np
 
 PATTERN_DENSITY = {"default": 0.037, "kinect": 0.183, "real": 0.312}
@@ -21,8 +26,29 @@ def _blur3(a):
             + 4 * p[1:-1, 1:-1]) / 16.0
 
 
+_PATTERN_FILE = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden",
+                             "patterns_512x432.npz")
+_PATTERN_CACHE = {}
+
+
+def reference_pattern(kind):
+    """-> (pattern [512,432] float32, K [3,3], baseline) of the reference, or None when the fixture is absent."""
+    if not _PATTERN_CACHE and os.path.exists(_PATTERN_FILE):
+        with np.load(_PATTERN_FILE) as z:
+            for k in PATTERN_DENSITY:
+                _PATTERN_CACHE[k] = (z[k].astype(np.float32), z[k + "_K"].astype(np.float32), float(z[k + "_baseline"]))
+    return _PATTERN_CACHE.get(kind)
+
+
+def pattern_source(kind="default", hw=DATASET_HW):
+    """'reference' when dot_pattern() returns the reference's remapped pattern, 'procedural' for the stand-in."""
+    return "reference" if tuple(hw) == DATASET_HW and reference_pattern(kind) is not None else "procedural"
+
+
 def dot_pattern(kind="default", hw=DATASET_HW, seed=42):
-    """Projector dot pattern [H,W] float32 in [0,1]."""
+    """Projector dot pattern [H,W] float32 in [0,1]: the reference's at 512x432, a procedural stand-in otherwise."""
+    if pattern_source(kind, hw) == "reference":
+        return reference_pattern(kind)[0].copy()
     rng = np.random.default_rng(seed + sum(map(ord, kind)))
     H, W = hw
     density = PATTERN_DENSITY[kind]

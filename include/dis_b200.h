@@ -241,6 +241,18 @@ DIS_API int dis_geometric_grad_combine(const float* const* planes, const int* fr
                                        const float* scale, const float* disp, float baseline_focal,
                                        float* grad_disp, int tl, int bs, int H, int W, void* stream);
 
+/* ---- (next) resize_like / resize_flow_like / resize_flow_masks_like, model/multi_frame_networks.py:42-81 ----------
+ * Bilinear resize with align_corners=True of `count` tensors [N,C,H,W] -> [N,C,oh,ow] in ONE launch (ins / outs: HOST
+ * arrays of `count` device pointers: the entries of the reference's flow / mask dicts), fused with what follows it:
+ *   mode 0  plain                                             (resize_like, :42-52)
+ *   mode 1  flow: channel 0 *= ow/W, channel 1 *= oh/H; C == 2   (resize_flow_like, :54-68)
+ *   mode 2  mask: out = (value > 0.5) ? 1 : 0                 (resize_flow_masks_like, :70-81; (resize_like(m) > 0.5) :394)
+ * Same arithmetic as ATen's upsample_bilinear2d CUDA kernel.  backward: adjoint of mode 0 w.r.t. the input. */
+DIS_API int dis_resize_bilinear_forward(const float* const* ins, float* const* outs, int count, int N, int C, int H,
+                                        int W, int oh, int ow, int mode, void* stream);
+DIS_API int dis_resize_bilinear_backward(const float* grad_out, float* grad_in, int N, int C, int H, int W, int oh,
+                                         int ow, void* stream);
+
 /* ---- (next) neighbour selection + gather of FuseNet's Conv3D, model/multi_frame_networks.py:469-501 -------
  * xyz [tl,bs,3,h,w], feat [tl,bs,C,h,w], mask [tl,bs,1,h,w] -> for each of the M = bs*oh*ow output pixels
  * (ksize x ksize window, zero padding (ksize-1)/2, given stride) the `neighbors` candidates (of ksize^2*tl <= 64)

@@ -1132,6 +1132,77 @@ def test_conv3d_gather_more_configurations(mods, k, tl, C, stride, hw):
     assert_close(f1.grad, f2.grad, 1e-6, "grad feat")
 
 
+@pytest.mark.parametrize("nb", [4, 12, 16])
+def test_conv3d_gather_neighbour_counts_other_than_nine(mods, nb):
+    """3 x 3 window, 4 frames (the shape of the unrolled ranking kernel) with a neighbour count that is NOT the
+    reference's 9: the generic ranking kernel must be used (the unrolled one hard-codes 9 output slots)."""
+    _, _, mf = mods
+    torch.manual_seed(nb)
+    tl, bs, C, hw = 4, 2, 8, (14, 18)
+    xyz = torch.randn(tl, bs, 3, *hw, device="cuda") * 0.1
+    xyz[:, :, 2] += 1.5
+    feat = torch.randn(tl, bs, C, *hw, device="cuda")
+    mask = torch.ones(tl, bs, 1, *hw, device="cuda")
+    f1, f2 = feat.clone().requires_grad_(True), feat.clone().requires_grad_(True)
+    guard = torch.full((64,), 7.0, device="cuda")            # allocated right behind the outputs: must stay intact
+    xyz_nb, feat_nb, idx = mf.conv3d_gather(xyz, f1, mask, 3, 1, nb)
+    r_xyz, r_feat, r_ind = torch_port.conv3d_gather(xyz, f2, mask, 3, 1, nb)
+    assert xyz_nb.shape == r_xyz.shape and feat_nb.shape == r_feat.shape and idx.shape[1] == nb
+    assert bool((guard == 7.0).all())
+    a_x, a_i = _sort_by_index(xyz_nb, idx)
+    b_x, b_i = _sort_by_index(r_xyz, r_ind.squeeze(-1))
+    a_f, _ = _sort_by_index(feat_nb, idx)
+    b_f, _ = _sort_by_index(r_feat, r_ind.squeeze(-1))
+    same = (a_i == b_i).all(dim=1)                           # zero-padded border candidates tie: any choice is valid
+    assert same.float().mean() > 0.6
+    assert torch.equal(a_x[same], b_x[same]) and torch.equal(a_f[same], b_f[same])
+    wf = torch.randn_like(feat_nb)
+    sel = same.view(-1, 1, 1).float()
+    ga = lambda t, o: torch.gather(t, 1, o.unsqueeze(-1).expand(-1, -1, t.shape[-1]))
+    (ga(feat_nb, torch.argsort(idx.long(), dim=1)) * wf * sel).sum().backward()
+    (ga(r_feat, torch.argsort(r_ind.squeeze(-1), dim=1)) * wf * sel).sum().backward()
+    assert_close(f1.grad, f2.grad, 1e-6, "grad feat")
+
+
+@pytest.mark.parametrize("hw,size", [((512, 432), (256, 216)), ((512, 432), (128, 108)), ((37, 53), (64, 80)), ((20, 30), (20, 30)),
+                                     ((16, 24), (1, 7))])
+def test_resize_ops_match_interpolate(mods, hw, size):
+    """resize_like / resize_flow_like / resize_flow_masks_like (model/multi_frame_networks.py:42-81) against the
+    reference's own composition: F.interpolate(bilinear, align_corners=True) + in-place rescale / threshold."""
+    _, _, mf = mods
+    F = torch.nn.functional
+    torch.manual_seed(hw[0] + size[1])
+    x = torch.randn(2, 3, 5, *hw, device="cuda")                        # [tl, bs, C, H, W]
+    target = torch.empty(1, 1, *size, device="cuda")
+    ref = F.interpolate(x.view(-1, 5, *hw), size=size, mode="bilinear", align_corners=True).view(2, 3, 5, *size)
+    out = mf.resize_like(x, target)
+    err = float((out - ref).abs().max())
+    print(f"resize_like {hw}->{size}: max abs diff vs ATen {err:.3e}, bit-exact {bool(torch.equal(out, ref))}")
+    assert out.shape == ref.shape and err <= 1e-6 * float(ref.abs().max())
+    flows = {f"flow_{i}{j}": 6.0 * torch.randn(3, 2, *hw, device="cuda") for i in range(3) for j in range(3) if i != j}
+    got = mf.resize_flow_like(flows, target)
+    for k, v in flows.items():
+        r = F.interpolate(v, size=size, mode="bilinear", align_corners=True)
+        r[:, 0, :, :] *= float(size[1]) / float(hw[1])
+        r[:, 1, :, :] *= float(size[0]) / float(hw[0])
+        assert got[k].shape == r.shape and float((got[k] - r).abs().max()) <= 1e-6 * float(r.abs().max()), k
+    masks = {k: (torch.rand(3, 1, *hw, device="cuda") > 0.4).float() for k in flows}
+    gotm = mf.resize_flow_masks_like(masks, target)
+    mism = 0.0
+    for k, v in masks.items():
+        r = (F.interpolate(v, size=size, mode="bilinear", align_corners=True) > 0.5).float()
+        mism = max(mism, float((gotm[k] != r).float().mean()))
+    print(f"resize_flow_masks_like {hw}->{size}: mismatching mask pixels {mism:.2e}")
+    assert mism == 0.0, "thresholded masks (integer work) must match bit for bit"
+    # gradient of resize_like w.r.t. its input
+    a = torch.randn(2, 4, *hw, device="cuda", requires_grad=True)
+    b = a.detach().clone().requires_grad_(True)
+    g = torch.randn(2, 4, *size, device="cuda")
+    mf.resize_like(a, size).backward(g)
+    F.interpolate(b, size=size, mode="bilinear", align_corners=True).backward(g)
+    assert_close(a.grad, b.grad, 2e-6, "resize_like grad")
+
+
 def test_sgm_warmup_term_matches_reference_formula(mods):
     """single_frame_worker.py:158-163 with the noise made explicit: value and gradient of every scale."""
     from depthinspace_b200 import losses

@@ -34,7 +34,7 @@ ALL_FRAMES = True
 CONV3D = False
 
 
-def build(bs, dev):
+def build(bs, dev, group=None):
     n = TL * bs
     base = min(n, 8)                      # a few distinct synthetic frames, tiled up to the batch
     fr = synth.make_frames(base, HW, "default", n_scales=1, seed=42)
@@ -57,15 +57,13 @@ def build(bs, dev):
     view = lambda a: a.view(TL, bs, *a.shape[1:])
     pattern = torch.from_numpy(np.repeat(fr["pattern"], 3, axis=1)).to(dev)
     focal, baseline = float(g["K"][0, 0]), 0.075
-    loss = losses.MultiFrameLoss(HW[0], HW[1], pattern, K=K, Ki=Ki, focal_length=focal, baseline=baseline).to(dev)
+    loss = losses.MultiFrameLoss(HW[0], HW[1], pattern, K=K, Ki=Ki, focal_length=focal, baseline=baseline,
+                                 process_group=group).to(dev)
     lcn = networks.LCN(5, 0.05).to(dev)
-    feats, flows_lr, grads, grads_all = [], [], [], []
+    feats, grads, grads_all = [], [], []
     gen = torch.Generator(device=dev).manual_seed(0)
     for (h, w) in FEAT:
         feats.append(torch.randn(TL, bs, C_FEAT, h, w, device=dev, generator=gen).requires_grad_(True))
-        sc = h / HW[0]
-        flows_lr.append({k: torch.nn.functional.interpolate(v, size=(h, w), mode="bilinear", align_corners=True) * sc
-                         for k, v in flow.items()})
         grads.append(torch.randn(TL, bs, C_FEAT, h, w, device=dev, generator=gen))
         grads_all.append(grads[-1][None].expand(TL, -1, -1, -1, -1, -1).contiguous())
     xyz = torch.randn(TL, bs, 3, *FEAT[0], device=dev, generator=gen)
@@ -82,7 +80,13 @@ def build(bs, dev):
             g_nb.append(torch.randn(bs * h * w, 9, C_FEAT, device=dev, generator=gen))
     im_bt = view(im).transpose(0, 1).contiguous()      # the DataLoader hands frames over as [bs, tl, 1, H, W]
     return dict(im=view(im), im_bt=im_bt, amb=view(amb), disp=view(disp), prim=view(dgt + 0.3), R=R, t=t, flow=flow, loss=loss, lcn=lcn,
-                feats=feats, flows_lr=flows_lr, grads=grads, grads_all=grads_all, xyz=xyz, bs=bs, xyz_lvl=xyz_lvl, mask_lvl=mask_lvl, g_nb=g_nb)
+                feats=feats, grads=grads, grads_all=grads_all, xyz=xyz, bs=bs, xyz_lvl=xyz_lvl, mask_lvl=mask_lvl, g_nb=g_nb)
+
+
+def resize_flows(w):
+    """FuseNet's resize_flow_like (multi_frame_networks.py:58-72) for the two feature resolutions: every step gets the
+    flows at full resolution from the data loader and needs them at 256x216 and 128x108."""
+    return [mfn.resize_flow_like(w["flow"], size) for size in FEAT]
 
 
 class Sections:
@@ -114,6 +118,8 @@ def step(w):
     im_cat, std = w["lcn"].prepare_input(w["im_bt"])
     SEC.mark("copy_data_ms")
     # ---- FuseNet warps
+    w["flows_lr"] = resize_flows(w)
+    SEC.mark("resize_flows_ms")
     with torch.no_grad():
         for tidx in range(TL):
             mfn.gather_warped(w["xyz"], w["flows_lr"][0], tidx, with_fb_mask=True)          # 12 xyz + 12 flow warps
@@ -168,7 +174,7 @@ def build_sf(bs, dev):
     K = torch.from_numpy(g["K"].astype(np.float64))
     w["loss"] = losses.SingleFrameLoss(HW[0], HW[1], pattern, K=K, Ki=torch.linalg.inv(K), focal_length=float(g["K"][0, 0]),
                                        baseline=0.075).to(dev)
-    for k in ("feats", "flows_lr", "grads", "grads_all", "xyz", "xyz_lvl", "mask_lvl", "g_nb"):
+    for k in ("feats", "grads", "grads_all", "xyz", "xyz_lvl", "mask_lvl", "g_nb"):
         w.pop(k)
     return w
 
@@ -183,6 +189,151 @@ def step_sf(w):
     total.backward()
     SEC.mark("loss_ms")
     return total
+
+
+WARP_BYTES_PER_FRAME = 657e6   # warp traffic of one FuseNet fwd + recompute + bwd per frame
+
+
+def cpu_step(threads):
+    """The same hot path for ONE track (bs 1, 4 frames) with the oracle's torch port on the host cores (the reference's
+    op sequence: LCN, warp() per neighbour + torch.stack, unfold-based photometric loss, flow-consistency modules)."""
+    import time
+    from oracle import torch_port as tp
+    torch.set_num_threads(threads)
+    w = build(1, torch.device("cpu"))
+    t0 = time.perf_counter()
+    im = w["im"].reshape(TL, 1, *HW)
+    im_l, im_s = tp.lcn(im)
+    fl_lr = [{k: torch.nn.functional.interpolate(v, size=size, mode="bilinear", align_corners=True) * (size[0] / HW[0])
+              for k, v in w["flow"].items()} for size in FEAT]
+    with torch.no_grad():
+        for t in range(TL):
+            for j in range(TL):
+                if j != t:
+                    tp.flow_warp(w["xyz"][j], fl_lr[0][f"flow_{t}{j}"])
+                    tp.fb_mask(fl_lr[0][f"flow_{t}{j}"], tp.flow_warp(fl_lr[0][f"flow_{j}{t}"], fl_lr[0][f"flow_{t}{j}"]))
+    for lvl in range(2):
+        x = w["feats"][lvl]
+        x.grad = None
+        for _ in range(BLOCKS):
+            for t in range(TL):
+                def gather():
+                    return torch.stack([x[t]] + [tp.flow_warp(x[j], fl_lr[lvl][f"flow_{t}{j}"]) for j in range(TL) if j != t])
+                with torch.no_grad():
+                    gather()                                   # checkpointed forward
+                gather().backward(w["grads"][lvl])            # recompute + backward
+    disp = w["disp"].detach().reshape(TL, 1, *HW).requires_grad_(True)
+    pat = w["loss"].ph_loss.pattern
+    vals = tp.multi_frame_loss(disp, im_l, im_s, w["amb"].reshape(TL, 1, *HW), pat, chunk=1, primary_disp=w["prim"].reshape(TL, 1, *HW))
+    g = synth.make_geometry(1, HW, seed=5)
+    K = torch.from_numpy(g["K"])
+    fc = tp.FlowConsistency(K, torch.linalg.inv(K.double()).float(), HW[0], HW[1], multi_frame=True)
+    depth = tp.disp_to_depth(disp.view(TL, 1, 1, *HW), float(g["K"][0, 0]), 0.075)
+    prim = tp.disp_to_depth(w["prim"], float(g["K"][0, 0]), 0.075)
+    for i in range(TL):
+        for j in range(i + 1, TL):
+            vals.append(fc(depth[i], depth[j], w["R"][i], w["t"][i], w["R"][j], w["t"][j], w["flow"][f"flow_{i}{j}"], w["flow"][f"flow_{j}{i}"],
+                           w["amb"][i], w["amb"][j], prim[i], prim[j]) * 0.2 / 6)
+    sum(vals).backward()
+    return time.perf_counter() - t0
+
+
+def measure(bs, dev, group, world, steps, peak_gbs, sync_all, cpu_leg):
+    """DIS-MF numbers for bench.py: `bs` samples on this rank (BASELINE configs[2]: 32 in total), frames/s over all ranks
+    (max over ranks of the device time), the dominant kernel against the HBM roofline, the end-to-end leg and (one GPU
+    only) the CPU leg."""
+    import time
+    import torch.distributed as dist
+    from depthinspace_b200 import _ops
+    w = build(bs, dev, group)
+    for _ in range(3):
+        step(w)
+    sync_all()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    SEC.marks, SEC.on = [], True
+    e0.record()
+    for _ in range(steps):
+        total = step(w)
+    e1.record()
+    sync_all()
+    SEC.on = False
+    ms = e0.elapsed_time(e1)
+    sections = SEC.summary(steps)
+    # dominant kernel alone: backward of the all-frames feature gather at 256x216, C = 32
+    h, wd = FEAT[0]
+    g = w["grads_all"][0]
+    fl = {(i, j): w["flows_lr"][0][f"flow_{i}{j}"] for i in range(TL) for j in range(TL) if i != j}
+    for _ in range(3):
+        _ops.flow_warp_gather_all_backward(fl, g)
+    k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    k0.record()
+    for _ in range(10):
+        _ops.flow_warp_gather_all_backward(fl, g)
+    k1.record()
+    torch.cuda.synchronize()
+    k_ms = k0.elapsed_time(k1) / 10
+    k_bytes = (TL * TL * C_FEAT + TL * (TL - 1) * 2 + TL * C_FEAT) * 4 * h * wd * bs
+    # end to end: the step's data-loader inputs come from pinned host memory every step, the loss goes back
+    keys = ("im_bt", "amb", "disp", "prim", "R", "t")
+    host = {k: w[k].cpu().pin_memory() for k in keys}
+    host_flow = {k: v.cpu().pin_memory() for k, v in w["flow"].items()}
+    h2d = sum(v.numel() * 4 for v in host.values()) + sum(v.numel() * 4 for v in host_flow.values())
+    side = torch.cuda.Stream()
+
+    def upload():
+        with torch.cuda.stream(side):
+            bufs = ({k: v.to(dev, non_blocking=True) for k, v in host.items()}, {k: v.to(dev, non_blocking=True) for k, v in host_flow.items()})
+            ev = torch.cuda.Event()
+            ev.record(side)
+        return bufs, ev
+
+    def run(k):
+        nxt = upload()
+        out = []
+        for i in range(k):
+            (b, f), ev = nxt
+            torch.cuda.current_stream().wait_event(ev)
+            if i + 1 < k:
+                nxt = upload()
+            for t in list(b.values()) + list(f.values()):
+                t.record_stream(torch.cuda.current_stream())
+            w.update(b)
+            w["flow"] = f
+            out.append(float(step(w).detach()))
+        return out
+    run(2)
+    sync_all()
+    t0 = time.perf_counter()
+    run(steps)
+    sync_all()
+    e2e_s = time.perf_counter() - t0
+    times = torch.tensor([ms, e2e_s * 1e3, k_ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(times, op=dist.ReduceOp.MAX)
+    ms, e2e_ms, k_ms = times.tolist()
+    frames = TL * bs * world
+    value = frames * steps / (ms * 1e-3)
+    line = {"value": value, "unit": "frames/s", "ms_per_step": ms / steps, "frames_per_step": frames, "samples_per_gpu": bs, "scaling": "strong",
+            "e2e": {"value": frames * steps / (e2e_ms * 1e-3), "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
+            "sections_ms": sections,
+            "roofline": {"bound": "hbm", "kernel": "flow_warp_gather_all_bwd_kernel (tl 4, C 32, 256x216)", "kernel_ms": k_ms,
+                         "algorithmic_bytes": k_bytes, "achieved": k_bytes / (k_ms * 1e-3) / 1e9, "peak": peak_gbs, "unit": "GB/s",
+                         "frac": k_bytes / (k_ms * 1e-3) / 1e9 / peak_gbs,
+                         "step_algorithmic_gbs": WARP_BYTES_PER_FRAME * (value / world) / 1e9,
+                         "step_frac": WARP_BYTES_PER_FRAME * (value / world) / 1e9 / peak_gbs,
+                         "limiter": "L2 reduction path of the feature-gradient scatter (RED.ADD), see DESIGN.md"},
+            "workload": "BASELINE configs[2]: DIS-MF hot path, bs 32 in total x tl 4 (copy_data LCN, flow resize to 2 levels, 24 xyz/flow + 96 C=32 "
+                        "feature warps fwd/recompute/bwd, 1-scale census_sad + smoothness + 12 flow-consistency terms + L1), see tools/bench_mf.py",
+            "loss": float(total.detach())}
+    del w
+    torch.cuda.empty_cache()
+    if cpu_leg:
+        threads = os.cpu_count() or 1
+        t = cpu_step(threads)
+        line["cpu_baseline"] = {"value": TL / t, "unit": "frames/s", "cores": threads, "kind": "port",
+                                "sample": "1 track (4 frames) of the 32, 1 pass, oracle torch port, all host threads"}
+    return line
 
 
 def main():
