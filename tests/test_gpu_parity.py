@@ -700,6 +700,45 @@ def test_gather_warped_all_equals_per_frame_gathers(mods, tl, C, hw):
     assert_close(x.grad, xr.grad, 2e-6, "gradient of the all-frames gather")
 
 
+@pytest.mark.parametrize("kind", ["large", "fold", "zero", "nonfinite"])
+def test_gather_warped_all_backward_tile_gather_special_flows(mods, kind):
+    """The experimental tile-local gather backward (DIS_GATHER_BWD=tile) against the default RED.ADD scatter kernels: flows
+    far larger than the tile halo (second launch), a fold that lands > 8 pixels in one cell (tile falls back to local
+    reductions), integer flows (zero weights skipped) and non-finite flows (sampled nowhere)."""
+    from depthinspace_b200 import _ops
+    tl, bs, C, hw = 3, 2, 6, (40, 70)
+    torch.manual_seed(7)
+    flows = {}
+    for i in range(tl):
+        for j in range(tl):
+            if i == j:
+                continue
+            f = dev(synth.make_flows(bs, hw, max_mag=3.0, seed=5 * i + j)[0])
+            if kind == "large":
+                f = f * 9.0                                              # up to ~27 px
+            elif kind == "fold":
+                u = torch.arange(hw[1], device="cuda", dtype=torch.float32).view(1, 1, -1)
+                f[:, 0] = -0.93 * (u - 20.0) + 0.3                       # 14x compression of the columns onto x ~ 20
+                f[:, 1] = 0.25
+            elif kind == "zero":
+                f = torch.round(f)
+            elif kind == "nonfinite":
+                f[0, 0, 3:6, 4:9] = float("nan")
+                f[1, 1, 10, :] = float("inf")
+            flows[(i, j)] = f.contiguous()
+    go = torch.randn(tl, tl, bs, C, *hw, device="cuda")
+    ref = _ops.flow_warp_gather_all_backward(flows, go)           # default: RED.ADD scatter kernels
+    os.environ["DIS_GATHER_BWD"] = "tile"
+    try:
+        got = _ops.flow_warp_gather_all_backward(flows, go)
+    finally:
+        del os.environ["DIS_GATHER_BWD"]
+    assert torch.isfinite(got).all()
+    err = float((got - ref).abs().max() / ref.abs().max())
+    print(f"tile gather backward [{kind}]: max rel deviation from the scatter kernels {err:.2e}")
+    assert err <= 2e-6
+
+
 def test_gather_warped_rejects_bad_arguments(mods):
     from depthinspace_b200 import _ops
     x = torch.randn(3, 1, 2, 8, 9, device="cuda")
