@@ -54,6 +54,10 @@ SIGNATURES = {
     "dis_flow_consistency_num_partials": [_i, _i, _i],
     "dis_flow_consistency_forward": [_f] * 10 + [_i, _f, _f, _f, _fl, _fl, _f, _f, _f, _f, _f, _i, _i, _i, _st],
     "dis_geometric_grad_combine": [_c.POINTER(_c.c_void_p), _c.POINTER(_c.c_int), _i, _f, _f, _fl, _f, _i, _i, _i, _i, _st],
+    "dis_ext_nn": [_f, _f, _f, _c.c_int64, _c.c_int64, _i, _st],
+    "dis_ext_crosscheck": [_f, _f, _f, _c.c_int64, _c.c_int64, _st],
+    "dis_ext_proj_nn": [_f, _f, _f, _f, _i, _i, _i, _i, _st],
+    "dis_ext_xcorrvol": [_f, _f, _f, _i, _i, _i, _i, _i, _st],
     "dis_resize_bilinear_forward": [_c.POINTER(_c.c_void_p), _c.POINTER(_c.c_void_p), _i, _i, _i, _i, _i, _i, _i, _i, _st],
     "dis_resize_bilinear_backward": [_f, _f, _i, _i, _i, _i, _i, _i, _st],
     "dis_conv3d_out_size": [_i, _i, _i],

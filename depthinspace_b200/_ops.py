@@ -393,6 +393,58 @@ def flow_warp_gather_all_backward(flows, grad_out):
     return gx
 
 
+def _chk_long(t, name):
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise RuntimeError(f"{name} must be a CUDA tensor: depthinspace_b200 has no CPU path")
+    if t.dtype != torch.int64:
+        raise TypeError(f"{name} must be int64, got {t.dtype}")
+    return t.contiguous()
+
+
+def ext_nn(in0, in1):
+    """ext_cuda.nn_cuda (reference model/ext_functions.py:46): in0 [n0,D], in1 [n1,D] -> int64 [n0] nearest row of in1."""
+    in0, in1 = _chk(in0, "in0", 2), _chk(in1, "in1", 2)
+    if in0.shape[1] != in1.shape[1]:
+        raise ValueError("in0 and in1 must have the same number of columns")
+    out = torch.empty(in0.shape[0], dtype=torch.int64, device=in0.device)
+    with _on(in0) as lib:
+        _lib.check(lib.dis_ext_nn(_ptr(in0), _ptr(in1), out.data_ptr(), in0.shape[0], in1.shape[0], in0.shape[1], _stream(in0)))
+    return out
+
+
+def ext_crosscheck(in0, in1):
+    """ext_cuda.crosscheck_cuda (:64): in0 int64 [n0] -> in1, in1 int64 [n1] -> in0; uint8 [n0] = (in1[in0[i]] == i)."""
+    in0, in1 = _chk_long(in0, "in0"), _chk_long(in1, "in1")
+    out = torch.empty(in0.numel(), dtype=torch.uint8, device=in0.device)
+    with _on(in0) as lib:
+        _lib.check(lib.dis_ext_crosscheck(in0.data_ptr(), in1.data_ptr(), out.data_ptr(), in0.numel(), in1.numel(), _stream(in0)))
+    return out.view(in0.shape)
+
+
+def ext_proj_nn(xyz0, xyz1, K, patch_size):
+    """ext_cuda.proj_nn_cuda (:81): xyz0, xyz1 [bs,H,W,3], K [3,3] -> int64 [bs,H,W] (flat index into xyz1 or -1)."""
+    xyz0, xyz1, K = _chk(xyz0, "xyz0"), _chk(xyz1, "xyz1"), _chk(K, "K", 2)
+    bs, H, W, three = xyz0.shape
+    if three != 3 or xyz1.shape != xyz0.shape or tuple(K.shape) != (3, 3):
+        raise ValueError("xyz0, xyz1 must be [bs,H,W,3] with equal shapes and K [3,3]")
+    out = torch.empty((bs, H, W), dtype=torch.int64, device=xyz0.device)
+    with _on(xyz0) as lib:
+        _lib.check(lib.dis_ext_proj_nn(_ptr(xyz0), _ptr(xyz1), _ptr(K), out.data_ptr(), bs, H, W, int(patch_size), _stream(xyz0)))
+    return out
+
+
+def ext_xcorrvol(in0, in1, n_disps, block_size):
+    """ext_cuda.xcorrvol_cuda (:100): in0, in1 [C,H,W] -> [n_disps,H,W] zero-normalised block cross correlation."""
+    in0, in1 = _chk(in0, "in0", 3), _chk(in1, "in1", 3)
+    if in0.shape != in1.shape:
+        raise ValueError("in0 and in1 must have equal shapes")
+    C, H, W = in0.shape
+    out = torch.empty((int(n_disps), H, W), dtype=torch.float32, device=in0.device)
+    with _on(in0) as lib:
+        _lib.check(lib.dis_ext_xcorrvol(_ptr(in0), _ptr(in1), _ptr(out), C, H, W, int(n_disps), int(block_size), _stream(in0)))
+    return out
+
+
 def resize_bilinear(tensors, size, mode=0):
     """Bilinear align_corners=True resize of a list of equally shaped [N,C,H,W] tensors to `size` in one launch.
     mode 0 plain, 1 flow (x / y channel rescaled by the size ratio), 2 mask (> 0.5 -> 1 / 0).  -> list of outputs"""

@@ -50,6 +50,11 @@ int geometric_grad_combine(const float* const*, const int*, int, const float*, c
 int resize_bilinear_forward(const float* const*, float* const*, int, int, int, int, int, int, int, int, cudaStream_t);
 int resize_bilinear_backward(const float*, float*, int, int, int, int, int, int, cudaStream_t);
 
+int ext_nn(const float*, const float*, long long*, long, long, int, cudaStream_t);
+int ext_crosscheck(const long long*, const long long*, uint8_t*, long, long, cudaStream_t);
+int ext_proj_nn(const float*, const float*, const float*, long long*, int, int, int, int, cudaStream_t);
+int ext_xcorrvol(const float*, const float*, float*, int, int, int, int, int, cudaStream_t);
+
 int conv3d_out_size(int, int, int);
 size_t conv3d_scratch_elems(int, int, int, int);
 int conv3d_gather_forward(const float*, const float*, const float*, float*, float*, uint8_t*, float*, int, int, int, int,
@@ -200,6 +205,37 @@ using namespace dis;
 extern "C" {
 
 int dis_abi_version(void) { return 3; }
+
+int dis_ext_nn(const float* in0, const float* in1, int64_t* out, int64_t n0, int64_t n1, int dim, void* stream) {
+  if (n0 < 0 || n1 < 0 || (n0 + 255) / 256 > INT_MAX) return DIS_ERR_BAD_SHAPE;
+  if (n0 == 0) return DIS_OK;
+  if (!in0 || !out || (n1 > 0 && !in1)) return DIS_ERR_NULL_POINTER;
+  return ext_nn(in0, in1, reinterpret_cast<long long*>(out), (long)n0, (long)n1, dim, as_stream(stream));
+}
+
+int dis_ext_crosscheck(const int64_t* in0, const int64_t* in1, uint8_t* out, int64_t n0, int64_t n1, void* stream) {
+  if (n0 < 0 || n1 < 0 || (n0 + 255) / 256 > INT_MAX) return DIS_ERR_BAD_SHAPE;
+  if (n0 == 0) return DIS_OK;
+  if (!in0 || !out || (n1 > 0 && !in1)) return DIS_ERR_NULL_POINTER;
+  return ext_crosscheck(reinterpret_cast<const long long*>(in0), reinterpret_cast<const long long*>(in1), out, (long)n0,
+                        (long)n1, as_stream(stream));
+}
+
+int dis_ext_proj_nn(const float* xyz0, const float* xyz1, const float* K, int64_t* out, int bs, int H, int W,
+                    int patch_size, void* stream) {
+  if (bs < 0 || H < 1 || W < 1 || patch_size < 1 || patch_size > 255) return DIS_ERR_BAD_SHAPE;
+  if (bs == 0) return DIS_OK;
+  if (!xyz0 || !xyz1 || !K || !out) return DIS_ERR_NULL_POINTER;
+  return ext_proj_nn(xyz0, xyz1, K, reinterpret_cast<long long*>(out), bs, H, W, patch_size, as_stream(stream));
+}
+
+int dis_ext_xcorrvol(const float* in0, const float* in1, float* out, int C, int H, int W, int n_disps, int block_size,
+                     void* stream) {
+  if (C < 1 || H < 1 || W < 1 || n_disps < 0 || block_size < 1 || block_size > 255) return DIS_ERR_BAD_SHAPE;
+  if (n_disps == 0) return DIS_OK;
+  if (!in0 || !in1 || !out) return DIS_ERR_NULL_POINTER;
+  return ext_xcorrvol(in0, in1, out, C, H, W, n_disps, block_size, as_stream(stream));
+}
 
 int dis_resize_bilinear_forward(const float* const* ins, float* const* outs, int count, int N, int C, int H, int W, int oh,
                                 int ow, int mode, void* stream) {

@@ -241,6 +241,20 @@ DIS_API int dis_geometric_grad_combine(const float* const* planes, const int* fr
                                        const float* scale, const float* disp, float baseline_focal,
                                        float* grad_disp, int tl, int bs, int H, int W, void* stream);
 
+/* ---- (next) the ext ops the reference wraps but never calls, model/ext_functions.py:41-110 ----------------------
+ * Replace ext_cuda.nn_cuda (:46), crosscheck_cuda (:64), proj_nn_cuda (:81), xcorrvol_cuda (:100).  Their definitions
+ * live in the un-vendored Connecting-the-Dots torchext: PARITY UNPINNED (semantics in csrc/ext_misc.cu).
+ *   nn:         in0 [n0,dim], in1 [n1,dim] (dim <= 8) -> out int64 [n0], index of the nearest row of in1 (-1 if n1 == 0)
+ *   crosscheck: in0 int64 [n0] (indices into in1), in1 int64 [n1] -> out uint8 [n0] = (in1[in0[i]] == i)
+ *   proj_nn:    xyz0, xyz1 [bs,H,W,3], K [3,3] row-major -> out int64 [bs,H,W], flat index into xyz1's points or -1
+ *   xcorrvol:   in0, in1 [C,H,W] -> out [n_disps,H,W] */
+DIS_API int dis_ext_nn(const float* in0, const float* in1, int64_t* out, int64_t n0, int64_t n1, int dim, void* stream);
+DIS_API int dis_ext_crosscheck(const int64_t* in0, const int64_t* in1, uint8_t* out, int64_t n0, int64_t n1, void* stream);
+DIS_API int dis_ext_proj_nn(const float* xyz0, const float* xyz1, const float* K, int64_t* out, int bs, int H, int W,
+                            int patch_size, void* stream);
+DIS_API int dis_ext_xcorrvol(const float* in0, const float* in1, float* out, int C, int H, int W, int n_disps,
+                             int block_size, void* stream);
+
 /* ---- (next) resize_like / resize_flow_like / resize_flow_masks_like, model/multi_frame_networks.py:42-81 ----------
  * Bilinear resize with align_corners=True of `count` tensors [N,C,H,W] -> [N,C,oh,ow] in ONE launch (ins / outs: HOST
  * arrays of `count` device pointers: the entries of the reference's flow / mask dicts), fused with what follows it:

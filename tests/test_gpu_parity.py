@@ -110,6 +110,96 @@ def test_photometric_reference_dropin_module_path(mods):
         ext_cuda.photometric_loss_forward(es, ta, 9, 5, 0.5)
 
 
+def test_unmodified_reference_boundary_runs_on_our_ext_cuda(mods):
+    """SURVEY 7.2 minimum slice: the reference's OWN model/ext_functions.py (unmodified copy placed under oracle/_ref/dropin
+    by __graft_entry__.build(), with config.json's CTD_DIR pointing at depthinspace_b200) resolves `import ext_cuda` to our
+    stand-in and runs PhotometricLossFunction forward + backward on libdis_b200.so."""
+    import importlib.util
+    import json
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    drop = os.path.join(root, "oracle", "_ref", "dropin")
+    path = os.path.join(drop, "model", "ext_functions.py")
+    if not os.path.isfile(path):
+        pytest.skip("oracle/_ref/dropin not installed (run __graft_entry__.build() where /root/reference exists)")
+    with open(os.path.join(drop, "config.json"), "w") as f:
+        json.dump({"CTD_DIR": os.path.join(root, "depthinspace_b200")}, f)
+    for name in ("ext_cpu", "ext_cuda"):
+        sys.modules.pop(name, None)
+    spec = importlib.util.spec_from_file_location("reference_ext_functions", path)
+    ref = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ref)
+    assert os.path.realpath(ref.ext_cuda.__file__).startswith(os.path.realpath(os.path.join(root, "depthinspace_b200", "torchext")))
+    torch.manual_seed(3)
+    es = torch.randn(2, 1, 45, 52, device="cuda", requires_grad=True)
+    ta = torch.randn(2, 1, 45, 52, device="cuda")
+    for t in TYPES:
+        es.grad = None
+        out = ref.photometric_loss(es, ta, 9, t, 0.5)              # the reference's wrapper and autograd.Function
+        go = torch.rand_like(out)
+        out.backward(go)
+        tid = c_oracle.TYPES[t]
+        assert_close(out, c_oracle.photometric_forward(to_np(es), to_np(ta), 9, tid, 0.5, "f64"), name=f"fwd {t}")
+        assert_close(es.grad, c_oracle.photometric_backward(to_np(es), to_np(ta), to_np(go), 9, tid, 0.5, "f64"), name=f"bwd {t}",
+                     outlier_frac=1e-4 if "sad" in t else 0)
+    with pytest.raises(Exception, match="invalid loss type"):
+        ref.photometric_loss(es, ta, 9, "ssim", 0.5)
+
+
+# ----------------------------------------------------------------------------- ext ops without callers (f4)
+def test_dead_ext_ops_against_brute_force(mods):
+    """nn / crosscheck / proj_nn / xcorrvol (model/ext_functions.py:41-110).  PARITY UNPINNED: the reference never calls
+    them and their definition lives in the un-vendored CTD torchext; checked against brute-force torch restatements of
+    that project's published functors.  Integer outputs bit-exact."""
+    _, ext, _ = mods
+    torch.manual_seed(0)
+    a, b = torch.randn(700, 3, device="cuda"), torch.randn(900, 3, device="cuda")
+    idx = ext.nn(a, b)
+    ref = torch.cdist(a.double(), b.double()).argmin(dim=1)
+    assert idx.dtype == torch.int64 and torch.equal(idx, ref)
+    back = ext.nn(b, a)
+    cc = ext.crosscheck(idx, back)
+    assert cc.dtype == torch.uint8 and torch.equal(cc.bool(), back[idx] == torch.arange(700, device="cuda"))
+    # proj_nn: organised point clouds, pinhole K
+    bs, H, W, patch = 2, 24, 30, 5
+    K = torch.tensor([[40.0, 0, 14.5], [0, 40.0, 11.5], [0, 0, 1]], device="cuda")
+    v, u = torch.meshgrid(torch.arange(H, device="cuda", dtype=torch.float32), torch.arange(W, device="cuda", dtype=torch.float32), indexing="ij")
+    z1 = 1.5 + 0.2 * torch.rand(bs, H, W, device="cuda")
+    xyz1 = torch.stack(((u - 14.5) / 40 * z1, (v - 11.5) / 40 * z1, z1), dim=-1).contiguous()
+    xyz0 = (xyz1 + 0.02 * torch.randn_like(xyz1)).contiguous()
+    got = ext.proj_nn(xyz0, xyz1, K, patch)
+    p = xyz0 @ K.t()
+    u0 = (p[..., 0] / p[..., 2] + 0.5).to(torch.int32)
+    v0 = (p[..., 1] / p[..., 2] + 0.5).to(torch.int32)
+    want = torch.full((bs, H, W), -1, dtype=torch.int64, device="cuda")
+    best = torch.full((bs, H, W), 1e9, device="cuda")
+    bidx = torch.arange(bs, device="cuda").view(bs, 1, 1).expand(bs, H, W)
+    for pv in range(patch):
+        for pu in range(patch):
+            u1, v1 = u0 + pu - patch // 2, v0 + pv - patch // 2
+            ok = (u1 >= 0) & (v1 >= 0) & (u1 < W) & (v1 < H)
+            j = (bidx * H + v1.clamp(0, H - 1)) * W + u1.clamp(0, W - 1)
+            d = ((xyz0 - xyz1.view(-1, 3)[j]) ** 2).sum(-1)
+            better = ok & (d < best)
+            best = torch.where(better, d, best)
+            want = torch.where(better, j, want)
+    assert got.dtype == torch.int64
+    assert float((got != want).float().mean()) < 1e-3        # (fp32 summation order of the distance may flip exact ties)
+    # xcorrvol
+    C, n_disps, blk = 2, 6, 5
+    i0, i1 = torch.randn(C, H, W, device="cuda"), torch.randn(C, H, W, device="cuda")
+    vol = ext.xcorrvol(i0, i1, n_disps, blk)
+    hh = (torch.arange(H, device="cuda").view(H, 1, 1, 1) + torch.arange(blk, device="cuda").view(1, 1, blk, 1) - blk // 2).clamp(0, H - 1)
+    ww = torch.arange(W, device="cuda").view(1, W, 1, 1) + torch.arange(blk, device="cuda").view(1, 1, 1, blk) - blk // 2
+    refv = torch.zeros(n_disps, H, W, device="cuda", dtype=torch.float64)
+    for d in range(n_disps):
+        p0 = i0.double()[:, hh, ww.clamp(0, W - 1)]                    # [C,H,W,blk,blk]
+        p1 = i1.double()[:, hh, (ww - d).clamp(0, W - 1)]
+        p0 = p0 - p0.mean(dim=(-1, -2), keepdim=True)
+        p1 = p1 - p1.mean(dim=(-1, -2), keepdim=True)
+        refv[d] = ((p0 * p1).sum((-1, -2)) / (torch.sqrt((p0 * p0).sum((-1, -2)) * (p1 * p1).sum((-1, -2))) + 1e-8)).sum(0)
+    assert_close(vol, refv, 1e-5, "xcorrvol")
+
+
 @pytest.mark.parametrize("t", TYPES)
 def test_photometric_vs_torch_cuda_port_dataset_shape(mods, t):
     """512x432 (the dataset's frame shape) against the reference's formula run by torch on the GPU."""
