@@ -10,7 +10,7 @@ import numpy as np
 import pytest
 import torch
 
-from helpers import assert_close, assert_scalar_close, to_np
+from helpers import assert_close, assert_mismatch_frac, assert_scalar_close, to_np
 from depthinspace_b200 import synth
 from oracle import c_oracle, torch_port
 
@@ -45,7 +45,7 @@ def test_photometric_vs_c_oracle(mods, t, k):
     ref_out = c_oracle.photometric_forward(es, ta, k, tid, 0.5, "f64")
     ref_grad = c_oracle.photometric_backward(es, ta, go, k, tid, 0.5, "f64")
     assert_close(out, ref_out, name=f"fwd {t} k={k}")
-    assert_close(e.grad, ref_grad, name=f"bwd {t} k={k}", outlier_frac=SIGN_OUTLIERS if t in ("sad", "census_sad") else 0)
+    assert_close(e.grad, ref_grad, name=f"bwd {t} k={k}", outlier_frac=0)
 
 
 @pytest.mark.parametrize("t", TYPES)
@@ -62,7 +62,7 @@ def test_photometric_edge_shapes(mods, t, shape):
     tid = c_oracle.TYPES[t]
     assert_close(out, c_oracle.photometric_forward(es, ta, 9, tid, 0.1, "f64"), name="fwd")
     assert_close(e.grad, c_oracle.photometric_backward(es, ta, go, 9, tid, 0.1, "f64"), name="bwd",
-                 outlier_frac=1e-3 if t in ("sad", "census_sad") else 0)
+                 outlier_frac=0)
 
 
 @pytest.mark.parametrize("case", ["k9", "k5c2", "k3"])
@@ -105,7 +105,7 @@ def test_photometric_reference_dropin_module_path(mods):
     go = torch.rand_like(out)
     grad = ext_cuda.photometric_loss_backward(es, ta, go, 9, 3, 0.5)
     assert_close(out, c_oracle.photometric_forward(to_np(es), to_np(ta), 9, 3, 0.5, "f64"))
-    assert_close(grad, c_oracle.photometric_backward(to_np(es), to_np(ta), to_np(go), 9, 3, 0.5, "f64"), outlier_frac=1e-4)
+    assert_close(grad, c_oracle.photometric_backward(to_np(es), to_np(ta), to_np(go), 9, 3, 0.5, "f64"), outlier_frac=0)
     with pytest.raises(Exception, match="invalid loss type"):
         ext_cuda.photometric_loss_forward(es, ta, 9, 5, 0.5)
 
@@ -140,7 +140,7 @@ def test_unmodified_reference_boundary_runs_on_our_ext_cuda(mods):
         tid = c_oracle.TYPES[t]
         assert_close(out, c_oracle.photometric_forward(to_np(es), to_np(ta), 9, tid, 0.5, "f64"), name=f"fwd {t}")
         assert_close(es.grad, c_oracle.photometric_backward(to_np(es), to_np(ta), to_np(go), 9, tid, 0.5, "f64"), name=f"bwd {t}",
-                     outlier_frac=1e-4 if "sad" in t else 0)
+                     outlier_frac=0)
     with pytest.raises(Exception, match="invalid loss type"):
         ref.photometric_loss(es, ta, 9, "ssim", 0.5)
 
@@ -183,7 +183,7 @@ def test_dead_ext_ops_against_brute_force(mods):
             best = torch.where(better, d, best)
             want = torch.where(better, j, want)
     assert got.dtype == torch.int64
-    assert float((got != want).float().mean()) < 1e-3        # (fp32 summation order of the distance may flip exact ties)
+    assert_mismatch_frac(got, want, 0.0, "proj_nn indices")   # (fp32 summation order of the distance may flip exact ties)
     # xcorrvol
     C, n_disps, blk = 2, 6, 5
     i0, i1 = torch.randn(C, H, W, device="cuda"), torch.randn(C, H, W, device="cuda")
@@ -280,8 +280,8 @@ def test_pattern_loss_vs_c_oracle(mods, lt, use_std):
     # rounding of an integer, the fp64 evaluation may pick the neighbouring cell (a different, equally valid
     # one-sided derivative).  The fp32 oracle replays the CUDA op order, so it picks the same cell as the kernel.
     o32g = c_oracle.pattern_loss(disp, im_l, im_s if use_std else None, to_np(mod.pattern), 9, c_oracle.TYPES[lt], 0.5, True, "f32")
-    assert_close(dd.grad, 1.7 * o32g["grad_disp"], name="grad_disp vs fp32 oracle", outlier_frac=1e-4 if "sad" in lt else 0)
-    assert_close(dd.grad, 1.7 * o["grad_disp"], 2e-5, name="grad_disp vs fp64 oracle", outlier_frac=2e-3)
+    assert_close(dd.grad, 1.7 * o32g["grad_disp"], name="grad_disp vs fp32 oracle", outlier_frac=0)
+    assert_close(dd.grad, 1.7 * o["grad_disp"], 2e-5, name="grad_disp vs fp64 oracle", outlier_frac=1e-3)
 
 
 def test_pattern_loss_golden(mods, golden):
@@ -295,12 +295,12 @@ def test_pattern_loss_golden(mods, golden):
             dd = dev(g["disp"]).requires_grad_(True)
             val, proj = mod(dd, dev(g["im_lcn"]), dev(g["im_std"]) if use_std else None)
             val.backward()
-            assert_scalar_close(val.item(), g[f"{key}_val"], 2e-5, key)       # reference ran torch-CPU coordinates
-            assert_close(proj, g["proj"], 2e-5, "proj")
-            assert_close(dd.grad, g[f"{key}_grad"], 5e-5, key + " grad")
+            assert_scalar_close(val.item(), g[f"{key}_val"], 1e-6, key)       # reference ran torch-CPU coordinates
+            assert_close(proj, g["proj"], 1e-5, "proj")
+            assert_close(dd.grad, g[f"{key}_grad"], (2.5e-5 if "census" in key else 1.5e-5), key + " grad")
     mod = net.RectifiedPatternSimilarityLoss(H, W, dev(np.repeat(g["pattern_lcn"], 3, axis=1)))
     diff, proj = mod(dev(g["disp"]), dev(g["im_lcn"]), dev(g["im_std"]), output_mean=False)
-    assert_close(diff, g["census_sad_map"], 2e-5, "per-pixel map")
+    assert_close(diff, g["census_sad_map"], 1e-5, "per-pixel map")
 
 
 def test_pattern_loss_map_backward_and_proj_gradient(mods):
@@ -318,7 +318,7 @@ def test_pattern_loss_map_backward_and_proj_gradient(mods):
     rdiff, rproj = torch_port.pattern_loss(dt, dev(im_l).double(), None, mod.pattern.double(), output_mean=False)
     ((rdiff * w.double()).sum() + 0.3 * rproj.sum()).backward()
     assert_close(diff, rdiff, name="map")
-    assert_close(dd.grad, dt.grad, 2e-5, name="grad through map + proj", outlier_frac=1e-4)
+    assert_close(dd.grad, dt.grad, 1e-5, name="grad through map + proj", outlier_frac=0)
     # mean path with a gradient through pattern_proj as well
     dd.grad = None
     val, proj = mod(dd, dev(im_l), dev(im_s))
@@ -326,7 +326,7 @@ def test_pattern_loss_map_backward_and_proj_gradient(mods):
     dt.grad = None
     rval, rproj = torch_port.pattern_loss(dt, dev(im_l).double(), dev(im_s).double(), mod.pattern.double())
     (rval + 0.01 * (rproj ** 2).sum()).backward()
-    assert_close(dd.grad, dt.grad, 2e-5, name="grad through val + proj", outlier_frac=1e-4)
+    assert_close(dd.grad, dt.grad, 1e-5, name="grad through val + proj", outlier_frac=0)
 
 
 def test_pattern_loss_dataset_shape_vs_torch_cuda_port(mods):
@@ -343,7 +343,7 @@ def test_pattern_loss_dataset_shape_vs_torch_cuda_port(mods):
         rval, _ = torch_port.pattern_loss(dt, dev(im_l), dev(im_s), mod.pattern, chunk=1)
         rval.backward()
         assert_scalar_close(val.item(), rval.item(), name=f"val scale {s}")
-        assert_close(dd.grad, dt.grad, 2e-5, name=f"grad scale {s}", outlier_frac=1e-4)
+        assert_close(dd.grad, dt.grad, 2e-5, name=f"grad scale {s}", outlier_frac=7e-5)
 
 
 def test_pattern_loss_is_deterministic_and_batch_separable(mods):
@@ -384,6 +384,8 @@ def test_lcn_vs_fp64_oracle(mods, hw, radius):
     theirs = float(np.abs(to_np(r_s) - o_s).max())
     assert ours <= theirs + 1e-7, (ours, theirs)
     assert_close(lcn, r_l, 2e-5, "lcn vs reference fp32 arithmetic")
+    # sigma: the reference's own fp32 E[x^2] - mu^2 cancels on flat regions; the bound is ITS error vs fp64
+    assert_close(std, r_s, 2e-3, "std vs reference fp32 arithmetic")   # measured 8.2e-4 (profiles/r02_parity_report.jsonl)
 
 
 def test_lcn_golden(mods, golden):
@@ -412,7 +414,7 @@ def test_smooth_loss_vs_oracle(mods, hw):
     (val * 0.4).backward()
     o_val, o_grad = c_oracle.smooth_loss(disp, d["ambient"], True, "f64")
     assert_scalar_close(val.item(), o_val, name="val")
-    assert_close(dd.grad, 0.4 * o_grad, name="grad", outlier_frac=2e-4)
+    assert_close(dd.grad, 0.4 * o_grad, name="grad", outlier_frac=0)
 
 
 def test_smooth_golden_and_sobel(mods, golden):
@@ -422,7 +424,7 @@ def test_smooth_golden_and_sobel(mods, golden):
     val = net.DisparitySmoothLoss()(dd, dev(g["ambient"]))
     val.backward()
     assert_scalar_close(val.item(), float(g["val_f64"]), name="val")
-    assert_close(dd.grad, g["grad_f64"], name="grad", outlier_frac=2e-3)
+    assert_close(dd.grad, g["grad_f64"], name="grad", outlier_frac=0)
     x = dev(g["disp"]).requires_grad_(True)
     s = net.SobelFilter()(x)
     assert_close(s, g["sobel_f64"], name="sobel")
@@ -458,8 +460,8 @@ def test_flow_warp_vs_oracle(mods, shape):
     assert_close(xt.grad, o_gx, 2e-6, name="grad x vs fp32 oracle")
     assert_close(ft.grad, o_gf, 1e-5, name="grad flow vs fp32 oracle")
     o_gx64, o_gf64 = c_oracle.flow_warp_backward(x, f01, go, True, "f64")
-    assert_close(xt.grad, o_gx64, 1e-4, name="grad x vs fp64 oracle")
-    assert_close(ft.grad, o_gf64, 1e-4, name="grad flow vs fp64 oracle", outlier_frac=1e-2)
+    assert_close(xt.grad, o_gx64, 7e-5, name="grad x vs fp64 oracle")
+    assert_close(ft.grad, o_gf64, 1e-4, name="grad flow vs fp64 oracle", outlier_frac=9e-3)
     # corner indices are integer work: bit-exact
     from depthinspace_b200 import _ops
     _, _, cx, cy = _ops.flow_warp_forward(dev(x), dev(f01), want_corners=True)
@@ -488,7 +490,7 @@ def test_flow_warp_bit_exact_vs_torch_cuda_and_fb_mask(mods):
         ref_cudnn = torch_port.flow_warp(x, dev(f01))
         assert_close(y, ref_cudnn, 1e-5, "vs cuDNN spatial-transformer path")
         mask_cudnn = torch_port.fb_mask(dev(f01), torch_port.flow_warp(dev(f10), dev(f01)))
-        assert float((mask != mask_cudnn).float().mean()) < 1e-4
+        assert_mismatch_frac(mask, mask_cudnn, 0.0, "fb-mask vs cuDNN sampler path")
 
 
 def test_flow_warp_golden(mods, golden):
@@ -497,10 +499,10 @@ def test_flow_warp_golden(mods, golden):
     xt = dev(g["x"]).requires_grad_(True)
     y = mf.warp(xt, dev(g["flow"]))
     y.backward(dev(g["go"]))
-    assert_close(y, g["out_f64"], 2e-5, "out")       # fp32 coordinates vs fp64 coordinates
-    assert_close(xt.grad, g["grad_x_f64"], 2e-5, "grad_x")
+    assert_close(y, g["out_f64"], 1e-5, "out")       # fp32 coordinates vs fp64 coordinates
+    assert_close(xt.grad, g["grad_x_f64"], 1e-5, "grad_x")
     _, mask = mf.warp_with_fb_mask(dev(g["flow_back"]), dev(g["flow"]))
-    assert float((to_np(mask) != g["fb_mask"]).mean()) < 1e-3
+    assert_mismatch_frac(mask, g["fb_mask"], 0.0, "fb-mask vs golden (torch-CPU coordinates)")
 
 
 # ----------------------------------------------------------------------------- multi-scale kernel + loss assembly (a8)
@@ -524,14 +526,14 @@ def test_pattern_loss_multi_scale_kernel(mods, lt, S, hw, k):
         o64 = c_oracle.pattern_loss(disps[s], im_l, im_s, to_np(mod.pattern), k, tid, 0.5, True, "f64")
         o32 = c_oracle.pattern_loss(disps[s], im_l, im_s, to_np(mod.pattern), k, tid, 0.5, True, "f32")
         assert_scalar_close(vals[s].item(), o64["val"], name=f"val scale {s}")
-        assert_close(dd[s].grad, (0.5 ** s) * o32["grad_disp"], name=f"grad scale {s} vs fp32 oracle", outlier_frac=5e-4 if "sad" in lt else 0)
-        assert_close(dd[s].grad, (0.5 ** s) * o64["grad_disp"], 2e-5, name=f"grad scale {s} vs fp64 oracle", outlier_frac=2e-3)
+        assert_close(dd[s].grad, (0.5 ** s) * o32["grad_disp"], name=f"grad scale {s} vs fp32 oracle", outlier_frac=2.6e-4 if "sad" in lt else 0)
+        assert_close(dd[s].grad, (0.5 ** s) * o64["grad_disp"], 2e-5, name=f"grad scale {s} vs fp64 oracle", outlier_frac=1.5e-3)
         # single-scale kernel on the same inputs
         d1 = dev(disps[s]).requires_grad_(True)
         v1, _ = mod(d1, dev(im_l), dev(im_s))
         (v1 * (0.5 ** s)).backward()
         assert_scalar_close(vals[s].item(), v1.item(), 2e-6, name="multi vs single kernel")
-        assert_close(dd[s].grad, d1.grad, 2e-6, name="multi vs single kernel grad", outlier_frac=5e-4 if "sad" in lt else 0)
+        assert_close(dd[s].grad, d1.grad, 2e-6, name="multi vs single kernel grad", outlier_frac=1.3e-4 if "sad" in lt else 0)
 
 
 def test_pattern_loss_multi_exact_zero_when_estimate_equals_target(mods):
@@ -582,9 +584,9 @@ def test_single_frame_loss_assembly_vs_torch_port(mods, n_scales, lt, pgt):
         rvals = rvals + [(r - dev(d["disp_gt"] + 0.1).double()).abs().mean() * 0.1 / 2 ** s for s, r in enumerate(refs)]
     sum(rvals).backward()
     for i, (a, b) in enumerate(zip(vals, rvals)):
-        assert_scalar_close(a.item(), b.item(), 2e-5 if lt == "mse" else 1e-5, name=f"term {i}")
+        assert_scalar_close(a.item(), b.item(), 2e-6, name=f"term {i}")
     for s in range(n_scales):
-        assert_close(outs[s].grad.view(-1, 1, *hw), refs[s].grad, 5e-5, name=f"grad scale {s}", outlier_frac=2e-3)
+        assert_close(outs[s].grad.view(-1, 1, *hw), refs[s].grad, 1e-5, name=f"grad scale {s}", outlier_frac=6e-4)
 
 
 def test_multi_frame_loss_assembly_vs_torch_port(mods):
@@ -605,7 +607,7 @@ def test_multi_frame_loss_assembly_vs_torch_port(mods):
     assert len(vals) == 3
     for a, b in zip(vals, rvals):
         assert_scalar_close(a.item(), b.item(), name="term")
-    assert_close(o.grad, r.grad, 5e-5, name="grad", outlier_frac=2e-3)
+    assert_close(o.grad, r.grad, 1.3e-5, name="grad", outlier_frac=0)
 
 
 # ----------------------------------------------------------------------------- flow-consistency loss (a9)
@@ -653,11 +655,11 @@ def test_flow_consistency_vs_oracle(mods, mf, hw, bs):
         assert np.array_equal(to_np(out[1]), A["mask"]) and np.array_equal(to_np(out[2]), B["mask"]), "masks must be bit-exact"
         assert np.array_equal(to_np(out[3]), A["orig_mask"][0, 0])
     assert 0.3 < A["mask"].mean() < 0.98
-    assert_close(d0.grad, 0.2 * (A["grad_depth0"] + B["grad_depth1"]), 2e-5, "grad depth0", outlier_frac=1e-3)
-    assert_close(d1.grad, 0.2 * (A["grad_depth1"] + B["grad_depth0"]), 2e-5, "grad depth1", outlier_frac=1e-3)
+    assert_close(d0.grad, 0.2 * (A["grad_depth0"] + B["grad_depth1"]), 2e-5, "grad depth0", outlier_frac=7e-5)
+    assert_close(d1.grad, 0.2 * (A["grad_depth1"] + B["grad_depth0"]), 2e-5, "grad depth1", outlier_frac=7e-5)
     A64, B64 = _fc_oracle(g, mf, "f64")
     # fp64 coordinates flip a handful of thresholded mask pixels; the loss moves by their share
-    assert_scalar_close(loss.item(), A64["loss"] + B64["loss"], 2e-3, "loss vs fp64 oracle")
+    assert_scalar_close(loss.item(), A64["loss"] + B64["loss"], 1e-5, "loss vs fp64 oracle")
 
 
 @pytest.mark.parametrize("mf", [False, True])
@@ -681,10 +683,13 @@ def test_flow_consistency_vs_torch_cuda_port(mods, mf):
         rloss.backward()
     assert_scalar_close(loss.item(), rloss.item(), 2e-5, "loss")
     if not mf:
-        assert float((out[1] != rout[1]).float().mean()) < 2e-4 and float((out[2] != rout[2]).float().mean()) < 2e-4
-        assert float((out[3] != rout[3]).float().mean()) < 2e-4
-    assert_close(d0.grad, e0.grad, 5e-5, "grad depth0", outlier_frac=2e-3)
-    assert_close(d1.grad, e1.grad, 5e-5, "grad depth1", outlier_frac=2e-3)
+        # (the port runs torch's own CUDA kernels: bmm / grid_sample in a different association; the masks are bit-exact
+        #  against the fp32 C oracle, test_flow_consistency_vs_oracle)
+        assert_mismatch_frac(out[1], rout[1], 0.0, "mask0 vs torch port")
+        assert_mismatch_frac(out[2], rout[2], 0.0, "mask1 vs torch port")
+        assert_mismatch_frac(out[3], rout[3], 0.0, "orig_mask vs torch port")
+    assert_close(d0.grad, e0.grad, 1e-5, "grad depth0", outlier_frac=0)
+    assert_close(d1.grad, e1.grad, 1e-5, "grad depth1", outlier_frac=0)
 
 
 def test_flow_consistency_golden(mods, golden):
@@ -697,10 +702,10 @@ def test_flow_consistency_golden(mods, golden):
         out = mod(*args)
         loss = out if mf else out[0]
         loss.backward()
-        assert_scalar_close(loss.item(), float(g[f"{key}_loss"]), 2e-3, key)     # CPU-torch coordinates: a few mask flips
+        assert_scalar_close(loss.item(), float(g[f"{key}_loss"]), 2e-6, key)     # CPU-torch coordinates: a few mask flips
         if not mf:
-            assert float((to_np(out[1]) != g["sf_mask0"]).mean()) < 5e-3
-        assert_close(d0.grad, g[f"{key}_grad0"], 1e-2, "grad0", outlier_frac=2e-2)
+            assert_mismatch_frac(out[1], g["sf_mask0"], 0.0, "mask0 vs golden (torch-CPU coordinates)")
+        assert_close(d0.grad, g[f"{key}_grad0"], 1e-5, "grad0", outlier_frac=0)
 
 
 def test_full_single_frame_assembly_with_geometric_terms(mods):
@@ -740,9 +745,9 @@ def test_full_single_frame_assembly_with_geometric_terms(mods):
                 rv.append(v * 0.2 / 6)
         sum(rv).backward()
     for k, (a, b) in enumerate(zip(vals, rv)):
-        assert_scalar_close(a.item(), b.item(), 5e-5, f"term {k}")
+        assert_scalar_close(a.item(), b.item(), 1e-6, f"term {k}")
     for s in range(4):
-        assert_close(outs[s].grad, refs[s].grad, 1e-4, f"grad scale {s}", outlier_frac=5e-3)
+        assert_close(outs[s].grad, refs[s].grad, 1e-5, f"grad scale {s}", outlier_frac=0)
 
 
 @pytest.mark.parametrize("tl,tidx,C", [(4, 1, 5), (4, 0, 32), (4, 3, 3), (2, 1, 2), (1, 0, 4)])
@@ -855,7 +860,7 @@ def test_lcn_backward_vs_reference_autograd(mods):
         xr = dev(x).double().requires_grad_(True)
         rl, rs = torch_port.lcn(xr, radius, 0.05)
         ((rl * wl.double()).sum() + (rs * ws.double()).sum()).backward()
-        assert_close(xt.grad, xr.grad, 2e-4, f"lcn backward r={radius}")   # mu, sqrt(var) are recovered from fp32 outputs
+        assert_close(xt.grad, xr.grad, 1e-5, f"lcn backward r={radius}")   # mu, var come from the fp64 window sums
         # only one of the two outputs used
         xt.grad = None
         lcn, std = net.LCN(radius, 0.05)(xt)
@@ -863,7 +868,7 @@ def test_lcn_backward_vs_reference_autograd(mods):
         xr.grad = None
         rl, _ = torch_port.lcn(xr, radius, 0.05)
         (rl * wl.double()).sum().backward()
-        assert_close(xt.grad, xr.grad, 2e-4, "lcn backward, lcn output only")
+        assert_close(xt.grad, xr.grad, 1e-5, "lcn backward, lcn output only")
 
 
 # ----------------------------------------------------------------------------- BASELINE.json configs as parity cases
@@ -882,7 +887,7 @@ def test_config_sweep_dataset_shape_real_and_kinect_patterns(mods, kind, k):
     rval, _ = torch_port.pattern_loss(dt, dev(im_l), dev(im_s), mod.pattern, block_size=k, chunk=1)
     rval.backward()
     assert_scalar_close(val.item(), rval.item(), name=f"{kind} k={k}")
-    assert_close(dd.grad, dt.grad, 2e-5, name="grad", outlier_frac=2e-4)
+    assert_close(dd.grad, dt.grad, 2e-5, name="grad", outlier_frac=1.4e-4)
 
 
 def test_config_dis_ftsf_pseudo_gt_kinect(mods):
@@ -902,7 +907,7 @@ def test_config_dis_ftsf_pseudo_gt_kinect(mods):
     for a, b in zip(vals, rvals):
         assert_scalar_close(a.item(), b.item(), 2e-5)
     for a, b in zip(outs, refs):
-        assert_close(a.grad, b.grad, 5e-5, outlier_frac=2e-3)
+        assert_close(a.grad, b.grad, 5e-5, outlier_frac=4e-5)
 
 
 def test_lcn_prepare_input_matches_copy_data(mods):
@@ -993,7 +998,7 @@ def test_fused_pattern_loss_window_sizes(mods, k, lt):
     for s in range(2):
         o32 = c_oracle.pattern_loss(d["disp_pred"][s], im_l, im_s, to_np(mod.pattern), k, tid, 0.5, True, "f32")
         assert_scalar_close(vals[s].item(), o32["val"], 2e-6, f"val k={k}")
-        assert_close(dd[s].grad, o32["grad_disp"], 1e-5, f"grad k={k}", outlier_frac=5e-4 if "sad" in lt else 0)
+        assert_close(dd[s].grad, o32["grad_disp"], 1e-5, f"grad k={k}", outlier_frac=0)
 
 
 # ----------------------------------------------------------------------------- BASELINE full size, size-independent properties
@@ -1050,7 +1055,7 @@ def test_full_size_step_properties(mods):
     o3, og = run(disps, sl)
     assert_scalar_close(o3[1, 2].item(), rv.item(), name="slice value vs oracle")
     rv.backward()
-    assert_close(og[1] / o3[1, 1].float().cuda(), r.grad, 5e-5, name="slice gradient vs oracle", outlier_frac=2e-3)
+    assert_close(og[1] / o3[1, 1].float().cuda(), r.grad, 5e-5, name="slice gradient vs oracle", outlier_frac=7e-4)
 
 
 def test_full_size_lcn_smooth_warp_properties(mods):
@@ -1083,14 +1088,14 @@ def test_full_size_lcn_smooth_warp_properties(mods):
     f = torch.randn(bs, C, h, w, device="cuda", generator=gen)
     zero = torch.zeros(bs, 2, h, w, device="cuda")
     # not bit-exact by design: the reference's normalise -> un-normalise round trip moves coordinates by ~1e-5 px
-    assert_close(mf.warp(f, zero), f, 1e-4, "zero flow")
+    assert_close(mf.warp(f, zero), f, 5e-5, "zero flow")
     shift = zero.clone()
     shift[:, 0] = 3.0
     shift[:, 1] = -2.0
     out = mf.warp(f, shift)                      # out(v, u) = f(v - 2, u + 3), zeros outside
     ref = torch.zeros_like(f)
     ref[:, :, 2:, : w - 3] = f[:, :, : h - 2, 3:]
-    assert_close(out, ref, 1e-4, "integer translation")
+    assert_close(out, ref, 5e-5, "integer translation")
 
 
 @pytest.mark.parametrize("n_scales,pgt,hw", [(4, False, (64, 80)), (2, True, (37, 52)), (4, True, (48, 64))])
@@ -1161,7 +1166,7 @@ def test_random_shape_sweep_vs_c_oracle(mods, i, H, W, N, k, t):
     out = ext.photometric_loss(e, dev(ta), k, t, 0.5)
     out.backward(dev(go))
     assert_close(out, c_oracle.photometric_forward(es, ta, k, tid, 0.5, "f64"), name="ext fwd")
-    assert_close(e.grad, c_oracle.photometric_backward(es, ta, go, k, tid, 0.5, "f64"), name="ext bwd", outlier_frac=2e-3 if sad else 0)
+    assert_close(e.grad, c_oracle.photometric_backward(es, ta, go, k, tid, 0.5, "f64"), name="ext bwd", outlier_frac=4e-4 if sad else 0)
     # LCN (radius must stay below the image size: reflection padding)
     radius = int(min(5, H - 1, W - 1))
     x = rng.random((N, 1, H, W)).astype(np.float32)
@@ -1177,7 +1182,7 @@ def test_random_shape_sweep_vs_c_oracle(mods, i, H, W, N, k, t):
     val.backward()
     o_v, o_g = c_oracle.smooth_loss(disp, amb, True, "f64")
     assert_scalar_close(val.item(), o_v, name="smooth value")
-    assert_close(dd.grad, o_g, 2e-5, "smooth grad", outlier_frac=2e-3)
+    assert_close(dd.grad, o_g, 1e-5, "smooth grad", outlier_frac=0)
     # fused pattern loss (value, projection bit-exact vs the fp32 oracle, gradient vs the fp32 oracle)
     pat = rng.random((1, 1, H, W)).astype(np.float32)
     sig = (0.05 + rng.random((N, 1, H, W))).astype(np.float32)
@@ -1190,7 +1195,7 @@ def test_random_shape_sweep_vs_c_oracle(mods, i, H, W, N, k, t):
     o64 = c_oracle.pattern_loss(dsp, ta, sig, to_np(mod.pattern), k, tid, 0.5, False, "f64")
     assert_scalar_close(v.item(), o64["val"], 2e-5, "pattern loss value")
     assert np.array_equal(to_np(proj), o["proj"]), "pattern_proj differs from the fp32 oracle"
-    assert_close(d2.grad, o["grad_disp"], 2e-5, "pattern loss grad", outlier_frac=2e-3 if sad else 1e-4)
+    assert_close(d2.grad, o["grad_disp"], 1e-5, "pattern loss grad", outlier_frac=0)
 
 
 def _mf_sweep_cases(n, seed):
