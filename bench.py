@@ -133,13 +133,32 @@ def bind_to_gpu_numa_node(local_rank):
         bdf = f"{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
         with open(f"/sys/bus/pci/devices/{bdf}/numa_node") as f:
             node = int(f.read().strip())
-        if node < 0:
-            return "numa node unknown (single node or virtualised): not bound"
-        with open(f"/sys/devices/system/node/node{node}/cpulist") as f:
-            cpus = set()
-            for part in f.read().strip().split(","):
+        def parse(cpulist):
+            out = set()
+            for part in cpulist.strip().split(","):
                 lo, _, hi = part.partition("-")
-                cpus.update(range(int(lo), int(hi or lo) + 1))
+                out.update(range(int(lo), int(hi or lo) + 1))
+            return out
+        if node < 0:
+            # sysfs has no NUMA node for the device (virtualised PCI topology): ask the driver for the GPU's CPU affinity
+            import re
+            topo = subprocess.run(["nvidia-smi", "topo", "-m"], capture_output=True, text=True, timeout=20).stdout
+            cpus = None
+            for line in topo.splitlines():
+                tok = re.sub(r"\x1b\[[0-9;]*m", "", line).split()
+                if tok and tok[0] == f"GPU{local_rank}":
+                    lists = [t for t in tok[1:] if re.fullmatch(r"\d+(-\d+)?(,\d+(-\d+)?)*", t) and ("-" in t or "," in t)]
+                    if lists:
+                        cpus = parse(lists[0])
+            if not cpus:
+                return "numa node unknown (single node or virtualised): not bound"
+            cpus &= os.sched_getaffinity(0)
+            if not cpus or cpus == os.sched_getaffinity(0):
+                return "driver reports one CPU affinity set for every GPU: not bound"
+            os.sched_setaffinity(0, cpus)
+            return f"bound to the driver's CPU affinity of GPU {local_rank} ({len(cpus)} cpus)"
+        with open(f"/sys/devices/system/node/node{node}/cpulist") as f:
+            cpus = parse(f.read())
         cpus &= os.sched_getaffinity(0)
         if not cpus:
             return f"numa node {node}: no allowed cpu, not bound"

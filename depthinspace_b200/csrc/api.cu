@@ -172,20 +172,23 @@ MarchPlan march_plan(int N, int H, int W, int R) {
   const int min_rows = 2 * RH + 2 * MV;
   int band_rows = env_int("DIS_MARCH_BAND_ROWS", 0);
   if (band_rows <= 0) {
-    double best_cost = 0.0;
-    for (int nrb = 1; nrb <= 64; ++nrb) {
-      int rows = (EH + nrb - 1) / nrb;
-      rows = ((rows + MV - 1) / MV) * MV;
-      if (rows < min_rows) break;
-      const long ctas = (long)N * best.ncb * nrb;
-      const double waves = (double)((ctas + slots - 1) / slots);
-      // a partially filled last wave costs a full band; 0.25 of a band models launch + tail skew per wave
-      const double cost = waves * (rows + RH + 0.25 * rows / (nrb > 0 ? 1 : 1));
-      if (band_rows <= 0 || cost < best_cost) {
-        best_cost = cost;
-        band_rows = rows;
+    // cost of a plan = (waves of CTAs) x (rows marched per CTA); among the plans within 5 % of the cheapest take the one
+    // with the longest bands (fewer halo rows and prologues: measured 6.82 ms at 130 rows vs 6.89 at 88, 256 frames)
+    double best_cost = -1.0;
+    for (int pass = 0; pass < 2; ++pass)
+      for (int nrb = 1; nrb <= 64; ++nrb) {
+        int rows = (EH + nrb - 1) / nrb;
+        rows = ((rows + MV - 1) / MV) * MV;
+        if (rows < min_rows) break;
+        const long ctas = (long)N * best.ncb * nrb;
+        const double cost = (double)((ctas + slots - 1) / slots) * (rows + RH);
+        if (pass == 0) {
+          if (best_cost < 0.0 || cost < best_cost) best_cost = cost;
+        } else if (cost <= 1.05 * best_cost) {
+          band_rows = rows;
+          break;
+        }
       }
-    }
     if (band_rows <= 0) band_rows = ((EH + MV - 1) / MV) * MV;
   }
   band_rows = ((band_rows + MV - 1) / MV) * MV;

@@ -40,6 +40,9 @@ constexpr int MARCH_CTAS_PER_SM = 3;
 #ifndef DIS_MARCH_UNROLL
 #define DIS_MARCH_UNROLL 9
 #endif
+#ifndef DIS_MARCH_SYNCWARP
+#define DIS_MARCH_SYNCWARP 1
+#endif
 #ifndef DIS_MARCH_PREFETCH
 #define DIS_MARCH_PREFETCH 0     // streaming loads of the next step's rows issued one step ahead
 #endif
@@ -396,6 +399,9 @@ __global__ void __maxnreg__(MARCH_MAX_REGS) pattern_march_kernel(PatternMarchArg
 #pragma unroll
         for (int p = 0; p < NPAIR; ++p) cur.v[p] = sub2(cur.v[p], cs.v[p]);
         strip_st<NPAIR>(c, cur);
+#if DIS_MARCH_SYNCWARP
+        __syncwarp();   // memory-model form of the hand-over to the neighbour lane (the LSU already keeps the order)
+#endif
       }
     };
     using T_ = std::true_type;

@@ -51,6 +51,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--time", action="store_true")
     ap.add_argument("--no-oracle", action="store_true")
+    ap.add_argument("--small", action="store_true", help="skip the large shapes (for compute-sanitizer runs)")
     a = ap.parse_args()
     worst = {"val_tile": 0.0, "grad_tile": 0.0, "val_o64": 0.0, "grad_o64_frac": 0.0}
     ok = True
@@ -77,6 +78,8 @@ def main():
         (1, (480, 640), 9, 4, "census_sad", {}),
     ]
     for (N, hw, k, S, lt, env) in cases:
+        if a.small and hw[0] * hw[1] > 100 * 160:
+            continue
         if min(hw) >= 24:
             d = synth.make_frames(N, hw, "kinect", n_scales=S, max_disp=min(48, max(2, hw[1] // 2)), seed=k + S)
             lcn_im, std = _ops.lcn_forward(dev(d["im"]), 5, 0.05)
