@@ -362,7 +362,13 @@ int dis_pattern_warp_forward(const float* disp, const float* pattern, float* pro
 
 int dis_pattern_loss_num_partials(int N, int H, int W) {
   if (N < 0 || H < 1 || W < 1) return DIS_ERR_BAD_SHAPE;
-  return N * ((H + TH - 1) / TH) * ((W + TW - 1) / TW);
+  long most = (long)N * ((H + TH - 1) / TH) * ((W + TW - 1) / TW);      // tile kernels (mse / sad, maps, 1 x 1 windows)
+  for (int R = 1; R <= MAX_R; ++R) {                                      // marching kernel (census types)
+    const MarchPlan p = march_plan(N, H, W, R);
+    const long n = (long)N * p.ncb * p.nrb;
+    if (n > most) most = n;
+  }
+  return most > INT_MAX ? DIS_ERR_BAD_SHAPE : (int)most;
 }
 
 int dis_pattern_loss_forward(const float* disp, const float* im, const float* std_in, const float* pattern,
@@ -380,7 +386,36 @@ int dis_pattern_loss_forward_scaled(const float* disp, const float* im, const fl
   if (N < 0 || H < 2 || W < 2) return DIS_ERR_BAD_SHAPE;
   if (N == 0) return DIS_OK;
   const size_t hw = (size_t)H * W;
+  const int num_blocks = dis_pattern_loss_num_partials(N, H, W);
+  if (num_blocks < 0) return num_blocks;
+  // census types without the per-pixel loss map: the pair-symmetric marching kernel (one scale: the packed pair is
+  // (estimate, target)); everything else stays on the tile kernels
+  if (type >= CENSUS_MSE && !diff && use_march(block_size / 2)) {
+    const int R = block_size / 2;
+    const MarchPlan plan = march_plan(N, H, W, R);
+    const int per_frame = plan.ncb * plan.nrb;
+    for (int n0 = 0; n0 < N; n0 += MAX_GRID_Z) {
+      PatternMarchArgs a{};
+      a.disp[0] = disp + n0 * hw;
+      a.grad[0] = grad_num ? grad_num + n0 * hw : nullptr;
+      a.proj = proj ? proj + n0 * hw : nullptr;
+      a.im = im + n0 * hw; a.std_in = std_in ? std_in + n0 * hw : nullptr; a.pattern = pattern;
+      a.partials = partials;
+      a.grad_scale = grad_scale;
+      a.N = N - n0 < MAX_GRID_Z ? N - n0 : MAX_GRID_Z; a.H = H; a.W = W;
+      a.ncb = plan.ncb; a.nrb = plan.nrb; a.band_rows = plan.band_rows;
+      a.num_blocks = num_blocks; a.total_blocks = N * per_frame; a.block_offset = n0 * per_frame;
+      a.eps = eps; a.inv_k2 = 1.0f / (float)(block_size * block_size);
+      a.inv_w = 1.0f / (float)(W - 1); a.inv_h = 1.0f / (float)(H - 1);
+      if (int rc = dispatch_pattern_march(R, a, plan, 1, type, as_stream(stream))) return rc;
+    }
+    return DIS_OK;
+  }
   const int per_frame = ((H + TH - 1) / TH) * ((W + TW - 1) / TW);
+  if (num_blocks > N * per_frame) {   // slots the tile kernels do not write must read as zero
+    const cudaError_t e = cudaMemsetAsync(partials, 0, sizeof(float) * 2 * (size_t)num_blocks, as_stream(stream));
+    if (e != cudaSuccess) { set_last_cuda_error(e); return DIS_ERR_CUDA_LAUNCH; }
+  }
   for (int n0 = 0; n0 < N; n0 += MAX_GRID_Z) {
     PatternLossArgs a{};
     a.disp = disp + n0 * hw; a.im = im + n0 * hw; a.std_in = std_in ? std_in + n0 * hw : nullptr;

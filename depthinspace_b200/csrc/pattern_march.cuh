@@ -15,19 +15,21 @@
 // rows / columns; the gradient collected by a virtual pixel is folded onto the border pixel it replicates
 // (= the backward of F.pad).  Clamp multiplicities come out exactly, with no special border pass.
 //
-// Organisation.  A CTA owns a band of the extended image: up to 7 warps side by side (lane = column), marching
+// Organisation.  A CTA owns a band of the extended image: up to 8 warps side by side (lane = column), marching
 // down the band MV = 2 rows per step.  Per step a thread owns pixels p0 = (row, col), p1 = (row + 1, col) and
 // visits the cells q of rows row .. row + R + 1: the values of q are loaded once for both pairs (p0,q), (p1,q).
 // The p side of the gradient stays in registers; the q side goes into a WARP-PRIVATE strip of shared-memory
-// accumulators (RING rows x (32 + 2R) cells, all scales of a cell in one 128-bit word), one read-modify-write per
-// cell.  Strips of neighbouring warps are merged in a fixed order when a row retires: no atomics, bitwise
-// reproducible.  Staged planes (warped pattern of every scale, LCN image, sigma) live in a ring of RING rows;
-// every pixel of the band is staged exactly once (halo: R rows at the top of a band, R columns between column
-// bands).  d proj / d disp is parked in the gradient output buffer at staging time and read back (L2 hit) when
-// the row retires, instead of occupying shared memory for R + 2 rows.
+// accumulators (RING rows x (32 + 2R) cells, all scales of a cell in one word of up to 128 bits), one
+// read-modify-write per cell.  Strips of neighbouring warps are merged in a fixed order when a row retires: no
+// atomics, bitwise reproducible.  Staged planes (warped pattern of every scale, LCN image, sigma) live in a ring
+// of RING rows; every pixel of the band is staged exactly once (halo: R rows at the top of a band, R columns
+// between column bands).  d proj / d disp is parked in the gradient output buffer at staging time and read back
+// (L2 hit) when the row retires, instead of occupying shared memory for R + 2 rows.
 //
-// Cost per unordered pair for 4 scales: 5 MUFU.RSQ and ~46 issue slots (the tile kernel in pattern_multi.cuh
-// pays 43 slots and 5 MUFU per ORDERED pair, i.e. twice).
+// Scales.  NS = 2 / 4: the estimates of two scales share a packed fp32x2 register (FADD2 / FFMA2 / FMUL2), the target
+// side of the soft census is computed once per pair for all scales.  NS = 1: (estimate, target) form the packed pair.
+// Cost per unordered pair: NS = 4: 5 MUFU.RSQ, ~41 issue slots (the tile kernel in pattern_multi.cuh pays 43 slots and
+// 5 MUFU per ORDERED pair, i.e. twice); NS = 1: 2 MUFU.RSQ, ~16 slots (census_kernels.cuh: 14 slots, 2 MUFU per ordered pair).
 #pragma once
 #include <type_traits>
 #include "window.cuh"
@@ -44,10 +46,10 @@ constexpr int MARCH_CTAS_PER_SM = 3;
 #define DIS_MARCH_SYNCWARP 1
 #endif
 #ifndef DIS_MARCH_PREFETCH
-#define DIS_MARCH_PREFETCH 0     // streaming loads of the next step's rows issued one step ahead
+#define DIS_MARCH_PREFETCH 0     // streaming loads of the next step's rows issued one step ahead (measured slower: registers)
 #endif
 #ifndef DIS_MARCH_STASH_EARLY
-#define DIS_MARCH_STASH_EARLY 0  // read-back of the parked d proj / d disp issued before the barrier
+#define DIS_MARCH_STASH_EARLY 0  // read-back of the parked d proj / d disp issued before the barrier (measured slower)
 #endif
 constexpr int MARCH_UNROLL = DIS_MARCH_UNROLL;   // cells per iteration of the rolled cell loops
 constexpr int MARCH_MAX_REGS = 80;      // 6 warps per SM sub-partition (16 K registers each): 3 CTAs of 7 warps
@@ -62,11 +64,12 @@ struct MarchGeom {
 struct PatternMarchArgs {
   const float* disp[4];
   float* grad[4];          // all NULL => forward only
+  float* proj;             // optional (NS == 1 only): the warped pattern [N,1,H,W] (model/networks.py:367)
   const float* im;
   const float* std_in;
   const float* pattern;
-  const float* grad_scale; // optional device float[S]
-  float* partials;         // [S][num_blocks][2] = (num_s, den)
+  const float* grad_scale; // optional device float[NS]
+  float* partials;         // [NS][num_blocks][2] = (num_s, den)
   int N, H, W;
   int ncb, nrb;            // column / row bands per frame
   int band_rows;           // extended rows owned by a row band (multiple of MV); the last band takes the rest
@@ -76,62 +79,92 @@ struct PatternMarchArgs {
   float eps, inv_k2, inv_w, inv_h;
 };
 
-// shared memory: ring of staged rows (estimate pairs, (t, w)), per-warp accumulator strips, reduction scratch
-template <int R, int NPAIR>
-__host__ __device__ constexpr size_t pattern_march_smem_bytes(int nwarps) {
-  using G = MarchGeom<R>;
-  const size_t pitch = 32 * (size_t)nwarps + 2 * R;
-  return G::RING * pitch * NPAIR * 8 + G::RING * pitch * 8 + (size_t)nwarps * G::RING * G::SW * NPAIR * 8 +
-         (size_t)nwarps * (2 * NPAIR + 1) * 8 + (size_t)(2 * NPAIR + 1) * 32 * nwarps * 8;
-}
-
-template <int NPAIR>
-struct MCell {  // all scales of one pixel: NPAIR packed fp32x2 values
-  u64 v[NPAIR];
+// ---- per-cell words ---------------------------------------------------------------------------------------------------
+// MCell<NP>: the staged estimates of one pixel, NP packed fp32x2 values (NS = 4: two scale pairs; NS = 2: one;
+// NS = 1: the pair (estimate, target)).
+template <int NP>
+struct MCell {
+  u64 v[NP];
 };
-template <int NPAIR>
-__device__ __forceinline__ MCell<NPAIR> mcell_load(const u64* p) {
-  MCell<NPAIR> c;
-  if (NPAIR == 2) {
+template <int NP>
+__device__ __forceinline__ MCell<NP> mcell_load(const u64* p) {
+  MCell<NP> c;
+  if (NP == 2) {
     const ulonglong2 q = *reinterpret_cast<const ulonglong2*>(p);
     c.v[0] = q.x;
-    c.v[NPAIR - 1] = q.y;
+    c.v[NP - 1] = q.y;
   } else {
     c.v[0] = *p;
   }
   return c;
 }
-template <int NPAIR>
-__device__ __forceinline__ void mcell_store(u64* p, const MCell<NPAIR>& c) {
-  if (NPAIR == 2) *reinterpret_cast<ulonglong2*>(p) = make_ulonglong2(c.v[0], c.v[NPAIR - 1]);
-  else *p = c.v[0];
-}
 
-// Accesses to the accumulator strips: volatile, so that the read-modify-write sequences of consecutive cells keep
-// their program order (the next cell of a lane is the previous cell of its neighbour lane; the warp runs them in
-// lockstep and the LSU executes a warp's shared-memory operations in order), while the plain loads of the staged
-// planes stay free to be scheduled early.
-template <int NPAIR>
-__device__ __forceinline__ MCell<NPAIR> strip_ld(unsigned addr) {
-  MCell<NPAIR> c;
-  if (NPAIR == 2) asm volatile("ld.volatile.shared.v2.u64 {%0, %1}, [%2];" : "=l"(c.v[0]), "=l"(c.v[NPAIR - 1]) : "r"(addr));
-  else asm volatile("ld.volatile.shared.u64 %0, [%1];" : "=l"(c.v[0]) : "r"(addr));
-  return c;
-}
-template <int NPAIR>
-__device__ __forceinline__ void strip_st(unsigned addr, const MCell<NPAIR>& c) {
-  if (NPAIR == 2) asm volatile("st.volatile.shared.v2.u64 [%0], {%1, %2};" ::"r"(addr), "l"(c.v[0]), "l"(c.v[NPAIR - 1]));
-  else asm volatile("st.volatile.shared.u64 [%0], %1;" ::"r"(addr), "l"(c.v[0]));
-}
-
-// Estimate side of one unordered pair {p (centre), q} for all scales, given the target side (ngt = -(dt * rt) rounded,
-// rest = the exact rounding residual of dt * rt) and the pair weight ws = w(p) + w(q).
-// acc: forward accumulators, gp: p-side gradient, cell: running sum for q's cell.
-template <int TYPE, int NPAIR, bool GRAD, bool FIRST>
-__device__ __forceinline__ void march_scales(const MCell<NPAIR>& ec, const MCell<NPAIR>& eq, float ngt, float rest, float ws,
-                                             u64 eps2, float (&acc)[2 * NPAIR], MCell<NPAIR>& gp, MCell<NPAIR>& cell) {
+// MAcc<NS>: the gradient accumulator of one pixel, one float per scale (packed in pairs for NS >= 2).  Accesses to the
+// accumulator strips are volatile, so that the read-modify-write sequences of consecutive cells keep their program
+// order (the next cell of a lane is the previous cell of its neighbour lane; the warp runs them in lockstep and the LSU
+// executes a warp's shared-memory operations in order), while the plain loads of the staged planes stay free to move.
+template <int NS>
+struct MAcc {
+  static constexpr int NP = NS / 2;
+  static constexpr int BYTES = 4 * NS;
+  u64 v[NP];
+  __device__ __forceinline__ void zero() {
 #pragma unroll
-  for (int p = 0; p < NPAIR; ++p) {
+    for (int p = 0; p < NP; ++p) v[p] = 0ull;
+  }
+  __device__ __forceinline__ void add(const MAcc& o) {
+#pragma unroll
+    for (int p = 0; p < NP; ++p) v[p] = add2(v[p], o.v[p]);
+  }
+  __device__ __forceinline__ void sub(const MAcc& o) {
+#pragma unroll
+    for (int p = 0; p < NP; ++p) v[p] = sub2(v[p], o.v[p]);
+  }
+  __device__ __forceinline__ void ld(unsigned addr) {
+    if (NP == 2) asm volatile("ld.volatile.shared.v2.u64 {%0, %1}, [%2];" : "=l"(v[0]), "=l"(v[NP - 1]) : "r"(addr));
+    else asm volatile("ld.volatile.shared.u64 %0, [%1];" : "=l"(v[0]) : "r"(addr));
+  }
+  __device__ __forceinline__ void st(unsigned addr) const {
+    if (NP == 2) asm volatile("st.volatile.shared.v2.u64 [%0], {%1, %2};" ::"r"(addr), "l"(v[0]), "l"(v[NP - 1]));
+    else asm volatile("st.volatile.shared.u64 [%0], %1;" ::"r"(addr), "l"(v[0]));
+  }
+  __device__ __forceinline__ float get(int s) const {
+    float lo, hi;
+    upk2(v[s >> 1], lo, hi);
+    return (s & 1) ? hi : lo;
+  }
+};
+template <>
+struct MAcc<1> {
+  static constexpr int BYTES = 4;
+  float v;
+  __device__ __forceinline__ void zero() { v = 0.0f; }
+  __device__ __forceinline__ void add(const MAcc& o) { v += o.v; }
+  __device__ __forceinline__ void sub(const MAcc& o) { v -= o.v; }
+  __device__ __forceinline__ void ld(unsigned addr) { asm volatile("ld.volatile.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr)); }
+  __device__ __forceinline__ void st(unsigned addr) const { asm volatile("st.volatile.shared.f32 [%0], %1;" ::"r"(addr), "f"(v)); }
+  __device__ __forceinline__ float get(int) const { return v; }
+};
+
+// shared memory: ring of staged rows (estimate cells, (t, w)), per-warp accumulator strips, reduction scratch
+template <int R, int NS>
+__host__ __device__ constexpr size_t pattern_march_smem_bytes(int nwarps) {
+  using G = MarchGeom<R>;
+  const size_t np = (NS + 1) / 2;
+  const size_t pitch = 32 * (size_t)nwarps + 2 * R;
+  const size_t strips = ((size_t)nwarps * G::RING * G::SW * 4 * NS + 15) / 16 * 16;
+  return G::RING * pitch * np * 8 + G::RING * pitch * 8 + strips + (size_t)nwarps * (NS + 1) * 8 +
+         (size_t)(NS + 1) * 32 * nwarps * 8;
+}
+
+// ---- NS = 2 / 4: estimate side of one unordered pair {p (centre), q} for all scales, given the target side
+// (ngt = -(dt * rt) rounded, rest = the exact rounding residual of dt * rt) and the pair weight ws = w(p) + w(q).
+// acc: forward accumulators, gp: p-side gradient, cell: running sum for q's cell.
+template <int TYPE, int NS, bool GRAD, bool FIRST>
+__device__ __forceinline__ void march_scales(const MCell<NS / 2>& ec, const MCell<NS / 2>& eq, float ngt, float rest, float ws,
+                                             u64 eps2, float (&acc)[NS], MAcc<NS>& gp, MAcc<NS>& cell) {
+#pragma unroll
+  for (int p = 0; p < NS / 2; ++p) {
     const u64 de = sub2(eq.v[p], ec.v[p]);
     const u64 xe = fma2(de, de, eps2);
     float x0f, x1f;
@@ -167,22 +200,21 @@ __device__ __forceinline__ void march_scales(const MCell<NPAIR>& ec, const MCell
 }
 
 // one pair: scalar target side
-template <int TYPE, int NPAIR, bool GRAD>
-__device__ __forceinline__ void march_pair1(const MCell<NPAIR>& ec, float tc, float wc, const MCell<NPAIR>& eq, float tq,
-                                            float wq, float eps, u64 eps2, float (&acc)[2 * NPAIR], MCell<NPAIR>& gp,
-                                            MCell<NPAIR>& cell) {
+template <int TYPE, int NS, bool GRAD>
+__device__ __forceinline__ void march_pair1(const MCell<NS / 2>& ec, float tc, float wc, const MCell<NS / 2>& eq, float tq,
+                                            float wq, float eps, u64 eps2, float (&acc)[NS], MAcc<NS>& gp, MAcc<NS>& cell) {
   const float dt = tq - tc;
   const float rt = rsqrt_fast(fmaf(dt, dt, eps));
   const float gt = __fmul_rn(dt, rt);
   const float rest = __fmaf_rn(dt, rt, -gt);
-  march_scales<TYPE, NPAIR, GRAD, true>(ec, eq, -gt, rest, wq + wc, eps2, acc, gp, cell);
+  march_scales<TYPE, NS, GRAD, true>(ec, eq, -gt, rest, wq + wc, eps2, acc, gp, cell);
 }
 
 // both pixels of the thread against the same q: the two target sides share packed instructions
-template <int TYPE, int NPAIR, bool GRAD>
-__device__ __forceinline__ void march_pair2(const MCell<NPAIR>& ec0, const MCell<NPAIR>& ec1, u64 tc2, u64 wc2,
-                                            const MCell<NPAIR>& eq, float tq, float wq, u64 eps2, float (&acc)[2 * NPAIR],
-                                            MCell<NPAIR>& gp0, MCell<NPAIR>& gp1, MCell<NPAIR>& cell) {
+template <int TYPE, int NS, bool GRAD>
+__device__ __forceinline__ void march_pair2(const MCell<NS / 2>& ec0, const MCell<NS / 2>& ec1, u64 tc2, u64 wc2,
+                                            const MCell<NS / 2>& eq, float tq, float wq, u64 eps2, float (&acc)[NS],
+                                            MAcc<NS>& gp0, MAcc<NS>& gp1, MAcc<NS>& cell) {
   const u64 dt = sub2(bc2(tq), tc2);
   const u64 xt = fma2(dt, dt, eps2);
   float x0f, x1f;
@@ -196,53 +228,120 @@ __device__ __forceinline__ void march_pair2(const MCell<NPAIR>& ec0, const MCell
   upk2(ngt, n0, n1);
   upk2(rest, r0, r1);
   upk2(ws, w0, w1);
-  march_scales<TYPE, NPAIR, GRAD, true>(ec0, eq, n0, r0, w0, eps2, acc, gp0, cell);
-  march_scales<TYPE, NPAIR, GRAD, false>(ec1, eq, n1, r1, w1, eps2, acc, gp1, cell);
+  march_scales<TYPE, NS, GRAD, true>(ec0, eq, n0, r0, w0, eps2, acc, gp0, cell);
+  march_scales<TYPE, NS, GRAD, false>(ec1, eq, n1, r1, w1, eps2, acc, gp1, cell);
+}
+
+// ---- NS = 1: the cell is the packed pair (estimate, target); both sides of the soft census share every instruction.
+// The two products d * r are rounded separately (one FMUL2) before they are subtracted, so e == t gives exactly 0.
+template <int TYPE, bool GRAD>
+__device__ __forceinline__ void march_et_pair1(u64 c_et, float wc, u64 q_et, float wq, u64 eps2, float& acc, MAcc<1>& gp,
+                                               MAcc<1>& cell) {
+  const u64 d = sub2(q_et, c_et);
+  const u64 x = fma2(d, d, eps2);
+  float xe, xt;
+  upk2(x, xe, xt);
+  const float re = rsqrt_fast(xe), rt = rsqrt_fast(xt);
+  float pe, pt;
+  upk2(mul2(d, pk2(re, rt)), pe, pt);
+  const float diff = __fsub_rn(pe, pt);
+  const float ws = wq + wc;
+  acc = (TYPE == CENSUS_SAD) ? fmaf(fabsf(diff), ws, acc) : fmaf(diff * diff, ws, acc);
+  if (GRAD) {
+    const float r3 = re * re * re;
+    const float u = (TYPE == CENSUS_SAD) ? signed_mag(r3, diff) : diff * r3;
+    const float v = u * ws;
+    gp.v += v;
+    cell.v = v;
+  }
+}
+template <int TYPE, bool GRAD>
+__device__ __forceinline__ void march_et_pair2(u64 c0_et, u64 c1_et, u64 wc2, u64 q_et, float wq, u64 eps2, float& acc,
+                                               MAcc<1>& gp0, MAcc<1>& gp1, MAcc<1>& cell) {
+  const u64 d0 = sub2(q_et, c0_et), d1 = sub2(q_et, c1_et);
+  const u64 x0 = fma2(d0, d0, eps2), x1 = fma2(d1, d1, eps2);
+  float xe0, xt0, xe1, xt1;
+  upk2(x0, xe0, xt0);
+  upk2(x1, xe1, xt1);
+  const float re0 = rsqrt_fast(xe0), rt0 = rsqrt_fast(xt0), re1 = rsqrt_fast(xe1), rt1 = rsqrt_fast(xt1);
+  float pe0, pt0, pe1, pt1;
+  upk2(mul2(d0, pk2(re0, rt0)), pe0, pt0);
+  upk2(mul2(d1, pk2(re1, rt1)), pe1, pt1);
+  const float diff0 = __fsub_rn(pe0, pt0), diff1 = __fsub_rn(pe1, pt1);
+  const u64 ws2 = add2(bc2(wq), wc2);
+  float ws0, ws1;
+  upk2(ws2, ws0, ws1);
+  if (TYPE == CENSUS_SAD) {
+    acc = fmaf(fabsf(diff0), ws0, acc);
+    acc = fmaf(fabsf(diff1), ws1, acc);
+  } else {
+    acc = fmaf(diff0 * diff0, ws0, acc);
+    acc = fmaf(diff1 * diff1, ws1, acc);
+  }
+  if (GRAD) {
+    const u64 rp = pk2(re0, re1);
+    const u64 r3 = mul2(mul2(rp, rp), rp);
+    u64 u;
+    if (TYPE == CENSUS_SAD) {
+      float q0, q1;
+      upk2(r3, q0, q1);
+      u = pk2(signed_mag(q0, diff0), signed_mag(q1, diff1));
+    } else {
+      u = mul2(pk2(diff0, diff1), r3);
+    }
+    float v0, v1;
+    upk2(mul2(u, ws2), v0, v1);
+    gp0.v += v0;
+    gp1.v += v1;
+    cell.v = v0 + v1;
+  }
 }
 
 // Sum of everything the strips hold for CTA-lane position P of strip row rq (own strip, then the halo cells of the
 // left and of the right neighbour warp: fixed order); the cells are zeroed for their next use.
-template <int R, int NPAIR>
-__device__ __forceinline__ MCell<NPAIR> strip_collect(unsigned strips_addr, int P, int rq, int nwarps) {
+template <int R, int NS>
+__device__ __forceinline__ MAcc<NS> strip_collect(unsigned strips_addr, int P, int rq, int nwarps) {
   using G = MarchGeom<R>;
   const int w = P >> 5, l = P & 31;
-  MCell<NPAIR> zero;
-#pragma unroll
-  for (int p = 0; p < NPAIR; ++p) zero.v[p] = 0ull;
-  const unsigned own = strips_addr + (unsigned)(((w * G::RING + rq) * G::SW + l + R) * NPAIR * 8);
-  MCell<NPAIR> t = strip_ld<NPAIR>(own);
-  strip_st<NPAIR>(own, zero);
+  MAcc<NS> zero, t, c;
+  zero.zero();
+  const unsigned own = strips_addr + (unsigned)(((w * G::RING + rq) * G::SW + l + R) * MAcc<NS>::BYTES);
+  t.ld(own);
+  zero.st(own);
   if (l < R && w > 0) {
-    const unsigned h = strips_addr + (unsigned)((((w - 1) * G::RING + rq) * G::SW + 32 + R + l) * NPAIR * 8);
-    const MCell<NPAIR> c = strip_ld<NPAIR>(h);
-    strip_st<NPAIR>(h, zero);
-#pragma unroll
-    for (int p = 0; p < NPAIR; ++p) t.v[p] = add2(t.v[p], c.v[p]);
+    const unsigned h = strips_addr + (unsigned)((((w - 1) * G::RING + rq) * G::SW + 32 + R + l) * MAcc<NS>::BYTES);
+    c.ld(h);
+    zero.st(h);
+    t.add(c);
   }
   if (l >= 32 - R && w < nwarps - 1) {
-    const unsigned h = strips_addr + (unsigned)((((w + 1) * G::RING + rq) * G::SW + l - 32 + R) * NPAIR * 8);
-    const MCell<NPAIR> c = strip_ld<NPAIR>(h);
-    strip_st<NPAIR>(h, zero);
-#pragma unroll
-    for (int p = 0; p < NPAIR; ++p) t.v[p] = add2(t.v[p], c.v[p]);
+    const unsigned h = strips_addr + (unsigned)((((w + 1) * G::RING + rq) * G::SW + l - 32 + R) * MAcc<NS>::BYTES);
+    c.ld(h);
+    zero.st(h);
+    t.add(c);
   }
   return t;
 }
 
-template <int TYPE, int R, int NPAIR, bool GRAD>
+template <int TYPE, int R, int NS, bool GRAD>
 __global__ void __maxnreg__(MARCH_MAX_REGS) pattern_march_kernel(PatternMarchArgs a) {
   static_assert(TYPE == CENSUS_MSE || TYPE == CENSUS_SAD, "pair symmetry is a property of the census types");
   static_assert(R >= 1, "a 1 x 1 window has no pairs");
+  static_assert(NS == 1 || NS == 2 || NS == 4, "1, 2 or 4 scales");
   using G = MarchGeom<R>;
-  constexpr int S = 2 * NPAIR;
+  constexpr int S = NS;
+  constexpr int NP = (NS + 1) / 2;          // packed words per staged cell
+  constexpr bool ET = (NS == 1);            // the packed pair is (estimate, target)
+  using Acc = MAcc<NS>;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int LW = blockDim.x, nwarps = LW >> 5;
   const int PITCH = LW + 2 * R;
   extern __shared__ __align__(16) unsigned char march_smem[];
-  u64* ring_e = reinterpret_cast<u64*>(march_smem);                                  // [RING][PITCH][NPAIR]
-  float2* ring_tw = reinterpret_cast<float2*>(ring_e + (size_t)G::RING * PITCH * NPAIR);  // [RING][PITCH] (t, w)
-  u64* strips = reinterpret_cast<u64*>(ring_tw + (size_t)G::RING * PITCH);           // [nwarps][RING][SW][NPAIR]
-  double* red = reinterpret_cast<double*>(strips + (size_t)nwarps * G::RING * G::SW * NPAIR);  // [nwarps][S+1]
+  u64* ring_e = reinterpret_cast<u64*>(march_smem);                                  // [RING][PITCH][NP]
+  float2* ring_tw = reinterpret_cast<float2*>(ring_e + (size_t)G::RING * PITCH * NP);     // [RING][PITCH] (t, w)
+  unsigned char* strips = reinterpret_cast<unsigned char*>(ring_tw + (size_t)G::RING * PITCH);   // [nwarps][RING][SW] Acc
+  const size_t strip_bytes = ((size_t)nwarps * G::RING * G::SW * Acc::BYTES + 15) / 16 * 16;
+  double* red = reinterpret_cast<double*>(strips + strip_bytes);                     // [nwarps][S+1]
   double* sums = red + nwarps * (S + 1);                                             // [S+1][LW]
 
   const int H = a.H, W = a.W;
@@ -274,17 +373,17 @@ __global__ void __maxnreg__(MARCH_MAX_REGS) pattern_march_kernel(PatternMarchArg
   const u64 eps2 = bc2(a.eps);
 
   // ---- one-time initialisation: zero strips, finite zero-weight padding cells of the ring --------------------
-  for (int i = tid; i < nwarps * G::RING * G::SW * NPAIR; i += LW) strips[i] = 0ull;
+  for (int i = tid; i < (int)(strip_bytes / 4); i += LW) reinterpret_cast<float*>(strips)[i] = 0.0f;
   for (int i = tid; i < G::RING * 2 * R; i += LW) {
     const int r = i / (2 * R), k = i - r * 2 * R;
     const int slot = r * PITCH + (k < R ? k : LW + k);
 #pragma unroll
-    for (int p = 0; p < NPAIR; ++p) ring_e[(size_t)slot * NPAIR + p] = 0ull;
+    for (int p = 0; p < NP; ++p) ring_e[(size_t)slot * NP + p] = 0ull;
     ring_tw[slot] = make_float2(0.0f, 0.0f);
   }
 
-  // Staging of one extended row in two halves: the streaming loads (issued a phase early so that their DRAM latency
-  // hides behind the pair arithmetic), then the pattern warp of every scale and the stores into the ring.
+  // Staging of one extended row in two halves: the streaming loads, then the pattern warp of every scale and the
+  // stores into the ring.
   struct Raw {
     float dv[S];
     float tv, wv;
@@ -306,20 +405,26 @@ __global__ void __maxnreg__(MARCH_MAX_REGS) pattern_march_kernel(PatternMarchArg
     const WarpRow row = warp_row_setup(y, H, W, a.inv_h);
     const float* prow0 = a.pattern + row.off0;
     const float* prow1 = a.pattern + row.off1;
-    const bool want_dd = GRAD && inside && col_own && er >= own_r0 && er < own_r1;
+    const bool own_px = inside && col_own && er >= own_r0 && er < own_r1;
+    const bool want_dd = GRAD && own_px;
     float ev[S], dd[S];
 #pragma unroll
     for (int s = 0; s < S; ++s)
       ev[s] = warp_col_sample_clamped(prow0, prow1, row.wy0, row.wy1, r.dv[s], x, W, a.inv_w, want_dd ? &dd[s] : nullptr);
     const int slot = (er % G::RING) * PITCH + R + tid;
+    if (ET) {
+      ring_e[slot] = pk2(ev[0], r.tv);
+    } else {
 #pragma unroll
-    for (int p = 0; p < NPAIR; ++p) ring_e[(size_t)slot * NPAIR + p] = pk2(ev[2 * p], ev[2 * p + 1]);
+      for (int p = 0; p < NP; ++p) ring_e[(size_t)slot * NP + p] = pk2(ev[2 * p], ev[2 * p + (NS > 1 ? 1 : 0)]);
+    }
     ring_tw[slot] = make_float2(r.tv, r.wv);
+    const size_t g = (size_t)y * W + x;
     if (want_dd) {
-      const size_t g = (size_t)y * W + x;
 #pragma unroll
       for (int s = 0; s < S; ++s) a.grad[s][fo + g] = dd[s] * gss[s];   // parked; multiplied by G(p) when the row retires
     }
+    if (ET && a.proj && own_px) a.proj[fo + g] = ev[0];
   };
 
   for (int er = row_start; er < row_start + R; ++er) finish_row(er, load_raw(er));
@@ -335,18 +440,17 @@ __global__ void __maxnreg__(MARCH_MAX_REGS) pattern_march_kernel(PatternMarchArg
   for (int s = 0; s <= S; ++s) my_sums[s * LW] = 0.0;
   // vertical fold: first the top virtual rows (added to image row 0, then reset), later image row H-1 plus the
   // virtual rows below it -- never both at once (H >= 2), so one accumulator serves both
-  MCell<NPAIR> facc;
-#pragma unroll
-  for (int p = 0; p < NPAIR; ++p) facc.v[p] = 0ull;
+  Acc facc;
+  facc.zero();
   const unsigned strips_addr = (unsigned)__cvta_generic_to_shared(strips);
-  const unsigned my_strip = strips_addr + (unsigned)((wid * G::RING * G::SW + lane + R) * NPAIR * 8);
-  constexpr unsigned STRIP_ROW_BYTES = G::SW * NPAIR * 8;
+  const unsigned my_strip = strips_addr + (unsigned)((wid * G::RING * G::SW + lane + R) * Acc::BYTES);
+  constexpr unsigned STRIP_ROW_BYTES = G::SW * Acc::BYTES;
 
 #pragma unroll 1
   for (int step = 0; step < nsteps; ++step) {
     const int ys = row_start + step * MV;
     const int r0 = ys % G::RING;
-    // ---- the MV new rows of this step enter the ring (their streaming loads were issued a step ago) --------------
+    // ---- the MV new rows of this step enter the ring ---------------------------------------------------------
     if (!DIS_MARCH_PREFETCH) {
 #pragma unroll
       for (int i = 0; i < MV; ++i) raw[i] = load_raw(ys + R + i);
@@ -359,7 +463,8 @@ __global__ void __maxnreg__(MARCH_MAX_REGS) pattern_march_kernel(PatternMarchArg
       for (int i = 0; i < MV; ++i) raw[i] = load_raw(ys + MV + R + i);
     }
 
-    MCell<NPAIR> pe[MV], gp[MV];
+    MCell<NP> pe[MV];
+    Acc gp[MV];
     float ptc[MV], pwc[MV];
     float acc[S];
 #pragma unroll
@@ -369,36 +474,38 @@ __global__ void __maxnreg__(MARCH_MAX_REGS) pattern_march_kernel(PatternMarchArg
       int rq = r0 + i;
       if (rq >= G::RING) rq -= G::RING;
       const int slot = rq * PITCH + R + tid;
-      pe[i] = mcell_load<NPAIR>(ring_e + (size_t)slot * NPAIR);
+      pe[i] = mcell_load<NP>(ring_e + (size_t)slot * NP);
       const float2 tw = ring_tw[slot];
       ptc[i] = tw.x;
       pwc[i] = tw.y;
-#pragma unroll
-      for (int p = 0; p < NPAIR; ++p) gp[i].v[p] = 0ull;
+      gp[i].zero();
     }
     const u64 tc2 = pk2(ptc[0], ptc[1]), wc2 = pk2(pwc[0], pwc[1]);
     float stash[MV][S];     // d proj / d disp x constants of my two pixels, parked in the gradient buffer at staging
     int stash_at[MV];
 
-    // one cell q = (row ys + j, column + dx); P0 / P1: which of my two pixels pair with it.  The cell loops are kept
-    // rolled (MARCH_UNROLL cells per iteration): the fully unrolled step is ~70 KB of code and 21 warps at different
-    // places in it thrash the instruction cache (ncu: 34 % "no instruction" stalls in the staging phase).
+    // one cell q = (row ys + j, column + dx); P0 / P1: which of my two pixels pair with it.
     auto cell = [&](int rq, int dx, auto p0_tag, auto p1_tag) __attribute__((always_inline)) {
       constexpr bool P0 = decltype(p0_tag)::value, P1 = decltype(p1_tag)::value;
       const int slot = rq * PITCH + R + tid + dx;
-      const unsigned c = my_strip + (unsigned)rq * STRIP_ROW_BYTES + dx * (NPAIR * 8);
-      MCell<NPAIR> cur;
-      if (GRAD) cur = strip_ld<NPAIR>(c);     // issued first: its latency hides behind the pair arithmetic
-      const MCell<NPAIR> eq = mcell_load<NPAIR>(ring_e + (size_t)slot * NPAIR);
+      const unsigned c = my_strip + (unsigned)rq * STRIP_ROW_BYTES + dx * Acc::BYTES;
+      Acc cur;
+      if (GRAD) cur.ld(c);     // issued first: its latency hides behind the pair arithmetic
+      const MCell<NP> eq = mcell_load<NP>(ring_e + (size_t)slot * NP);
       const float2 tw = ring_tw[slot];
-      MCell<NPAIR> cs;
-      if (P0 && P1) march_pair2<TYPE, NPAIR, GRAD>(pe[0], pe[1], tc2, wc2, eq, tw.x, tw.y, eps2, acc, gp[0], gp[1], cs);
-      else if (P0) march_pair1<TYPE, NPAIR, GRAD>(pe[0], ptc[0], pwc[0], eq, tw.x, tw.y, a.eps, eps2, acc, gp[0], cs);
-      else march_pair1<TYPE, NPAIR, GRAD>(pe[1], ptc[1], pwc[1], eq, tw.x, tw.y, a.eps, eps2, acc, gp[1], cs);
+      Acc cs;
+      if constexpr (ET) {
+        if (P0 && P1) march_et_pair2<TYPE, GRAD>(pe[0].v[0], pe[1].v[0], wc2, eq.v[0], tw.y, eps2, acc[0], gp[0], gp[1], cs);
+        else if (P0) march_et_pair1<TYPE, GRAD>(pe[0].v[0], pwc[0], eq.v[0], tw.y, eps2, acc[0], gp[0], cs);
+        else march_et_pair1<TYPE, GRAD>(pe[1].v[0], pwc[1], eq.v[0], tw.y, eps2, acc[0], gp[1], cs);
+      } else {
+        if (P0 && P1) march_pair2<TYPE, NS, GRAD>(pe[0], pe[1], tc2, wc2, eq, tw.x, tw.y, eps2, acc, gp[0], gp[1], cs);
+        else if (P0) march_pair1<TYPE, NS, GRAD>(pe[0], ptc[0], pwc[0], eq, tw.x, tw.y, a.eps, eps2, acc, gp[0], cs);
+        else march_pair1<TYPE, NS, GRAD>(pe[1], ptc[1], pwc[1], eq, tw.x, tw.y, a.eps, eps2, acc, gp[1], cs);
+      }
       if (GRAD) {
-#pragma unroll
-        for (int p = 0; p < NPAIR; ++p) cur.v[p] = sub2(cur.v[p], cs.v[p]);
-        strip_st<NPAIR>(c, cur);
+        cur.sub(cs);
+        cur.st(c);
 #if DIS_MARCH_SYNCWARP
         __syncwarp();   // memory-model form of the hand-over to the neighbour lane (the LSU already keeps the order)
 #endif
@@ -438,13 +545,11 @@ __global__ void __maxnreg__(MARCH_MAX_REGS) pattern_march_kernel(PatternMarchArg
     if (GRAD) {  // my own pixels' p-side sums join the strip
 #pragma unroll
       for (int i = 0; i < MV; ++i) {
-        int rq = r0 + i;
-        if (rq >= G::RING) rq -= G::RING;
-        const unsigned c = my_strip + (unsigned)rq * STRIP_ROW_BYTES;
-        MCell<NPAIR> cur = strip_ld<NPAIR>(c);
-#pragma unroll
-        for (int p = 0; p < NPAIR; ++p) cur.v[p] = add2(cur.v[p], gp[i].v[p]);
-        strip_st<NPAIR>(c, cur);
+        const unsigned c = my_strip + (unsigned)ring_row(i) * STRIP_ROW_BYTES;
+        Acc cur;
+        cur.ld(c);
+        cur.add(gp[i]);
+        cur.st(c);
       }
     }
     auto load_stash = [&]() __attribute__((always_inline)) {
@@ -471,52 +576,33 @@ __global__ void __maxnreg__(MARCH_MAX_REGS) pattern_march_kernel(PatternMarchArg
 #pragma unroll
       for (int i = 0; i < MV; ++i) {
         const int er = ys + i;
-        int rq = r0 + i;
-        if (rq >= G::RING) rq -= G::RING;
+        const int rq = ring_row(i);
         const bool row_own = er >= own_r0 && er < own_r1;
         if (row_own) my_sums[S * LW] += (double)ring_tw[rq * PITCH + R + tid].y;
         if (GRAD) {
-          MCell<NPAIR> t = strip_collect<R, NPAIR>(strips_addr, tid, rq, nwarps);
+          Acc t = strip_collect<R, NS>(strips_addr, tid, rq, nwarps);
           if (ec == R) {  // left border column: virtual columns 0 .. R-1 fold onto it
-            for (int k = 0; k < R; ++k) {
-              const MCell<NPAIR> c = strip_collect<R, NPAIR>(strips_addr, tid - R + k, rq, nwarps);
-#pragma unroll
-              for (int p = 0; p < NPAIR; ++p) t.v[p] = add2(t.v[p], c.v[p]);
-            }
+            for (int k = 0; k < R; ++k) t.add(strip_collect<R, NS>(strips_addr, tid - R + k, rq, nwarps));
           }
           if (ec == EW - R - 1) {  // right border column
-            for (int k = 1; k <= R; ++k) {
-              const MCell<NPAIR> c = strip_collect<R, NPAIR>(strips_addr, tid + k, rq, nwarps);
-#pragma unroll
-              for (int p = 0; p < NPAIR; ++p) t.v[p] = add2(t.v[p], c.v[p]);
-            }
+            for (int k = 1; k <= R; ++k) t.add(strip_collect<R, NS>(strips_addr, tid + k, rq, nwarps));
           }
           if (row_own) {
             bool emit = true;
             if (er < R) {                      // top virtual row
-#pragma unroll
-              for (int p = 0; p < NPAIR; ++p) facc.v[p] = add2(facc.v[p], t.v[p]);
+              facc.add(t);
               emit = false;
             } else if (er >= EH - R - 1) {     // image row H-1 and the virtual rows below it
-#pragma unroll
-              for (int p = 0; p < NPAIR; ++p) facc.v[p] = add2(facc.v[p], t.v[p]);
+              facc.add(t);
               emit = (er == EH - 1);
               t = facc;
             } else if (er == R) {              // image row 0
-#pragma unroll
-              for (int p = 0; p < NPAIR; ++p) {
-                t.v[p] = add2(t.v[p], facc.v[p]);
-                facc.v[p] = 0ull;
-              }
+              t.add(facc);
+              facc.zero();
             }
             if (emit) {
 #pragma unroll
-              for (int p = 0; p < NPAIR; ++p) {
-                float t0, t1;
-                upk2(t.v[p], t0, t1);
-                a.grad[2 * p][fo + stash_at[i]] = t0 * stash[i][2 * p];
-                a.grad[2 * p + 1][fo + stash_at[i]] = t1 * stash[i][2 * p + 1];
-              }
+              for (int s = 0; s < S; ++s) a.grad[s][fo + stash_at[i]] = t.get(s) * stash[i][s];
             }
           }
         }

@@ -113,20 +113,29 @@ int pattern_multi_t(const PatternMultiArgs& a, cudaStream_t s) {
 }
 
 #if DIS_R >= 1
-template <int TYPE, int R, int NPAIR>
+template <int TYPE, int R, int NS>
 int pattern_march_t(const PatternMarchArgs& a, const MarchPlan& plan, cudaStream_t s) {
   const dim3 block(32 * plan.nwarps);
   const dim3 grid(plan.ncb, plan.nrb, a.N);
-  const size_t smem = pattern_march_smem_bytes<R, NPAIR>(plan.nwarps);
-  const size_t smem_max = pattern_march_smem_bytes<R, NPAIR>(MARCH_MAX_WARPS);   // the opt-in is made once per kernel
+  const size_t smem = pattern_march_smem_bytes<R, NS>(plan.nwarps);
+  const size_t smem_max = pattern_march_smem_bytes<R, NS>(MARCH_MAX_WARPS);   // the opt-in is made once per kernel
   if (a.grad[0]) {
-    if (int rc = prepare(pattern_march_kernel<TYPE, R, NPAIR, true>, smem_max)) return rc;
-    pattern_march_kernel<TYPE, R, NPAIR, true><<<grid, block, smem, s>>>(a);
+    if (int rc = prepare(pattern_march_kernel<TYPE, R, NS, true>, smem_max)) return rc;
+    pattern_march_kernel<TYPE, R, NS, true><<<grid, block, smem, s>>>(a);
   } else {
-    if (int rc = prepare(pattern_march_kernel<TYPE, R, NPAIR, false>, smem_max)) return rc;
-    pattern_march_kernel<TYPE, R, NPAIR, false><<<grid, block, smem, s>>>(a);
+    if (int rc = prepare(pattern_march_kernel<TYPE, R, NS, false>, smem_max)) return rc;
+    pattern_march_kernel<TYPE, R, NS, false><<<grid, block, smem, s>>>(a);
   }
   return check_launch();
+}
+template <int TYPE, int R>
+int pattern_march_s(const PatternMarchArgs& a, const MarchPlan& plan, int S, cudaStream_t s) {
+  switch (S) {
+    case 1: return pattern_march_t<TYPE, R, 1>(a, plan, s);
+    case 2: return pattern_march_t<TYPE, R, 2>(a, plan, s);
+    case 4: return pattern_march_t<TYPE, R, 4>(a, plan, s);
+  }
+  return DIS_ERR_UNSUPPORTED_COMBINATION;
 }
 #endif
 
@@ -135,8 +144,8 @@ int pattern_march_t(const PatternMarchArgs& a, const MarchPlan& plan, cudaStream
 template <>
 int launch_pattern_march<DIS_R>(const PatternMarchArgs& a, const MarchPlan& plan, int S, int type, cudaStream_t s) {
 #if DIS_R >= 1
-  if (type == CENSUS_SAD) return S == 4 ? pattern_march_t<CENSUS_SAD, DIS_R, 2>(a, plan, s) : pattern_march_t<CENSUS_SAD, DIS_R, 1>(a, plan, s);
-  if (type == CENSUS_MSE) return S == 4 ? pattern_march_t<CENSUS_MSE, DIS_R, 2>(a, plan, s) : pattern_march_t<CENSUS_MSE, DIS_R, 1>(a, plan, s);
+  if (type == CENSUS_SAD) return pattern_march_s<CENSUS_SAD, DIS_R>(a, plan, S, s);
+  if (type == CENSUS_MSE) return pattern_march_s<CENSUS_MSE, DIS_R>(a, plan, S, s);
 #endif
   return DIS_ERR_UNSUPPORTED_COMBINATION;
 }
