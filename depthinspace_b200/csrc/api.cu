@@ -134,6 +134,19 @@ int dispatch_pattern_march(int R, const PatternMarchArgs& a, const MarchPlan& pl
   return DIS_ERR_UNSUPPORTED_BLOCK_SIZE;
 }
 
+int dispatch_photometric_march(int R, const PatternMarchArgs& a, const MarchPlan& plan, int mode, int type, cudaStream_t s) {
+  switch (R) {
+    case 1: return launch_photometric_march<1>(a, plan, mode, type, s);
+    case 2: return launch_photometric_march<2>(a, plan, mode, type, s);
+    case 3: return launch_photometric_march<3>(a, plan, mode, type, s);
+    case 4: return launch_photometric_march<4>(a, plan, mode, type, s);
+    case 5: return launch_photometric_march<5>(a, plan, mode, type, s);
+    case 6: return launch_photometric_march<6>(a, plan, mode, type, s);
+    case 7: return launch_photometric_march<7>(a, plan, mode, type, s);
+  }
+  return DIS_ERR_UNSUPPORTED_BLOCK_SIZE;
+}
+
 // Tuning / A-B knobs, read per call (no cached state): DIS_MULTI_IMPL=tile selects the round-1 tile kernel,
 // DIS_MARCH_BAND_ROWS / DIS_MARCH_WARPS override the band plan.
 int env_int(const char* name, int dflt) {
@@ -321,6 +334,19 @@ int dis_photometric_loss_forward(const float* es, const float* ta, float* out, i
   if (N < 0 || C < 1 || H < 1 || W < 1) return DIS_ERR_BAD_SHAPE;
   if (N == 0) return DIS_OK;
   const size_t hw = (size_t)H * W;
+  if (type >= CENSUS_MSE && C == 1 && H >= 2 && W >= 2 && use_march(block_size / 2)) {   // pair-symmetric marching kernel
+    const MarchPlan plan = march_plan(N, H, W, block_size / 2);
+    for (int n0 = 0; n0 < N; n0 += MAX_GRID_Z) {
+      PatternMarchArgs a{};
+      a.es = es + (size_t)n0 * hw; a.im = ta + (size_t)n0 * hw; a.out = out + (size_t)n0 * hw;
+      a.grad[0] = a.out;        // (non-null: selects the strip path)
+      a.N = N - n0 < MAX_GRID_Z ? N - n0 : MAX_GRID_Z; a.H = H; a.W = W;
+      a.ncb = plan.ncb; a.nrb = plan.nrb; a.band_rows = plan.band_rows;
+      a.eps = eps; a.inv_k2 = 1.0f / (float)(block_size * block_size);
+      if (int rc = dispatch_photometric_march(block_size / 2, a, plan, MARCH_MAP, type, as_stream(stream))) return rc;
+    }
+    return DIS_OK;
+  }
   for (int n0 = 0; n0 < N; n0 += MAX_GRID_Z) {
     PhotoArgs a{};
     a.es = es + (size_t)n0 * C * hw; a.ta = ta + (size_t)n0 * C * hw; a.out = out + (size_t)n0 * hw;
@@ -339,6 +365,19 @@ int dis_photometric_loss_backward(const float* es, const float* ta, const float*
   if (N < 0 || C < 1 || H < 1 || W < 1 || C > MAX_GRID_Z) return DIS_ERR_BAD_SHAPE;
   if (N == 0) return DIS_OK;
   const size_t hw = (size_t)H * W;
+  if (type >= CENSUS_MSE && C == 1 && H >= 2 && W >= 2 && use_march(block_size / 2)) {
+    const MarchPlan plan = march_plan(N, H, W, block_size / 2);
+    for (int n0 = 0; n0 < N; n0 += MAX_GRID_Z) {
+      PatternMarchArgs a{};
+      a.es = es + (size_t)n0 * hw; a.im = ta + (size_t)n0 * hw; a.std_in = grad_out + (size_t)n0 * hw;
+      a.grad[0] = grad_es + (size_t)n0 * hw;
+      a.N = N - n0 < MAX_GRID_Z ? N - n0 : MAX_GRID_Z; a.H = H; a.W = W;
+      a.ncb = plan.ncb; a.nrb = plan.nrb; a.band_rows = plan.band_rows;
+      a.eps = eps; a.inv_k2 = 1.0f / (float)(block_size * block_size);
+      if (int rc = dispatch_photometric_march(block_size / 2, a, plan, MARCH_GRAD_E, type, as_stream(stream))) return rc;
+    }
+    return DIS_OK;
+  }
   const int step = MAX_GRID_Z / C;
   for (int n0 = 0; n0 < N; n0 += step) {
     PhotoArgs a{};

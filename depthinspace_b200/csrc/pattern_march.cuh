@@ -65,6 +65,8 @@ struct PatternMarchArgs {
   const float* disp[4];
   float* grad[4];          // all NULL => forward only
   float* proj;             // optional (NS == 1 only): the warped pattern [N,1,H,W] (model/networks.py:367)
+  const float* es;         // MODE 1 / 2: the estimate plane itself (no pattern warp); im = target, std_in = upstream weights
+  float* out;              // MODE 1: the per-pixel loss map [N,1,H,W]
   const float* im;
   const float* std_in;
   const float* pattern;
@@ -234,7 +236,8 @@ __device__ __forceinline__ void march_pair2(const MCell<NS / 2>& ec0, const MCel
 
 // ---- NS = 1: the cell is the packed pair (estimate, target); both sides of the soft census share every instruction.
 // The two products d * r are rounded separately (one FMUL2) before they are subtracted, so e == t gives exactly 0.
-template <int TYPE, bool GRAD>
+// MAP: instead of the weighted loss sum and its gradient, the tap value itself goes to both pixels (per-pixel loss map).
+template <int TYPE, bool GRAD, bool MAP = false>
 __device__ __forceinline__ void march_et_pair1(u64 c_et, float wc, u64 q_et, float wq, u64 eps2, float& acc, MAcc<1>& gp,
                                                MAcc<1>& cell) {
   const u64 d = sub2(q_et, c_et);
@@ -245,6 +248,12 @@ __device__ __forceinline__ void march_et_pair1(u64 c_et, float wc, u64 q_et, flo
   float pe, pt;
   upk2(mul2(d, pk2(re, rt)), pe, pt);
   const float diff = __fsub_rn(pe, pt);
+  if (MAP) {
+    const float f = (TYPE == CENSUS_SAD) ? fabsf(diff) : diff * diff;
+    gp.v += f;
+    cell.v = f;
+    return;
+  }
   const float ws = wq + wc;
   acc = (TYPE == CENSUS_SAD) ? fmaf(fabsf(diff), ws, acc) : fmaf(diff * diff, ws, acc);
   if (GRAD) {
@@ -255,7 +264,7 @@ __device__ __forceinline__ void march_et_pair1(u64 c_et, float wc, u64 q_et, flo
     cell.v = v;
   }
 }
-template <int TYPE, bool GRAD>
+template <int TYPE, bool GRAD, bool MAP = false>
 __device__ __forceinline__ void march_et_pair2(u64 c0_et, u64 c1_et, u64 wc2, u64 q_et, float wq, u64 eps2, float& acc,
                                                MAcc<1>& gp0, MAcc<1>& gp1, MAcc<1>& cell) {
   const u64 d0 = sub2(q_et, c0_et), d1 = sub2(q_et, c1_et);
@@ -268,6 +277,14 @@ __device__ __forceinline__ void march_et_pair2(u64 c0_et, u64 c1_et, u64 wc2, u6
   upk2(mul2(d0, pk2(re0, rt0)), pe0, pt0);
   upk2(mul2(d1, pk2(re1, rt1)), pe1, pt1);
   const float diff0 = __fsub_rn(pe0, pt0), diff1 = __fsub_rn(pe1, pt1);
+  if (MAP) {
+    const float f0 = (TYPE == CENSUS_SAD) ? fabsf(diff0) : diff0 * diff0;
+    const float f1 = (TYPE == CENSUS_SAD) ? fabsf(diff1) : diff1 * diff1;
+    gp0.v += f0;
+    gp1.v += f1;
+    cell.v = f0 + f1;
+    return;
+  }
   const u64 ws2 = add2(bc2(wq), wc2);
   float ws0, ws1;
   upk2(ws2, ws0, ws1);
@@ -323,11 +340,19 @@ __device__ __forceinline__ MAcc<NS> strip_collect(unsigned strips_addr, int P, i
   return t;
 }
 
-template <int TYPE, int R, int NS, bool GRAD>
+// MODE 0: fused pattern loss (pattern warp by `disp`, sigma-weighted sums, d/d disp).
+// MODE 1 / 2 (NS == 1): the ext boundary ops on given planes es / ta (C == 1), reference model/ext_functions.py:115-140:
+//   1  photometric_loss_forward:  the per-pixel loss map (no weights, nothing folded: virtual pixels have no output)
+//   2  photometric_loss_backward: d/d es for upstream weights grad_out (in the `std_in` slot), written to grad[0]
+constexpr int MARCH_FUSED = 0, MARCH_MAP = 1, MARCH_GRAD_E = 2;
+
+template <int TYPE, int R, int NS, bool GRAD, int MODE = MARCH_FUSED>
 __global__ void __maxnreg__(MARCH_MAX_REGS) pattern_march_kernel(PatternMarchArgs a) {
   static_assert(TYPE == CENSUS_MSE || TYPE == CENSUS_SAD, "pair symmetry is a property of the census types");
   static_assert(R >= 1, "a 1 x 1 window has no pairs");
   static_assert(NS == 1 || NS == 2 || NS == 4, "1, 2 or 4 scales");
+  static_assert(MODE == MARCH_FUSED || (NS == 1 && GRAD), "the ext modes work on one plane and use the strips");
+  constexpr bool MAP = (MODE == MARCH_MAP);
   using G = MarchGeom<R>;
   constexpr int S = NS;
   constexpr int NP = (NS + 1) / 2;          // packed words per staged cell
@@ -394,9 +419,9 @@ __global__ void __maxnreg__(MARCH_MAX_REGS) pattern_march_kernel(PatternMarchArg
     const size_t g = (size_t)y * W + x;
     Raw r;
 #pragma unroll
-    for (int s = 0; s < S; ++s) r.dv[s] = __ldg(a.disp[s] + fo + g);
+    for (int s = 0; s < S; ++s) r.dv[s] = __ldg((MODE == MARCH_FUSED ? a.disp[s] : a.es) + fo + g);
     r.tv = __ldg(a.im + fo + g);
-    r.wv = inside ? (a.std_in ? __ldg(a.std_in + fo + g) : 1.0f) : 0.0f;
+    r.wv = (inside && !MAP) ? (a.std_in ? __ldg(a.std_in + fo + g) : 1.0f) : 0.0f;
     return r;
   };
   auto finish_row = [&](int er, const Raw& r) __attribute__((always_inline)) {
@@ -406,11 +431,12 @@ __global__ void __maxnreg__(MARCH_MAX_REGS) pattern_march_kernel(PatternMarchArg
     const float* prow0 = a.pattern + row.off0;
     const float* prow1 = a.pattern + row.off1;
     const bool own_px = inside && col_own && er >= own_r0 && er < own_r1;
-    const bool want_dd = GRAD && own_px;
+    const bool want_dd = GRAD && own_px && MODE == MARCH_FUSED;
     float ev[S], dd[S];
 #pragma unroll
     for (int s = 0; s < S; ++s)
-      ev[s] = warp_col_sample_clamped(prow0, prow1, row.wy0, row.wy1, r.dv[s], x, W, a.inv_w, want_dd ? &dd[s] : nullptr);
+      ev[s] = MODE == MARCH_FUSED ? warp_col_sample_clamped(prow0, prow1, row.wy0, row.wy1, r.dv[s], x, W, a.inv_w, want_dd ? &dd[s] : nullptr)
+                                  : r.dv[s];
     const int slot = (er % G::RING) * PITCH + R + tid;
     if (ET) {
       ring_e[slot] = pk2(ev[0], r.tv);
@@ -424,7 +450,7 @@ __global__ void __maxnreg__(MARCH_MAX_REGS) pattern_march_kernel(PatternMarchArg
 #pragma unroll
       for (int s = 0; s < S; ++s) a.grad[s][fo + g] = dd[s] * gss[s];   // parked; multiplied by G(p) when the row retires
     }
-    if (ET && a.proj && own_px) a.proj[fo + g] = ev[0];
+    if (ET && MODE == MARCH_FUSED && a.proj && own_px) a.proj[fo + g] = ev[0];
   };
 
   for (int er = row_start; er < row_start + R; ++er) finish_row(er, load_raw(er));
@@ -495,16 +521,17 @@ __global__ void __maxnreg__(MARCH_MAX_REGS) pattern_march_kernel(PatternMarchArg
       const float2 tw = ring_tw[slot];
       Acc cs;
       if constexpr (ET) {
-        if (P0 && P1) march_et_pair2<TYPE, GRAD>(pe[0].v[0], pe[1].v[0], wc2, eq.v[0], tw.y, eps2, acc[0], gp[0], gp[1], cs);
-        else if (P0) march_et_pair1<TYPE, GRAD>(pe[0].v[0], pwc[0], eq.v[0], tw.y, eps2, acc[0], gp[0], cs);
-        else march_et_pair1<TYPE, GRAD>(pe[1].v[0], pwc[1], eq.v[0], tw.y, eps2, acc[0], gp[1], cs);
+        if (P0 && P1) march_et_pair2<TYPE, GRAD, MAP>(pe[0].v[0], pe[1].v[0], wc2, eq.v[0], tw.y, eps2, acc[0], gp[0], gp[1], cs);
+        else if (P0) march_et_pair1<TYPE, GRAD, MAP>(pe[0].v[0], pwc[0], eq.v[0], tw.y, eps2, acc[0], gp[0], cs);
+        else march_et_pair1<TYPE, GRAD, MAP>(pe[1].v[0], pwc[1], eq.v[0], tw.y, eps2, acc[0], gp[1], cs);
       } else {
         if (P0 && P1) march_pair2<TYPE, NS, GRAD>(pe[0], pe[1], tc2, wc2, eq, tw.x, tw.y, eps2, acc, gp[0], gp[1], cs);
         else if (P0) march_pair1<TYPE, NS, GRAD>(pe[0], ptc[0], pwc[0], eq, tw.x, tw.y, a.eps, eps2, acc, gp[0], cs);
         else march_pair1<TYPE, NS, GRAD>(pe[1], ptc[1], pwc[1], eq, tw.x, tw.y, a.eps, eps2, acc, gp[1], cs);
       }
       if (GRAD) {
-        cur.sub(cs);
+        if (MAP) cur.add(cs);      // the tap value goes to both pixels; the gradient is antisymmetric
+        else cur.sub(cs);
         cur.st(c);
 #if DIS_MARCH_SYNCWARP
         __syncwarp();   // memory-model form of the hand-over to the neighbour lane (the LSU already keeps the order)
@@ -563,24 +590,29 @@ __global__ void __maxnreg__(MARCH_MAX_REGS) pattern_march_kernel(PatternMarchArg
           stash[i][s] = (out_lane && er >= own_r0 && er < own_r1 && er >= R) ? a.grad[s][fo + stash_at[i]] : 0.0f;
       }
     };
-    if (GRAD && DIS_MARCH_STASH_EARLY) load_stash();   // L2 hits, in flight across the barrier
-    if (ys >= own_r0) {  // pairs are counted by the band that owns p (halo steps only feed the strips)
+    if (GRAD && DIS_MARCH_STASH_EARLY && MODE == MARCH_FUSED) load_stash();   // L2 hits, in flight across the barrier
+    if (MODE == MARCH_FUSED && ys >= own_r0) {  // pairs are counted by the band that owns p (halo steps only feed the strips)
 #pragma unroll
       for (int s = 0; s < S; ++s) my_sums[s * LW] += (double)acc[s];
     }
     __syncthreads();
 
     // ---- rows ys, ys + 1 retire: merge strips, fold virtual pixels, write the gradient ------------------------
-    if (GRAD && !DIS_MARCH_STASH_EARLY) load_stash();
+    if (GRAD && !DIS_MARCH_STASH_EARLY && MODE == MARCH_FUSED) load_stash();
     if (out_lane) {
 #pragma unroll
       for (int i = 0; i < MV; ++i) {
         const int er = ys + i;
         const int rq = ring_row(i);
         const bool row_own = er >= own_r0 && er < own_r1;
-        if (row_own) my_sums[S * LW] += (double)ring_tw[rq * PITCH + R + tid].y;
+        if (MODE == MARCH_FUSED && row_own) my_sums[S * LW] += (double)ring_tw[rq * PITCH + R + tid].y;
         if (GRAD) {
           Acc t = strip_collect<R, NS>(strips_addr, tid, rq, nwarps);
+          if (MAP) {      // loss map: real pixels only, nothing to fold
+            if (row_own && er >= R && er < EH - R)
+              a.out[fo + (size_t)(er - R) * W + x] = t.get(0) * (fwd_scale<TYPE>() * a.inv_k2);
+            continue;
+          }
           if (ec == R) {  // left border column: virtual columns 0 .. R-1 fold onto it
             for (int k = 0; k < R; ++k) t.add(strip_collect<R, NS>(strips_addr, tid - R + k, rq, nwarps));
           }
@@ -601,8 +633,13 @@ __global__ void __maxnreg__(MARCH_MAX_REGS) pattern_march_kernel(PatternMarchArg
               facc.zero();
             }
             if (emit) {
+              if (MODE == MARCH_GRAD_E) {
+                const int y = er >= EH - R - 1 ? H - 1 : er - R;
+                a.grad[0][fo + (size_t)y * W + x] = t.get(0) * gs;
+              } else {
 #pragma unroll
-              for (int s = 0; s < S; ++s) a.grad[s][fo + stash_at[i]] = t.get(s) * stash[i][s];
+                for (int s = 0; s < S; ++s) a.grad[s][fo + stash_at[i]] = t.get(s) * stash[i][s];
+              }
             }
           }
         }
@@ -612,6 +649,7 @@ __global__ void __maxnreg__(MARCH_MAX_REGS) pattern_march_kernel(PatternMarchArg
     //  before the barrier above; strip rows ys, ys+1 are written again only after the barrier that follows the next staging)
   }
 
+  if (MODE != MARCH_FUSED) return;
   // ---- CTA reduction of S numerators + the denominator (fixed order) ------------------------------------------
   const double fs = (double)(fwd_scale<TYPE>() * a.inv_k2);
 #pragma unroll
@@ -654,5 +692,7 @@ struct MarchPlan {
 MarchPlan march_plan(int N, int H, int W, int R);
 
 template <int R> int launch_pattern_march(const PatternMarchArgs& a, const MarchPlan& plan, int S, int type, cudaStream_t s);
+// ext boundary ops (model/ext_functions.py:115-140) on planes es / ta, C == 1: mode MARCH_MAP or MARCH_GRAD_E
+template <int R> int launch_photometric_march(const PatternMarchArgs& a, const MarchPlan& plan, int mode, int type, cudaStream_t s);
 
 }  // namespace dis

@@ -128,6 +128,15 @@ int pattern_march_t(const PatternMarchArgs& a, const MarchPlan& plan, cudaStream
   }
   return check_launch();
 }
+template <int TYPE, int R, int MODE>
+int photometric_march_t(const PatternMarchArgs& a, const MarchPlan& plan, cudaStream_t s) {
+  const dim3 block(32 * plan.nwarps);
+  const dim3 grid(plan.ncb, plan.nrb, a.N);
+  const size_t smem = pattern_march_smem_bytes<R, 1>(plan.nwarps);
+  if (int rc = prepare(pattern_march_kernel<TYPE, R, 1, true, MODE>, pattern_march_smem_bytes<R, 1>(MARCH_MAX_WARPS))) return rc;
+  pattern_march_kernel<TYPE, R, 1, true, MODE><<<grid, block, smem, s>>>(a);
+  return check_launch();
+}
 template <int TYPE, int R>
 int pattern_march_s(const PatternMarchArgs& a, const MarchPlan& plan, int S, cudaStream_t s) {
   switch (S) {
@@ -146,6 +155,17 @@ int launch_pattern_march<DIS_R>(const PatternMarchArgs& a, const MarchPlan& plan
 #if DIS_R >= 1
   if (type == CENSUS_SAD) return pattern_march_s<CENSUS_SAD, DIS_R>(a, plan, S, s);
   if (type == CENSUS_MSE) return pattern_march_s<CENSUS_MSE, DIS_R>(a, plan, S, s);
+#endif
+  return DIS_ERR_UNSUPPORTED_COMBINATION;
+}
+
+template <>
+int launch_photometric_march<DIS_R>(const PatternMarchArgs& a, const MarchPlan& plan, int mode, int type, cudaStream_t s) {
+#if DIS_R >= 1
+  if (type == CENSUS_SAD)
+    return mode == MARCH_MAP ? photometric_march_t<CENSUS_SAD, DIS_R, MARCH_MAP>(a, plan, s) : photometric_march_t<CENSUS_SAD, DIS_R, MARCH_GRAD_E>(a, plan, s);
+  if (type == CENSUS_MSE)
+    return mode == MARCH_MAP ? photometric_march_t<CENSUS_MSE, DIS_R, MARCH_MAP>(a, plan, s) : photometric_march_t<CENSUS_MSE, DIS_R, MARCH_GRAD_E>(a, plan, s);
 #endif
   return DIS_ERR_UNSUPPORTED_COMBINATION;
 }
