@@ -50,3 +50,11 @@ def test_gpu_arm_prints_the_contract_line():
     rf = d["roofline"]
     assert rf["bound"] == "hbm" and rf["unit"] == "GB/s" and abs(rf["frac"] - rf["achieved"] / rf["peak"]) < 1e-9
     assert {"sm_mhz", "sm_max_mhz", "reasons"} <= set(d["clocks"])
+    # round 2: the headline is the module path, the fused entry sits beside it; the roofline names its compute limiters
+    assert d["value_and_grad"]["value"] > 0 and d["value_and_grad"]["ms_per_step"] > 0
+    assert rf["traffic"] is None or rf["traffic"] > 0.5 * rf["algorithmic_bytes"]
+    assert rf["xu_frac"] is None or 0 < rf["xu_frac"] < 1
+    assert rf["issue_frac"] is None or 0 < rf["issue_frac"] < 1
+    lo = d["e2e"]["loader_inputs_only"]
+    assert lo["value"] >= d["e2e"]["value"] * 0.9 and lo["h2d_bytes_per_step"] == 2 * 4 * 512 * 432 * 64
+    assert d["strong"] is None and "forward() + backward()" in d["config"]["workload"]
