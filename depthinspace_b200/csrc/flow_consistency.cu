@@ -98,7 +98,9 @@ __global__ void __launch_bounds__(256, 4) flow_consistency_kernel(FCArgs a) {
     CornerIdx ci;
     ci.in[0] = in_bounds(b.y0, b.x0, a.H, a.W); ci.in[1] = in_bounds(b.y0, b.x0 + 1, a.H, a.W);
     ci.in[2] = in_bounds(b.y0 + 1, b.x0, a.H, a.W); ci.in[3] = in_bounds(b.y0 + 1, b.x0 + 1, a.H, a.W);
-    ci.o[0] = b.y0 * a.W + b.x0; ci.o[1] = ci.o[0] + 1; ci.o[2] = ci.o[0] + a.W; ci.o[3] = ci.o[2] + 1;
+    // (corner offsets from coordinates clamped to [-1, size]: identical for every corner that passes the predicate, and no
+    //  int overflow for garbage flows whose y0 * W would not fit)
+    ci.o[0] = clampi(b.y0, -1, a.H) * a.W + clampi(b.x0, -1, a.W); ci.o[1] = ci.o[0] + 1; ci.o[2] = ci.o[0] + a.W; ci.o[3] = ci.o[2] + 1;
     float vd[4], vfx[4], vfy[4], va[4];
     gather4(a.depth1 + fo, ci, vd);
     gather4(a.flow1 + (size_t)n * 2 * hw, ci, vfx);

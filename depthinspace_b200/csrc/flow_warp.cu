@@ -32,7 +32,7 @@ __device__ __forceinline__ void warp_pixel_fwd(const float* __restrict__ xp, flo
   // corner offsets and predicates once per pixel; channels in groups of 4 so that 16 gathers are in flight
   const bool bnw = in_bounds(b.y0, b.x0, H, W), bne = in_bounds(b.y0, b.x0 + 1, H, W);
   const bool bsw = in_bounds(b.y0 + 1, b.x0, H, W), bse = in_bounds(b.y0 + 1, b.x0 + 1, H, W);
-  const int o_nw = b.y0 * W + b.x0;
+  const int o_nw = clampi(b.y0, -1, H) * W + clampi(b.x0, -1, W);   // (clamped: no overflow; unchanged where a corner is in bounds)
   o0 = 0.f; o1 = 0.f;
   int c = 0;
   for (; c + 4 <= C; c += 4) {
