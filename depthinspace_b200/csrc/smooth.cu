@@ -3,21 +3,30 @@
 //   g  = sobel5x5(replicate_pad2(disp)) -> (gx, gy);  gi = sobel5x5(replicate_pad2(im))
 //   val = mean | g * exp(-|255 gi|) |   over [N,2,H,W]
 //
-// smooth_loss_kernel does the whole forward in one pass over a 64x32 tile and, on request, the exact
-// gradient w.r.t. disp in the same pass (gather form of the adjoint: conv-transpose of
-// u = sign(g a) a, followed by the adjoint of the replicate padding, folded into the border pixels).
+// smooth_march_kernel does the whole forward and, on request, the exact gradient w.r.t. disp in one pass.  The 5x5 Sobel
+// pair is rank 2:  kx = a (x) [-1 0 0 0 1] + b (x) [0 -1 0 1 0]  with the vertical smoothers a = (5 8 10 8 5) / 240 and
+// b = (4 10 20 10 4) / 240, ky = kx^T, so
+//   gx(y, x) = VA(y, x+2) - VA(y, x-2) + VB(y, x+1) - VB(y, x-1),   VA = a *_vertical v,  VB = b *_vertical v
+//   gy(y, x) = HA(y+2, x) - HA(y-2, x) + HB(y+1, x) - HB(y-1, x),   HA = a *_horizontal v, HB = b *_horizontal v
+// (22 instead of 40 multiply-adds per pixel and image), and the adjoint is the same filter pair applied to
+// u = sign(g a) a with the sign flipped (kx is odd in x and even in y), followed by the adjoint of the replicate
+// padding (the padded positions fold onto the border pixels).
 #include "common.cuh"
+#include <map>
+#include <mutex>
 
 namespace dis {
 namespace {
 
-constexpr int STW = 64, STH = 32, SNT = 256;
-#ifndef DIS_SMOOTH_FILL_UNROLL
-#define DIS_SMOOTH_FILL_UNROLL 4
+#ifndef DIS_SMOOTH_MAX_T
+#define DIS_SMOOTH_MAX_T 224
 #endif
-constexpr int kSmoothFillUnroll = DIS_SMOOTH_FILL_UNROLL;   // staging loads in flight per thread (the phase is latency-bound)
-constexpr int IN_H = STH + 8, IN_W = STW + 8, IN_P = IN_W;      // inputs with halo 4 (replicate-clamped)
-constexpr int U_H = STH + 4, U_W = STW + 4, U_P = U_W;          // u with halo 2 (zero outside the image)
+constexpr int SM_MAX_T = DIS_SMOOTH_MAX_T;    // threads = columns of a strip with a halo of 4 on either side (432 = 2 x 216; 216 + 8 = 224)
+constexpr int SM_HALO = 4;       // v at +-4 -> g, u at +-2 -> gradient
+constexpr int SM_MIN_BAND = 16;  // shortest row band (the partials buffer is sized for it)
+#ifndef DIS_SMOOTH_MIN_CTAS
+#define DIS_SMOOTH_MIN_CTAS 4
+#endif
 
 // kx[i][j] / 240 rounded to float exactly like torch.from_numpy(kx).float()  (:701-705); ky = kx^T
 #define SOB(v) ((float)((v) / 240.0))
@@ -40,201 +49,194 @@ __device__ __forceinline__ void sobel5_at(const float* __restrict__ t, int pitch
   gx = ax;
   gy = ay;
 }
-// adjoint tap: sum_{i,j} kx[i][j] * ux(q - (i-2, j-2)) + ky[i][j] * uy(q - (i-2, j-2))
-template <typename F>
-__device__ __forceinline__ float sobel5_adjoint(F u_at, int qy, int qx) {
-  constexpr float k[5][5] = {{SOB(-5.0), SOB(-4.0), 0.f, SOB(4.0), SOB(5.0)},
-                             {SOB(-8.0), SOB(-10.0), 0.f, SOB(10.0), SOB(8.0)},
-                             {SOB(-10.0), SOB(-20.0), 0.f, SOB(20.0), SOB(10.0)},
-                             {SOB(-8.0), SOB(-10.0), 0.f, SOB(10.0), SOB(8.0)},
-                             {SOB(-5.0), SOB(-4.0), 0.f, SOB(4.0), SOB(5.0)}};
-  float acc = 0.f;
-#pragma unroll
-  for (int i = 0; i < 5; ++i)
-#pragma unroll
-    for (int j = 0; j < 5; ++j) {
-      const float2 u = u_at(qy - (i - 2), qx - (j - 2));
-      if (j != 2) acc = fmaf(k[i][j], u.x, acc);
-      if (i != 2) acc = fmaf(k[j][i], u.y, acc);
-    }
-  return acc;
-}
 
-__device__ __forceinline__ void load_row8(const float* __restrict__ p, float (&r)[8]) {
-  const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
-  r[0] = a.x; r[1] = a.y; r[2] = a.z; r[3] = a.w; r[4] = b.x; r[5] = b.y; r[6] = b.z; r[7] = b.w;
-}
+// A CTA owns a strip of columns (one thread per column, halo included) and marches down a band of rows, TWO rows per
+// step and ONE barrier per step.  Step (s, s+1), for each of its two rows r:
+//   A  loads row r of (disp, ambient) as an fp32x2 pair (replicate-clamped), pushes it into the thread's 5-row register
+//      ring, forms the vertical smoothers VA, VB of row y = r - 2 and posts v(r), VA(y), VB(y) in shared memory;
+//   -- barrier --
+//   C  (gradient) takes the u-side quantities the neighbours posted in the previous step, finishes the padded-domain
+//      gradient of row r - 6, and emits row r - 8 (held one more step so that the border columns can collect the two
+//      padded columns that fold onto them; the padded rows fold through a register);
+//   B  reads the neighbours' v(r), VA(y), VB(y): HA(r), HB(r) update the pending gy sums of rows r-2..r+2, gx(y) is a
+//      difference of four neighbours; g(y) -> loss and u(y); the vertical smoothers of ux for row q = y - 2 and uy(y)
+//      are posted for the next step.
+// Everything a step posts goes to buffer (step & 1) and is read before the barrier of the next step; the next write to
+// that buffer comes after that barrier.  Rings are indexed (PH + k) % 5 with the loop unrolled by 5 steps (10 rows): no
+// register moves.  The posted rows carry two pad columns on either side, so a neighbour is an immediate offset.
+struct SmoothRings {
+  u64 v[5];      // (disp, ambient) rows r-4..r
+  u64 gy[5];     // pending gy sums of rows r-2..r+2
+  float ux[5];   // ux rows y-4..y
+  float ga[5];   // pending uy-side gradient sums of rows y'-2..y'+2
+};
+template <int V> struct SmoothPhase { static constexpr int value = V; };
+constexpr int SM_PAD = 2, SM_ROW = SM_MAX_T + 2 * SM_PAD;
+struct SmoothPost {                       // what one step posts, per row r in {0, 1}
+  ulonglong2 ab[2][SM_ROW];               // (VA, VB) of row y
+  float4 u[2][SM_ROW];                    // (uy(y), UA(q), UB(q), padded-domain gradient of row r - 6)
+  u64 v[2][SM_ROW];                       // (disp, ambient) of row r
+};
 
-// 4 horizontally adjacent Sobel responses from a 5 x 8 register window of (disp, ambient) pairs: every FFMA2
-// advances both images.
-// out: gx2[q] = (sobel_x(disp), sobel_x(amb)), gy2[q] likewise, for 4 adjacent responses.
-__device__ __forceinline__ void sobel5_quad2(const u64 (&win)[5][8], u64 (&gx2)[4], u64 (&gy2)[4]) {
-  constexpr float k[5][5] = {{SOB(-5.0), SOB(-4.0), 0.f, SOB(4.0), SOB(5.0)},
-                             {SOB(-8.0), SOB(-10.0), 0.f, SOB(10.0), SOB(8.0)},
-                             {SOB(-10.0), SOB(-20.0), 0.f, SOB(20.0), SOB(10.0)},
-                             {SOB(-8.0), SOB(-10.0), 0.f, SOB(10.0), SOB(8.0)},
-                             {SOB(-5.0), SOB(-4.0), 0.f, SOB(4.0), SOB(5.0)}};
-#pragma unroll
-  for (int q = 0; q < 4; ++q) {
-    u64 ax = pk2(0.f, 0.f), ay = pk2(0.f, 0.f);
-#pragma unroll
-    for (int i = 0; i < 5; ++i)
-#pragma unroll
-      for (int j = 0; j < 5; ++j) {
-        if (j != 2) ax = fma2(bc2(k[i][j]), win[i][q + j], ax);
-        if (i != 2) ay = fma2(bc2(k[j][i]), win[i][q + j], ay);
-      }
-    gx2[q] = ax;
-    gy2[q] = ay;
-  }
-}
-
-__device__ __forceinline__ void load_row8x2(const float2* __restrict__ p, u64 (&r)[8]) {
-#pragma unroll
-  for (int v = 0; v < 4; ++v) {
-    const float4 a = *reinterpret_cast<const float4*>(p + 2 * v);
-    r[2 * v] = pk2(a.x, a.y);
-    r[2 * v + 1] = pk2(a.z, a.w);
-  }
-}
-
-// Tile 64 x 32.  Shared planes of float2, pitches chosen so that 128-bit row loads are 16-byte aligned and, for
-// threads that walk down consecutive rows, bank-conflict free (pitch * 2 = 20 or 12 mod 32):
-//   sin : (disp, ambient), replicate-clamped, origin (-4,-4): 40 rows x 72 cols, pitch 74
-//   sux, suy : u = sign(g a) a, zero outside the image, origin (-2,-2): 36 rows x 68 cols (plain float planes: the
-//              adjoint taps carry different weights for u_x and u_y, and only a scalar FFMA takes an immediate)
-// Responses are produced in quads starting at tile-local column -2 + 4q, so their 8-wide input windows
-// (origin -4 + 4q) and their stores (origin -2 + 4q) are both aligned; the adjoint quads start at 4q and read
-// the u window starting at 4q - 2, aligned again.  Both images go through the Sobel taps together as fp32x2.
-constexpr int PIN = 74, PU = U_P;
+// sign(v) * a for a > 0
+__device__ __forceinline__ float signed_mag0(float a, float v) { return v == 0.0f ? 0.0f : copysignf(a, v); }
 
 template <bool GRAD>
-__global__ void __launch_bounds__(SNT) smooth_loss_kernel(const float* __restrict__ disp, const float* __restrict__ im,
-                                                          float* __restrict__ grad_sum, float* __restrict__ partials,
-                                                          int H, int W, int vec_ok, float grad_scale, int accumulate) {
-  __shared__ __align__(16) float2 sin[IN_H * PIN];
-  __shared__ __align__(16) float sux[GRAD ? U_H * PU : 4];
-  __shared__ __align__(16) float suy[GRAD ? U_H * PU : 4];
-  __shared__ float red[2 * (SNT / 32)];
-  const int tid = threadIdx.x;
-  const int x0 = blockIdx.x * STW, y0 = blockIdx.y * STH, n = blockIdx.z;
+__global__ void __launch_bounds__(SM_MAX_T, DIS_SMOOTH_MIN_CTAS)
+smooth_march_kernel(const float* __restrict__ disp, const float* __restrict__ im, float* __restrict__ grad_sum,
+                    float* __restrict__ partials, int H, int W, int strip, int band_rows, int per_frame, float grad_scale,
+                    int accumulate) {
+  extern __shared__ __align__(16) unsigned char smooth_smem[];
+  SmoothPost* post = reinterpret_cast<SmoothPost*>(smooth_smem);   // [2]
+  __shared__ double red[SM_MAX_T / 32];
+  constexpr float A0 = SOB(5.0), A1 = SOB(8.0), A2 = SOB(10.0), B0 = SOB(4.0), B1 = SOB(10.0), B2 = SOB(20.0);
+  const int T = blockDim.x, t = threadIdx.x, n = blockIdx.z, tp = t + SM_PAD;
+  const int X0 = blockIdx.x * strip, X1 = min(X0 + strip, W);
+  const int xc = X0 - SM_HALO + t, cx = clampi(xc, 0, W - 1);
+  const bool col_img = xc >= 0 && xc < W, col_out = xc >= X0 && xc < X1;
+  const bool fold_l = GRAD && col_out && xc == 0, fold_r = GRAD && col_out && xc == W - 1;
+  const int y_begin = blockIdx.y * band_rows, y_end = min(y_begin + band_rows, H);
+  // padded-domain gradient rows [qb, qe) of this band: the first / last band also owns the two padded rows above / below
+  const int qb = (GRAD && y_begin == 0) ? -2 : y_begin, qe = (GRAD && y_end == H) ? H + 2 : y_end;
+  const int u_first = GRAD ? qb - 2 : y_begin;              // first row whose g is needed (rings are primed by then)
+  const int s0 = u_first - 2, s1 = GRAD ? qe + 7 : y_end + 1;   // first / last row to load
   const size_t hw = (size_t)H * W;
-  const float* d = disp + (size_t)n * hw;
-  const float* a = im + (size_t)n * hw;
-#pragma unroll kSmoothFillUnroll
-  for (int idx = tid; idx < IN_H * IN_W; idx += SNT) {
-    const int j = idx / IN_W, i = idx - j * IN_W;
-    const int g = clampi(y0 - 4 + j, 0, H - 1) * W + clampi(x0 - 4 + i, 0, W - 1);
-    sin[j * PIN + i] = make_float2(__ldg(d + g), __ldg(a + g));
-  }
-  __syncthreads();
+  const float* dn = disp + (size_t)n * hw + cx;
+  const float* an = im + (size_t)n * hw + cx;
+  float* go = GRAD ? grad_sum + (size_t)n * hw + cx : nullptr;
 
-  float lsum = 0.f, lcnt = 0.f;
-  constexpr int UROWS = GRAD ? U_H : STH;   // rows -2..33 with the gradient, 0..31 without
-  constexpr int UQ = U_W / 4;               // 17 quads: columns -2..65
-  for (int item = tid; item < UROWS * UQ; item += SNT) {
-    const int q = item / UROWS, jr = item - q * UROWS;   // consecutive threads walk down the rows of one quad
-    const int ly = GRAD ? jr - 2 : jr;      // tile-local row of the responses
-    const int lx = 4 * q - 2;               // tile-local column of the first response
-    const int gy = y0 + ly;
-    float ux[4] = {0.f, 0.f, 0.f, 0.f}, uy[4] = {0.f, 0.f, 0.f, 0.f};
-    if (gy >= 0 && gy < H) {
-      // response (ly, lx+c) reads tile-local rows ly-2..ly+2, cols lx+c-2..lx+c+2 = smem rows ly+2.., cols 4q+c..
-      u64 win[5][8];
+  SmoothRings R;
 #pragma unroll
-      for (int i = 0; i < 5; ++i) load_row8x2(sin + (ly + 2 + i) * PIN + 4 * q, win[i]);
-      u64 gx2[4], gy2[4];
-      sobel5_quad2(win, gx2, gy2);
+  for (int k = 0; k < 5; ++k) { R.v[k] = 0ull; R.gy[k] = 0ull; R.ux[k] = 0.f; R.ga[k] = 0.f; }
+  float lsum = 0.f, facc = 0.f, pre[4];
+  double dsum = 0.0;
+  int buf = 0;
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        const int gx = x0 + lx + c;
-        if (gx >= 0 && gx < W) {
-          float gdx, gix, gdy, giy;
-          upk2(gx2[c], gdx, gix);
-          upk2(gy2[c], gdy, giy);
-          const float ax = expf(-fabsf(255.0f * gix)), ay = expf(-fabsf(255.0f * giy));
-          const float vx = gdx * ax, vy = gdy * ay;
-          if (ly >= 0 && ly < STH && lx + c >= 0 && lx + c < STW) { lsum += fabsf(vx) + fabsf(vy); lcnt += 2.0f; }
-          ux[c] = sign0(vx) * ax;
-          uy[c] = sign0(vy) * ay;
-        }
-      }
-    }
-    if (GRAD) {  // response (ly, lx+c) lives at u-plane (ly+2, 4q+c)
-      *reinterpret_cast<float4*>(sux + (ly + 2) * PU + 4 * q) = make_float4(ux[0], ux[1], ux[2], ux[3]);
-      *reinterpret_cast<float4*>(suy + (ly + 2) * PU + 4 * q) = make_float4(uy[0], uy[1], uy[2], uy[3]);
-    }
+  for (int r = 0; r < 2; ++r) {
+    const int ro = clampi(s0 + r, 0, H - 1) * W;
+    pre[2 * r] = __ldg(dn + ro);
+    pre[2 * r + 1] = __ldg(an + ro);
   }
-  if (GRAD) {
+
+  auto step = [&](auto phase, const int s) __attribute__((always_inline)) {
+    constexpr int P0 = decltype(phase)::value * 2;   // ring phase of the step's first row
+#define RING(a, ph, k) a[((ph) + (k)) % 5]
+    SmoothPost& cur = post[buf];
+    const SmoothPost& prv = post[buf ^ 1];
+    // ---- A (the rows were requested a step ago; the next two are requested now)
+    const u64 vnew[2] = {pk2(pre[0], pre[1]), pk2(pre[2], pre[3])};
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      const int ro = clampi(s + 2 + r, 0, H - 1) * W;
+      pre[2 * r] = __ldg(dn + ro);
+      pre[2 * r + 1] = __ldg(an + ro);
+    }
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      RING(R.v, P0 + r, 4) = vnew[r];
+      const u64 t04 = add2(RING(R.v, P0 + r, 0), vnew[r]), t13 = add2(RING(R.v, P0 + r, 1), RING(R.v, P0 + r, 3));
+      const u64 va = fma2(bc2(A2), RING(R.v, P0 + r, 2), fma2(bc2(A1), t13, mul2(bc2(A0), t04)));
+      const u64 vb = fma2(bc2(B2), RING(R.v, P0 + r, 2), fma2(bc2(B1), t13, mul2(bc2(B0), t04)));
+      cur.v[r][tp] = vnew[r];
+      cur.ab[r][tp] = make_ulonglong2(va, vb);
+    }
     __syncthreads();
-    float* go = grad_sum + (size_t)n * hw;
-    constexpr float k[5][5] = {{SOB(-5.0), SOB(-4.0), 0.f, SOB(4.0), SOB(5.0)},
-                               {SOB(-8.0), SOB(-10.0), 0.f, SOB(10.0), SOB(8.0)},
-                               {SOB(-10.0), SOB(-20.0), 0.f, SOB(20.0), SOB(10.0)},
-                               {SOB(-8.0), SOB(-10.0), 0.f, SOB(10.0), SOB(8.0)},
-                               {SOB(-5.0), SOB(-4.0), 0.f, SOB(4.0), SOB(5.0)}};
-    auto u_at = [&](int ly, int lx) -> float2 {  // tile-local; zero beyond the stored halo (= outside the image)
-      if (ly < -2 || ly >= STH + 2 || lx < -2 || lx >= STW + 2) return make_float2(0.f, 0.f);
-      return make_float2(sux[(ly + 2) * PU + lx + 2], suy[(ly + 2) * PU + lx + 2]);
-    };
-    for (int item = tid; item < STH * (STW / 4); item += SNT) {
-      const int ly = item / (STW / 4), lx = 4 * (item - ly * (STW / 4));
-      const int gy = y0 + ly, gx = x0 + lx;
-      if (gy >= H || gx >= W) continue;
-      // grad(q) = sum_{i,j} kx[i][j] ux(q - (i-2, j-2)) + ky[i][j] uy(q - (i-2, j-2))
-      // u window: tile-local rows ly-2..ly+2, cols lx-2..lx+5 = u-plane rows ly.., cols lx..lx+7
-      float acc[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-      for (int r = 0; r < 5; ++r) {   // u row offset r-2  => i = 4 - r
-        float vx[8], vy[8];
-        load_row8(sux + (ly + r) * PU + lx, vx);
-        load_row8(suy + (ly + r) * PU + lx, vy);
-#pragma unroll
-        for (int c = 0; c < 4; ++c)
-#pragma unroll
-          for (int t = 0; t < 5; ++t) {  // u col offset t-2 => j = 4 - t
-            const int i = 4 - r, j = 4 - t;
-            if (j != 2) acc[c] = fmaf(k[i][j], vx[c + t], acc[c]);
-            if (i != 2) acc[c] = fmaf(k[j][i], vy[c + t], acc[c]);
+    for (int r = 0; r < 2; ++r) {
+      const int row = s + r;
+      float gnew = 0.f;
+      // ---- C: the previous step posted uy(y' = row - 4), UA / UB(q' = row - 6) and the gradient of row - 8
+      if (GRAD && s > s0) {
+        const float4 m2 = prv.u[r][tp - 2], m1 = prv.u[r][tp - 1], own = prv.u[r][tp], p1 = prv.u[r][tp + 1], p2 = prv.u[r][tp + 2];
+        const int qq = row - 8;   // row whose padded-domain gradient was posted
+        if (qq >= qb && qq < qe) {
+          float g = own.w;
+          if (fold_l) g += m1.w + m2.w;
+          if (fold_r) g += p1.w + p2.w;
+          facc += g;
+          if ((qq >= 0 && qq < H - 1) || qq == H + 1) {   // last padded row that folds onto image row clamp(qq)
+            if (col_out) {
+              float* o = go + clampi(qq, 0, H - 1) * W;
+              float v = facc * grad_scale;      // 1 for the plain sum; weight / count for a final gradient
+              if (accumulate) v += *o;          // add to a gradient another term already left there
+              __stcs(o, v);
+            }
+            facc = 0.f;
           }
-      }
-      // border-line pixels also collect the pad-2 positions that replicate-clamp onto them
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        const int px_ = gx + c;
-        if (px_ < W && (gy == 0 || gy == H - 1 || px_ == 0 || px_ == W - 1)) {
-          const int ylo = (gy == 0) ? -2 : 0, yhi = (gy == H - 1) ? 2 : 0;
-          const int xlo = (px_ == 0) ? -2 : 0, xhi = (px_ == W - 1) ? 2 : 0;
-          float v = 0.f;
-          for (int py2 = ylo; py2 <= yhi; ++py2)
-            for (int px2 = xlo; px2 <= xhi; ++px2) v += sobel5_adjoint(u_at, ly + py2, lx + c + px2);
-          acc[c] = v;
         }
+        const float e2 = m2.x + p2.x, e1 = m1.x + p1.x;
+        const float wa = fmaf(A2, own.x, fmaf(A1, e1, A0 * e2)), wb = fmaf(B2, own.x, fmaf(B1, e1, B0 * e2));
+        const float gfin = RING(R.ga, P0 + r, 0) + wa;     // row y' - 2 = row - 6 complete
+        RING(R.ga, P0 + r, 1) += wb;
+        RING(R.ga, P0 + r, 3) -= wb;
+        RING(R.ga, P0 + r, 4) = -wa;
+        gnew = -(((p2.y - m2.y) + (p1.z - m1.z)) + gfin);
       }
-      float* o = go + (size_t)gy * W + gx;
-#pragma unroll
-      for (int c = 0; c < 4; ++c) acc[c] *= grad_scale;      // 1 for the plain sum; weight / count for a final gradient
-      if (accumulate) {                                       // add to a gradient another term already left there
-        if (vec_ok && gx + 3 < W) {
-          const float4 old = *reinterpret_cast<const float4*>(o);
-          acc[0] += old.x; acc[1] += old.y; acc[2] += old.z; acc[3] += old.w;
-        } else {
-#pragma unroll
-          for (int c = 0; c < 4; ++c) if (gx + c < W) acc[c] += o[c];
-        }
-      }
-      if (vec_ok && gx + 3 < W) __stcs(reinterpret_cast<float4*>(o), make_float4(acc[0], acc[1], acc[2], acc[3]));
-      else {
-#pragma unroll
-        for (int c = 0; c < 4; ++c) if (gx + c < W) o[c] = acc[c];
+      // ---- B
+      const u64 vm2 = cur.v[r][tp - 2], vm1 = cur.v[r][tp - 1], vp1 = cur.v[r][tp + 1], vp2 = cur.v[r][tp + 2];
+      const u64 e2 = add2(vm2, vp2), e1 = add2(vm1, vp1);
+      const u64 ha = fma2(bc2(A2), vnew[r], fma2(bc2(A1), e1, mul2(bc2(A0), e2)));
+      const u64 hb = fma2(bc2(B2), vnew[r], fma2(bc2(B1), e1, mul2(bc2(B0), e2)));
+      const u64 gy2 = add2(RING(R.gy, P0 + r, 0), ha);   // row y = row - 2 complete
+      RING(R.gy, P0 + r, 1) = add2(RING(R.gy, P0 + r, 1), hb);
+      RING(R.gy, P0 + r, 3) = sub2(RING(R.gy, P0 + r, 3), hb);
+      RING(R.gy, P0 + r, 4) = sub2(0ull, ha);
+      const ulonglong2 am2 = cur.ab[r][tp - 2], am1 = cur.ab[r][tp - 1], ap1 = cur.ab[r][tp + 1], ap2 = cur.ab[r][tp + 2];
+      const u64 gx2 = add2(sub2(ap2.x, am2.x), sub2(ap1.y, am1.y));
+      float gdx, gix, gdy, giy;
+      upk2(gx2, gdx, gix);
+      upk2(gy2, gdy, giy);
+      const int y = row - 2;
+      const float ax = expf(-fabsf(255.0f * gix)), ay = expf(-fabsf(255.0f * giy));
+      const float vx = gdx * ax, vy = gdy * ay;
+      if (y >= y_begin && y < y_end && col_out) lsum += fabsf(vx) + fabsf(vy);
+      if (GRAD) {
+        const bool ok = y >= u_first && y >= 0 && y < H && col_img;   // u is zero outside the image
+        const float ux = ok ? signed_mag0(ax, vx) : 0.f, uy = ok ? signed_mag0(ay, vy) : 0.f;
+        RING(R.ux, P0 + r, 4) = ux;
+        const float c04 = RING(R.ux, P0 + r, 0) + ux, c13 = RING(R.ux, P0 + r, 1) + RING(R.ux, P0 + r, 3);
+        const float ua = fmaf(A2, RING(R.ux, P0 + r, 2), fmaf(A1, c13, A0 * c04));
+        const float ub = fmaf(B2, RING(R.ux, P0 + r, 2), fmaf(B1, c13, B0 * c04));
+        cur.u[r][tp] = make_float4(uy, ua, ub, gnew);
       }
     }
+    buf ^= 1;
+#undef RING
+  };
+
+  // groups of 5 steps (10 rows) restore the ring phase
+  int base = s0;
+  for (; base + 9 <= s1; base += 10) {
+    step(SmoothPhase<0>{}, base);
+    step(SmoothPhase<1>{}, base + 2);
+    step(SmoothPhase<2>{}, base + 4);
+    step(SmoothPhase<3>{}, base + 6);
+    step(SmoothPhase<4>{}, base + 8);
+    dsum += (double)lsum;   // fp32 only over 10 rows: the band sum keeps fp64 accuracy
+    lsum = 0.f;
   }
-  block_sum2<SNT>(lsum, lcnt, red);
-  if (tid == 0) {
-    const size_t b = ((size_t)n * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
-    partials[2 * b] = lsum;
-    partials[2 * b + 1] = lcnt;
+  if (base <= s1) {          // the last 1..4 steps (a row past s1 is harmless: clamped load, nothing emitted)
+    step(SmoothPhase<0>{}, base);
+    if (base + 2 <= s1) step(SmoothPhase<1>{}, base + 2);
+    if (base + 4 <= s1) step(SmoothPhase<2>{}, base + 4);
+    if (base + 6 <= s1) step(SmoothPhase<3>{}, base + 6);
+    if (base + 8 <= s1) step(SmoothPhase<4>{}, base + 8);
+    dsum += (double)lsum;
+  }
+
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) dsum += __shfl_xor_sync(0xffffffffu, dsum, o);
+  if ((t & 31) == 0) red[t >> 5] = dsum;
+  __syncthreads();
+  if (t == 0) {
+    double tot = 0.0;
+    for (int i = 0; i < T / 32; ++i) tot += red[i];
+    float* pf = partials + 2 * (size_t)n * per_frame;
+    const int b = blockIdx.y * gridDim.x + blockIdx.x;
+    pf[2 * b] = (float)tot;
+    pf[2 * b + 1] = 2.0f * (float)(y_end - y_begin) * (float)(X1 - X0);
+    if (b == 0)   // slots of the bands a finer plan would have used
+      for (int i = gridDim.x * gridDim.y; i < per_frame; ++i) { pf[2 * i] = 0.f; pf[2 * i + 1] = 0.f; }
   }
 }
 
@@ -313,14 +315,56 @@ inline int flat_grid(size_t total) {
 
 }  // namespace
 
-int smooth_loss_num_partials(int N, int H, int W) { return N * ((H + STH - 1) / STH) * ((W + STW - 1) / STW); }
+struct SmoothPlan {
+  int threads, strip, nstrips, band_rows, nbands, per_frame;
+};
+SmoothPlan smooth_plan(int N, int H, int W) {
+  SmoothPlan p;
+  int t = ((W + 2 * SM_HALO + 31) / 32) * 32;
+  if (t > SM_MAX_T) t = SM_MAX_T;
+  p.threads = t;
+  p.strip = t - 2 * SM_HALO;
+  p.nstrips = (W + p.strip - 1) / p.strip;
+  // every band re-primes 10 rows, so bands should be long; shorten them only when the batch cannot fill the SMs
+  p.band_rows = 64;
+  while (p.band_rows > SM_MIN_BAND && (long)N * p.nstrips * ((H + p.band_rows - 1) / p.band_rows) < 148L * DIS_SMOOTH_MIN_CTAS) p.band_rows >>= 1;
+  p.nbands = (H + p.band_rows - 1) / p.band_rows;
+  p.per_frame = p.nstrips * ((H + SM_MIN_BAND - 1) / SM_MIN_BAND);   // independent of N: callers chunk the batch
+  return p;
+}
+
+int smooth_loss_num_partials(int N, int H, int W) { return N * smooth_plan(N, H, W).per_frame; }
+
+// > 48 KB of dynamic shared memory needs an opt-in per kernel and device; done once, off the launch path
+template <typename K>
+int smooth_prepare(K kernel) {
+  static std::map<std::pair<const void*, int>, cudaError_t> done;
+  static std::mutex mu;
+  int device = 0;
+  cudaGetDevice(&device);
+  std::lock_guard<std::mutex> lock(mu);
+  const std::pair<const void*, int> key(reinterpret_cast<const void*>(kernel), device);
+  auto it = done.find(key);
+  if (it == done.end())
+    it = done.emplace(key, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * sizeof(SmoothPost)))).first;
+  if (it->second != cudaSuccess) { set_last_cuda_error(it->second); return DIS_ERR_CUDA_LAUNCH; }
+  return DIS_OK;
+}
 
 int smooth_loss_forward(const float* disp, const float* im, float* grad_sum, float* partials, int N, int H, int W,
                         float grad_scale, int accumulate, cudaStream_t s) {
-  dim3 grid((W + STW - 1) / STW, (H + STH - 1) / STH, N);
-  const int vec_ok = (W % 4 == 0) && ((reinterpret_cast<uintptr_t>(grad_sum) & 15) == 0);
-  if (grad_sum) smooth_loss_kernel<true><<<grid, SNT, 0, s>>>(disp, im, grad_sum, partials, H, W, vec_ok, grad_scale, accumulate);
-  else smooth_loss_kernel<false><<<grid, SNT, 0, s>>>(disp, im, nullptr, partials, H, W, vec_ok, grad_scale, 0);
+  const SmoothPlan p = smooth_plan(N, H, W);
+  dim3 grid(p.nstrips, p.nbands, N);
+  const size_t smem = 2 * sizeof(SmoothPost);
+  if (grad_sum) {
+    if (int rc = smooth_prepare(smooth_march_kernel<true>)) return rc;
+    smooth_march_kernel<true><<<grid, p.threads, smem, s>>>(disp, im, grad_sum, partials, H, W, p.strip, p.band_rows, p.per_frame,
+                                                            grad_scale, accumulate);
+  } else {
+    if (int rc = smooth_prepare(smooth_march_kernel<false>)) return rc;
+    smooth_march_kernel<false><<<grid, p.threads, smem, s>>>(disp, im, nullptr, partials, H, W, p.strip, p.band_rows, p.per_frame,
+                                                             grad_scale, 0);
+  }
   return check_launch();
 }
 
