@@ -33,6 +33,8 @@ SIGNATURES = {
     "dis_reduce_pairs": [_f, _i, _f, _st],
     "dis_reduce_pairs_batched": [_f, _i, _i, _f, _st],
     "dis_pattern_loss_multi_num_partials": [_i, _i, _i],
+    "dis_pattern_loss_point_num_partials": [_i, _i, _i],
+    "dis_pattern_loss_point_forward": [_c.POINTER(_c.c_void_p), _i, _f, _f, _f, _c.POINTER(_c.c_void_p), _c.POINTER(_c.c_void_p), _f, _f, _i, _f, _i, _i, _i, _i, _i, _st],
     "dis_pattern_loss_multi_forward": [_c.POINTER(_c.c_void_p), _i, _f, _f, _f, _c.POINTER(_c.c_void_p), _f, _i, _i, _i, _i, _i, _fl, _st],
     "dis_pattern_loss_multi_forward_scaled": [_c.POINTER(_c.c_void_p), _i, _f, _f, _f, _c.POINTER(_c.c_void_p), _f, _f, _i, _i, _i, _i, _i, _fl, _st],
     "dis_scale_by_device_scalar": [_f, _f, _sz, _f, _f, _st],

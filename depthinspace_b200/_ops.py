@@ -147,12 +147,63 @@ def pattern_loss_forward(disp, im, std, pattern, block_size, type, eps, want_pro
     return out3, proj, diff, gnum
 
 
+def pattern_loss_point_forward(disps, im, std, pattern, block_size, type, want_proj, want_grad, grad_scale=None,
+                               workspace=None, reuse_wbox=False):
+    """mse / sad pattern loss of S = 1..4 disparity maps of the same frames, no per-pixel map (dis_pattern_loss_point_forward).
+    -> (out3 [S,3] rows (num_s, den, num_s/den), list of proj | None, list of grad_num | None)
+    workspace: optional float tensor of 2*N*H*W elements; with reuse_wbox its second half already holds the box-filtered
+    weights of these frames (same std, block_size)."""
+    import ctypes
+    S = len(disps)
+    disps = [_chk(d, f"disp[{i}]") for i, d in enumerate(disps)]
+    im = _chk(im, "im")
+    N, C, H, W = disps[0].shape
+    if C != 1 or any(d.shape != disps[0].shape for d in disps) or tuple(im.shape) != (N, 1, H, W):
+        raise ValueError("all disparity maps and im must be [N,1,H,W] with equal shapes")
+    if std is not None:
+        std = _chk(std, "std")
+        if std.shape != im.shape:
+            raise ValueError("std must match im")
+    pattern = _chk(pattern, "pattern", None)
+    if pattern.numel() != H * W:
+        raise ValueError(f"pattern has {pattern.numel()} elements, expected {H}x{W}")
+    if workspace is None:
+        if reuse_wbox:
+            raise ValueError("reuse_wbox needs the workspace of the earlier call")
+        workspace = torch.empty(2 * im.numel(), dtype=torch.float32, device=im.device)
+    elif workspace.numel() < 2 * im.numel() or workspace.dtype != torch.float32 or not workspace.is_contiguous() or not workspace.is_cuda:
+        raise ValueError("workspace must be a contiguous float32 CUDA tensor of 2*N*H*W elements")
+    projs = [torch.empty_like(d) for d in disps] if want_proj else None
+    grads = [torch.empty_like(d) for d in disps] if want_grad else None
+    out3 = torch.empty((S, 3), dtype=torch.float32, device=im.device)
+    PtrArr = ctypes.c_void_p * S
+    d_arr = PtrArr(*[d.data_ptr() for d in disps])
+    p_arr = PtrArr(*[t.data_ptr() for t in projs]) if want_proj else None
+    g_arr = PtrArr(*[g.data_ptr() for g in grads]) if want_grad else None
+    with _on(im) as lib:
+        npart = lib.dis_pattern_loss_point_num_partials(N, H, W)
+        partials = torch.empty(2 * S * max(npart, 1), dtype=torch.float32, device=im.device)
+        s = _stream(im)
+        if grad_scale is not None:
+            grad_scale = _chk(grad_scale, "grad_scale", 1)
+            if grad_scale.numel() != S:
+                raise ValueError(f"grad_scale must have {S} elements")
+        _lib.check(lib.dis_pattern_loss_point_forward(d_arr, S, _ptr(im), _ptr(std), _ptr(pattern), p_arr, g_arr, _ptr(grad_scale),
+                                                      _ptr(workspace), int(bool(reuse_wbox)), _ptr(partials), N, H, W,
+                                                      int(block_size), loss_type_id(type), s))
+        _lib.check(lib.dis_reduce_pairs_batched(_ptr(partials), npart, S, _ptr(out3), s))
+    return out3, projs, grads
+
+
 def pattern_loss_multi_forward(disps, im, std, pattern, block_size, type, eps, want_grad, grad_scale=None):
-    """S = 2 or 4 disparity maps of the same frames, census types only.
+    """S = 2 or 4 disparity maps of the same frames (census types; mse / sad: S = 1..4, through the point-wise path).
     -> (out3 [S,3] rows (num_s, den, num_s/den), list of grad_num | None)
     grad_scale: optional device tensor of S floats; grad_num[s] is multiplied by it inside the kernel (final gradients)."""
     import ctypes
     S = len(disps)
+    if loss_type_id(type) < 2:
+        out3, _, grads = pattern_loss_point_forward(disps, im, std, pattern, block_size, type, False, want_grad, grad_scale)
+        return out3, grads
     disps = [_chk(d, f"disp[{i}]") for i, d in enumerate(disps)]
     im = _chk(im, "im")
     N, C, H, W = disps[0].shape

@@ -26,7 +26,7 @@ NVCC_FLAGS = [
     "-Xcompiler", "-fPIC,-fvisibility=hidden",
     "-I", CSRC, "-I", INCLUDE,
 ]
-PLAIN_UNITS = ["api.cu", "lcn.cu", "misc.cu", "smooth.cu", "flow_warp.cu", "flow_consistency.cu", "conv3d_gather.cu", "resize.cu", "ext_misc.cu"]
+PLAIN_UNITS = ["api.cu", "lcn.cu", "misc.cu", "smooth.cu", "flow_warp.cu", "flow_consistency.cu", "conv3d_gather.cu", "resize.cu", "ext_misc.cu", "point_loss.cu"]
 RADII = range(8)
 
 

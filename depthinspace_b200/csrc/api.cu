@@ -28,6 +28,10 @@ int l1_num_partials(size_t);
 int l1_forward(const float*, const float*, float*, float*, size_t, cudaStream_t);
 int masked_l1_forward(const float*, const float*, const float*, float, float*, float*, size_t, cudaStream_t);
 int smooth_loss_num_partials(int, int, int);
+int point_loss_num_partials(int, int, int);
+int box_weight(const float*, float*, float*, int, int, int, int, cudaStream_t);
+int point_pattern_loss(const float* const*, int, const float*, const float*, const float*, const float*, float* const*,
+                       float* const*, const float*, float*, int, int, int, int, cudaStream_t);
 int smooth_loss_forward(const float*, const float*, float*, float*, int, int, int, float, int, cudaStream_t);
 int sobel_forward(const float*, float*, int, int, int, int, cudaStream_t);
 int sobel_backward(const float*, float*, int, int, int, int, cudaStream_t);
@@ -572,6 +576,32 @@ int dis_pattern_loss_multi_forward_scaled(const float* const* disps, int S, cons
     if (int rc = dispatch_pattern_multi(block_size / 2, a, S, type, as_stream(stream))) return rc;
   }
   return DIS_OK;
+}
+
+int dis_pattern_loss_point_num_partials(int N, int H, int W) {
+  if (N < 0 || H < 2 || W < 2) return DIS_ERR_BAD_SHAPE;
+  if ((size_t)H * W > (size_t)INT_MAX / 2 || H > 4 * 65535 || (size_t)N * ((H + 3) / 4) * ((W + 255) / 256) > (size_t)INT_MAX / 16) return DIS_ERR_BAD_SHAPE;
+  return point_loss_num_partials(N, H, W);
+}
+
+int dis_pattern_loss_point_forward(const float* const* disps, int S, const float* im, const float* std_in,
+                                   const float* pattern, float* const* projs, float* const* grad_nums,
+                                   const float* grad_scale, float* workspace, int reuse_wbox, float* partials, int N, int H,
+                                   int W, int block_size, int type, void* stream) {
+  if (int rc = check_block(block_size, type)) return rc;
+  if (type != MSE && type != SAD) return DIS_ERR_UNSUPPORTED_COMBINATION;
+  if (S < 1 || S > 4) return DIS_ERR_UNSUPPORTED_COMBINATION;
+  if (!disps || !im || !pattern || !workspace || !partials) return DIS_ERR_NULL_POINTER;
+  for (int s = 0; s < S; ++s)
+    if (!disps[s]) return DIS_ERR_NULL_POINTER;
+  if (N < 0 || H < 2 || W < 2) return DIS_ERR_BAD_SHAPE;
+  if (dis_pattern_loss_point_num_partials(N, H, W) < 0) return DIS_ERR_BAD_SHAPE;
+  if (N == 0) return DIS_OK;
+  float* wbox = workspace + (size_t)N * H * W;
+  if (!reuse_wbox)
+    if (int rc = box_weight(std_in, workspace, wbox, N, H, W, block_size, as_stream(stream))) return rc;
+  return point_pattern_loss(disps, S, im, std_in, wbox, pattern, projs, grad_nums, grad_scale, partials, N, H, W, type,
+                            as_stream(stream));
 }
 
 int dis_scale_by_device_scalar(const float* in, float* out, size_t n, const float* numer, const float* denom,

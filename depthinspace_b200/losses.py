@@ -176,8 +176,8 @@ class _HotPathLoss(torch.nn.Module):
         ph = self.ph_loss
         type_id = _ops.loss_type_id(ph.loss_type)
         S = len(out)
-        if S not in (1, 2, 4) or (type_id < 2 and S != 1):
-            raise ValueError("value_and_grad covers 1 scale (any loss type) or 2 / 4 scales (census types); use forward() otherwise")
+        if S not in (1, 2, 4):
+            raise ValueError("value_and_grad covers 1, 2 or 4 scales; use forward() otherwise")
         im, std_m, amb = _merge(im_lcn)[:, 0:1].contiguous(), _merge(std), _merge(ambient)
         disps = [_merge(o).detach() for o in out]
         dev, group = im.device, ph.process_group

@@ -92,7 +92,7 @@ class _PatternLossMean(torch.autograd.Function):
 
 
 class _PatternLossMulti(torch.autograd.Function):
-    """S (2 or 4) scales of the same frames in one launch (census types): returns the S ratios."""
+    """S (2 or 4) scales of the same frames in one launch: returns the S ratios."""
 
     @staticmethod
     def forward(ctx, im, std, pattern, block_size, type_id, eps, group, *disps):
@@ -182,7 +182,8 @@ class RectifiedPatternSimilarityLoss(torch.nn.Module):
 
     def forward_multi(self, disps, im, std=None):
         """The worker's photometric loop (model/single_frame_worker.py:108-115) in as few launches as possible:
-        groups of 4 / 2 scales go through the packed multi-scale kernel (census types), the rest one by one.
+        groups of 4 / 2 scales go through one launch (census types: the packed multi-scale kernel; mse / sad: the
+        point-wise kernel behind one box filter of the weights), the rest one by one.
         -> list of 0-dim ratios, one per disparity map (un-weighted)."""
         self.pattern = self.pattern.to(device=im.device, dtype=torch.float32)
         type_id = _ops.loss_type_id(self.loss_type)
@@ -191,7 +192,7 @@ class RectifiedPatternSimilarityLoss(torch.nn.Module):
         while i < len(disps):
             left = len(disps) - i
             take = 4 if left >= 4 else (2 if left >= 2 else 1)
-            if take == 1 or type_id < 2:
+            if take == 1:
                 v, _ = _PatternLossMean.apply(disps[i], im, std, self.pattern, self.block_size, type_id, self.loss_eps,
                                               False, self.process_group)
                 vals.append(v)

@@ -136,6 +136,24 @@ DIS_API int dis_pattern_loss_multi_forward_scaled(const float* const* disps, int
                                                   float* partials, int N, int H, int W, int block_size,
                                                   int type, float eps, void* stream);
 
+/* mse / sad pattern loss of S = 1..4 disparity maps of the same frames WITHOUT the per-pixel loss map, as a point-wise
+ * kernel behind one box filter of the weights (replaces the same reference path as dis_pattern_loss_forward,
+ * model/networks.py:354-377 + model/ext_functions.py:156-168, for types DIS_LOSS_MSE / DIS_LOSS_SAD):
+ *   sum_p w(p) out(p) = sum_q s(q) M(q),  M(q) = (1/k^2) sum_{(p,o): clamp(p+o)=q} w(p),  d num / d e(q) = s'(q) M(q).
+ *   disps, projs, grad_nums  HOST arrays of S device pointers ([N,1,H,W] each); projs / grad_nums and any of their
+ *                      entries may be NULL
+ *   grad_scale         optional DEVICE array of S floats multiplied into grad_nums[s]
+ *   workspace          float[2 * N*H*W]: scratch in the first half, M in the second half; reuse_wbox != 0 says the
+ *                      second half already holds M of these frames (same std_in, block_size): the box passes are skipped
+ *   partials           float[2 * S * dis_pattern_loss_point_num_partials(N,H,W)], scale-major (num_s, den) pairs;
+ *                      reduce with dis_reduce_pairs_batched(partials, num_partials, S, out3). */
+DIS_API int dis_pattern_loss_point_num_partials(int N, int H, int W);
+DIS_API int dis_pattern_loss_point_forward(const float* const* disps, int S, const float* im, const float* std_in,
+                                           const float* pattern, float* const* projs, float* const* grad_nums,
+                                           const float* grad_scale, float* workspace, int reuse_wbox,
+                                           float* partials, int N, int H, int W, int block_size, int type,
+                                           void* stream);
+
 /* out[i] = in[i] * (*numer) / (*denom) (denom may be NULL = 1).  Scalars live on the device
  * so no host synchronisation is needed between forward and backward. */
 DIS_API int dis_scale_by_device_scalar(const float* in, float* out, size_t n, const float* numer,

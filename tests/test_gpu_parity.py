@@ -1001,6 +1001,42 @@ def test_fused_pattern_loss_window_sizes(mods, k, lt):
         assert_close(dd[s].grad, o32["grad_disp"], 1e-5, f"grad k={k}", outlier_frac=0)
 
 
+@pytest.mark.parametrize("lt", ["mse", "sad"])
+@pytest.mark.parametrize("use_std", [True, False])
+def test_point_pattern_loss_matches_the_tile_kernel_and_the_oracle(mods, lt, use_std):
+    """Several mse / sad scales of the same frames run as a point-wise kernel behind one box filter of the weights
+    (sum_p w(p) box(s)(p) = sum_q s(q) M(q)); a single scale keeps the tile kernel.  Same value, same gradient,
+    bit-identical projection; S = 1..4 scales share one box filter; the workspace can be reused."""
+    from depthinspace_b200 import _ops
+    hw, k = (37, 85), 7
+    d, im_l, im_s, pat = _frames(3, hw, "kinect", seed=21, scales=4)
+    im, sd, pt = dev(im_l), (dev(im_s) if use_std else None), dev(pat).reshape(hw)
+    disps = [dev(p) for p in d["disp_pred"]]
+    tid = c_oracle.TYPES[lt]
+    o3p, projp, gp = _ops.pattern_loss_point_forward(disps[:1], im, sd, pt, k, lt, True, True)             # point path
+    o3t, projt, _, gt = _ops.pattern_loss_forward(disps[0], im, sd, pt, k, lt, 0.5, True, False, True)     # tile path
+    assert torch.equal(projp[0], projt), "projection differs between the point-wise and the tile kernel"
+    assert_scalar_close(o3p[0, 0].item(), o3t[0].item(), 2e-6, "num point vs tile")
+    assert_scalar_close(o3p[0, 1].item(), o3t[1].item(), 2e-6, "den point vs tile")
+    assert_close(gp[0], gt, 2e-6, "grad point vs tile", outlier_frac=0)
+    for S in (1, 2, 3, 4):
+        out3, projs, grads = _ops.pattern_loss_point_forward(disps[:S], im, sd, pt, k, lt, False, True)
+        assert projs is None and out3.shape == (S, 3)
+        for s in range(S):
+            o = c_oracle.pattern_loss(d["disp_pred"][s], im_l, im_s if use_std else None, pat.reshape(hw), k, tid, 0.5, True, "f32")
+            assert_scalar_close(out3[s, 2].item(), o["val"], 2e-6, f"S={S} scale {s} value vs fp32 oracle")
+            # the oracle differentiates num / den; the kernel stores d num
+            assert_close(grads[s] / out3[s, 1], o["grad_disp"], 1e-5, f"S={S} scale {s} grad vs fp32 oracle", outlier_frac=0)
+    ws = torch.empty(2 * im.numel(), device="cuda")
+    a3, _, ag = _ops.pattern_loss_point_forward(disps[:2], im, sd, pt, k, lt, False, True, workspace=ws)
+    b3, _, bg = _ops.pattern_loss_point_forward(disps[2:], im, sd, pt, k, lt, False, True, workspace=ws, reuse_wbox=True)
+    c3, _, cg = _ops.pattern_loss_point_forward(disps, im, sd, pt, k, lt, False, True)
+    assert torch.equal(torch.cat((a3, b3)), c3) and all(torch.equal(x, y) for x, y in zip(ag + bg, cg))
+    scale = torch.tensor([0.5, 0.25], device="cuda")
+    _, _, sg = _ops.pattern_loss_point_forward(disps[:2], im, sd, pt, k, lt, False, True, grad_scale=scale)
+    assert_close(sg[1], 0.25 * ag[1], 1e-6, "grad_scale", outlier_frac=0)
+
+
 # ----------------------------------------------------------------------------- BASELINE full size, size-independent properties
 def test_full_size_step_properties(mods):
     """BASELINE configs[1] size (256 frames of 512x432, 4 scales): properties that need no oracle run.

@@ -55,6 +55,9 @@ def main():
     report("pattern_loss single-scale census_sad k9 fwd only", timeit(lambda: _ops.pattern_loss_forward(disp, im, std, pat, 9, 3, 0.5, False, False, False)), 12 * P * N, frames=N)
     d4 = [torch.rand(N, 1, H, W, device=dev) * 60 for _ in range(4)]
     report("pattern_loss 4-scale census_sad k9 fwd+grad", timeit(lambda: _ops.pattern_loss_multi_forward(d4, im, std, pat, 9, 3, 0.5, True)), 40 * P * N, frames=N)
+    for t in ("mse", "sad"):   # point-wise kernel behind one box filter of the weights: im, std, M once + (disp, grad) per scale
+        report(f"pattern_loss 4-scale {t} k9 fwd+grad", timeit(lambda: _ops.pattern_loss_multi_forward(d4, im, std, pat, 9, t, 0.5, True)), 40 * P * N, frames=N)
+    report("pattern_loss single-scale mse k9 fwd+grad+map (tile kernel)", timeit(lambda: _ops.pattern_loss_forward(disp, im, std, pat, 9, "mse", 0.5, False, True, True)), 20 * P * N, frames=N)
     g = torch.rand(N, 1, H, W, device=dev)
     one, den = torch.ones(1, device=dev), torch.full((1,), 3.0, device=dev)
     report("scale_by_device_scalar", timeit(lambda: _ops.scale_by_device_scalar(g, one, den)), 8 * P * N, frames=N)
