@@ -224,7 +224,7 @@ using namespace dis;
 
 extern "C" {
 
-int dis_abi_version(void) { return 3; }
+int dis_abi_version(void) { return 4; }
 
 int dis_ext_nn(const float* in0, const float* in1, int64_t* out, int64_t n0, int64_t n1, int dim, void* stream) {
   if (n0 < 0 || n1 < 0 || (n0 + 255) / 256 > INT_MAX) return DIS_ERR_BAD_SHAPE;
