@@ -66,6 +66,8 @@ SIGNATURES = {
     "dis_conv3d_scratch_elems": [_i, _i, _i, _i],
     "dis_conv3d_gather_forward": [_f, _f, _f, _f, _f, _f, _f, _i, _i, _i, _i, _i, _i, _i, _i, _st],
     "dis_conv3d_gather_backward": [_f, _f, _f, _f, _f, _i, _i, _i, _i, _i, _i, _i, _i, _st],
+    "dis_conv3d_rank": [_f, _f, _f, _f, _f, _i, _i, _i, _i, _i, _i, _i, _st],
+    "dis_conv3d_gather_features": [_f, _f, _f, _i, _i, _i, _i, _i, _i, _i, _i, _st],
     "dis_combine2": [_f, _f, _f, _sz, _f, _f, _f, _fl, _st],
 }
 _RESTYPE = {"dis_status_string": _c.c_char_p, "dis_last_cuda_error": _c.c_char_p, "dis_conv3d_scratch_elems": _c.c_size_t}

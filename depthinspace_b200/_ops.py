@@ -628,6 +628,40 @@ def conv3d_gather_forward(xyz, feat, mask, ksize, stride, neighbors):
     return xyz_nb, feat_nb, idx, (oh, ow)
 
 
+def conv3d_rank(xyz, mask, ksize, stride, neighbors):
+    """Neighbour selection only -> (xyz_nb [M,nb,3], idx uint8 [M,nb], (oh, ow)); depends on xyz and mask, not on features."""
+    xyz, mask = _chk(xyz, "xyz", 5), _chk(mask, "mask", 5)
+    tl, bs, _, h, w = xyz.shape
+    if xyz.shape[2] != 3 or tuple(mask.shape) != (tl, bs, 1, h, w):
+        raise ValueError("expected xyz [tl,bs,3,h,w], mask [tl,bs,1,h,w]")
+    with _on(xyz) as lib:
+        oh, ow = lib.dis_conv3d_out_size(h, ksize, stride), lib.dis_conv3d_out_size(w, ksize, stride)
+        M = bs * oh * ow
+        xyz_nb = torch.empty((M, neighbors, 3), dtype=torch.float32, device=xyz.device)
+        idx = torch.empty((M, neighbors), dtype=torch.uint8, device=xyz.device)
+        scratch = torch.empty(lib.dis_conv3d_scratch_elems(tl, bs, h, w), dtype=torch.float32, device=xyz.device)
+        _lib.check(lib.dis_conv3d_rank(_ptr(xyz), _ptr(mask), _ptr(xyz_nb), _ptr(idx), _ptr(scratch), tl, bs, h, w, int(ksize),
+                                       int(stride), int(neighbors), _stream(xyz)), launches=3)
+    return xyz_nb, idx, (oh, ow)
+
+
+def conv3d_gather_features(feat, idx, ksize, stride, neighbors):
+    """Feature gather for a given selection -> feat_nb [M,nb,C]."""
+    feat = _chk(feat, "feat", 5)
+    tl, bs, C, h, w = feat.shape
+    if idx.dtype != torch.uint8 or not idx.is_cuda or not idx.is_contiguous():
+        raise TypeError("idx must be a contiguous uint8 CUDA tensor")
+    with _on(feat) as lib:
+        oh, ow = lib.dis_conv3d_out_size(h, ksize, stride), lib.dis_conv3d_out_size(w, ksize, stride)
+        M = bs * oh * ow
+        if tuple(idx.shape) != (M, neighbors):
+            raise ValueError(f"idx must be [{M},{neighbors}], got {tuple(idx.shape)}")
+        feat_nb = torch.empty((M, neighbors, C), dtype=torch.float32, device=feat.device)
+        _lib.check(lib.dis_conv3d_gather_features(_ptr(feat), _ptr(idx), _ptr(feat_nb), tl, bs, C, h, w, int(ksize), int(stride),
+                                                  int(neighbors), _stream(feat)))
+    return feat_nb
+
+
 def conv3d_gather_backward(g_xyz_nb, g_feat_nb, idx, shape, ksize, stride, neighbors, want_xyz, want_feat):
     tl, bs, C, h, w = shape
     g_xyz = torch.empty((tl, bs, 3, h, w), dtype=torch.float32, device=idx.device) if want_xyz else None

@@ -63,6 +63,8 @@ int conv3d_out_size(int, int, int);
 size_t conv3d_scratch_elems(int, int, int, int);
 int conv3d_gather_forward(const float*, const float*, const float*, float*, float*, uint8_t*, float*, int, int, int, int,
                           int, int, int, int, cudaStream_t);
+int conv3d_rank(const float*, const float*, float*, uint8_t*, float*, int, int, int, int, int, int, int, cudaStream_t);
+int conv3d_gather_features(const float*, const uint8_t*, float*, int, int, int, int, int, int, int, int, cudaStream_t);
 int conv3d_gather_backward(const float*, const float*, const uint8_t*, float*, float*, int, int, int, int, int, int, int,
                            int, cudaStream_t);
 
@@ -785,6 +787,22 @@ int dis_conv3d_gather_forward(const float* xyz, const float* feat, const float* 
   if (bs == 0) return DIS_OK;
   return conv3d_gather_forward(xyz, feat, mask, xyz_nb, feat_nb, idx, scratch, tl, bs, C, h, w, ksize, stride,
                                neighbors, as_stream(stream));
+}
+
+int dis_conv3d_rank(const float* xyz, const float* mask, float* xyz_nb, uint8_t* idx, float* scratch, int tl, int bs, int h,
+                    int w, int ksize, int stride, int neighbors, void* stream) {
+  if (int rc = check_conv3d(tl, bs, 1, h, w, ksize, stride, neighbors)) return rc;
+  if (!xyz || !mask || !xyz_nb || !idx || !scratch) return DIS_ERR_NULL_POINTER;
+  if (bs == 0) return DIS_OK;
+  return conv3d_rank(xyz, mask, xyz_nb, idx, scratch, tl, bs, h, w, ksize, stride, neighbors, as_stream(stream));
+}
+
+int dis_conv3d_gather_features(const float* feat, const uint8_t* idx, float* feat_nb, int tl, int bs, int C, int h, int w,
+                               int ksize, int stride, int neighbors, void* stream) {
+  if (int rc = check_conv3d(tl, bs, C, h, w, ksize, stride, neighbors)) return rc;
+  if (!feat || !idx || !feat_nb) return DIS_ERR_NULL_POINTER;
+  if (bs == 0) return DIS_OK;
+  return conv3d_gather_features(feat, idx, feat_nb, tl, bs, C, h, w, ksize, stride, neighbors, as_stream(stream));
 }
 
 int dis_conv3d_gather_backward(const float* g_xyz_nb, const float* g_feat_nb, const uint8_t* idx, float* g_xyz,

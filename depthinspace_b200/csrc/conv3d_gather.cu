@@ -336,11 +336,11 @@ int conv3d_out_size(int n, int k, int stride) { return (n + 2 * ((k - 1) / 2) - 
 size_t conv3d_scratch_elems(int tl, int bs, int h, int w) { return 4 + (size_t)tl * bs * 3 * h * w; }
 
 // scratch: [0] = global max of the squared plane distances, [4 ...] = plane coordinates [tl,bs,3,h,w]
-int conv3d_gather_forward(const float* xyz, const float* feat, const float* mask, float* xyz_nb, float* feat_nb,
-                          uint8_t* idx, float* scratch, int tl, int bs, int C, int h, int w, int k, int stride, int nb,
-                          cudaStream_t s) {
+// neighbour selection only: xyz_nb and idx (depends on xyz and mask, not on the features)
+int conv3d_rank(const float* xyz, const float* mask, float* xyz_nb, uint8_t* idx, float* scratch, int tl, int bs, int h, int w,
+                int k, int stride, int nb, cudaStream_t s) {
   float* gmax = scratch;
-  C3Args a{xyz, feat, mask, xyz_nb, feat_nb, idx, gmax, scratch + 4, tl, bs, C, h, w, k, stride, nb,
+  C3Args a{xyz, nullptr, mask, xyz_nb, nullptr, idx, gmax, scratch + 4, tl, bs, 0, h, w, k, stride, nb,
            conv3d_out_size(h, k, stride), conv3d_out_size(w, k, stride)};
   const int M = bs * a.oh * a.ow;
   cudaError_t e = cudaMemsetAsync(gmax, 0, sizeof(float), s);
@@ -354,8 +354,25 @@ int conv3d_gather_forward(const float* xyz, const float* feat, const float* mask
     conv3d_rank_kernel<false, false><<<(M + 127) / 128, 128, 0, s>>>(a);
     conv3d_rank_kernel<true, false><<<(M + 127) / 128, 128, 0, s>>>(a);
   }
+  return check_launch();
+}
+
+// feature gather for a given selection (the selection of a FuseNet level serves every Conv3D layer of that level and the
+// checkpoint recompute: the ranking is paid once)
+int conv3d_gather_features(const float* feat, const uint8_t* idx, float* feat_nb, int tl, int bs, int C, int h, int w, int k,
+                           int stride, int nb, cudaStream_t s) {
+  C3Args a{nullptr, feat, nullptr, nullptr, feat_nb, const_cast<uint8_t*>(idx), nullptr, nullptr, tl, bs, C, h, w, k, stride, nb,
+           conv3d_out_size(h, k, stride), conv3d_out_size(w, k, stride)};
+  const int M = bs * a.oh * a.ow;
   conv3d_feat_gather_kernel<<<flat_grid((size_t)((M + FT - 1) / FT) * nb, FW), 32 * FW, 0, s>>>(a);
   return check_launch();
+}
+
+int conv3d_gather_forward(const float* xyz, const float* feat, const float* mask, float* xyz_nb, float* feat_nb,
+                          uint8_t* idx, float* scratch, int tl, int bs, int C, int h, int w, int k, int stride, int nb,
+                          cudaStream_t s) {
+  if (int rc = conv3d_rank(xyz, mask, xyz_nb, idx, scratch, tl, bs, h, w, k, stride, nb, s)) return rc;
+  return conv3d_gather_features(feat, idx, feat_nb, tl, bs, C, h, w, k, stride, nb, s);
 }
 
 int conv3d_gather_backward(const float* g_xyz_nb, const float* g_feat_nb, const uint8_t* idx, float* g_xyz, float* g_feat,

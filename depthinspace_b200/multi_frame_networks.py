@@ -151,11 +151,33 @@ def resize_flow_masks_like(flow_masks, target):
         return out.view(*lead, *out.shape[1:])
 
 
+class Conv3DRank:
+    """The neighbour selection of one (xyz, mask) pair: Conv3D ranks its candidates by xyz and mask alone (reference
+    :469-491), so the layers of a FuseNet level and the checkpoint recompute can share it (conv3d_rank / rank=...)."""
+
+    def __init__(self, xyz_nb, idx, cfg):
+        self.xyz_nb, self.idx, self.cfg = xyz_nb, idx, cfg
+
+
+def conv3d_rank(xyz, mask, ksize=3, stride=1, neighbors=9):
+    """-> Conv3DRank for conv3d_gather(..., rank=...).  No gradient is recorded here; conv3d_gather(rank=...) still
+    differentiates xyz_neighbors w.r.t. xyz (the selection itself has no gradient)."""
+    with torch.no_grad():
+        xyz_nb, idx, _ = _ops.conv3d_rank(xyz, mask, ksize, stride, neighbors)
+    return Conv3DRank(xyz_nb, idx, (tuple(xyz.shape), ksize, stride, neighbors))
+
+
 class _Conv3DGather(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, xyz, feat, mask, ksize, stride, neighbors):
+    def forward(ctx, xyz, feat, mask, ksize, stride, neighbors, rank):
         ctx.set_materialize_grads(False)
-        xyz_nb, feat_nb, idx, _ = _ops.conv3d_gather_forward(xyz, feat, mask, ksize, stride, neighbors)
+        if rank is None:
+            xyz_nb, feat_nb, idx, _ = _ops.conv3d_gather_forward(xyz, feat, mask, ksize, stride, neighbors)
+        else:
+            if rank.cfg != (tuple(xyz.shape), ksize, stride, neighbors):
+                raise ValueError("rank was computed for a different xyz shape / window / neighbour count")
+            idx, xyz_nb = rank.idx.detach(), rank.xyz_nb.detach()   # fresh tensor objects on the cached storage
+            feat_nb = _ops.conv3d_gather_features(feat, idx, ksize, stride, neighbors)
         ctx.save_for_backward(idx)
         ctx.cfg = (tuple(feat.shape), ksize, stride, neighbors)
         ctx.mark_non_differentiable(idx)
@@ -168,17 +190,18 @@ class _Conv3DGather(torch.autograd.Function):
         want_xyz = ctx.needs_input_grad[0] and g_xyz_nb is not None
         want_feat = ctx.needs_input_grad[1] and g_feat_nb is not None
         if not (want_xyz or want_feat):
-            return None, None, None, None, None, None
+            return None, None, None, None, None, None, None
         g_xyz, g_feat = _ops.conv3d_gather_backward(g_xyz_nb, g_feat_nb, idx, shape, ksize, stride, neighbors,
                                                     want_xyz, want_feat)
-        return g_xyz, g_feat, None, None, None, None
+        return g_xyz, g_feat, None, None, None, None, None
 
 
-def conv3d_gather(xyz, feat, mask, ksize=3, stride=1, neighbors=9):
+def conv3d_gather(xyz, feat, mask, ksize=3, stride=1, neighbors=9, rank=None):
     """Neighbour selection + gather of Conv3D.tforward (reference :469-501), everything up to the MLP:
     xyz [tl,bs,3,h,w], feat [tl,bs,C,h,w], mask [tl,bs,1,h,w] ->
       xyz_neighbors [M,neighbors,3] (local coordinates), feat_neighbors [M,neighbors,C],
       neighbors_ind [M,neighbors] (uint8 candidate index (ky*k+kx)*tl + t), M = bs*oh*ow.
     Neighbours come in ascending distance with ties broken by the lowest index (torch.topk(sorted=False) leaves both
-    unspecified; the reference only sums over them).  Gradients flow to xyz and feat."""
-    return _Conv3DGather.apply(xyz, feat, mask, ksize, stride, neighbors)
+    unspecified; the reference only sums over them).  Gradients flow to xyz and feat.
+    rank: a Conv3DRank of the same (xyz, mask) from conv3d_rank(): the selection is reused, only the features are gathered."""
+    return _Conv3DGather.apply(xyz, feat, mask, ksize, stride, neighbors, rank)

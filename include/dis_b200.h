@@ -299,6 +299,13 @@ DIS_API size_t dis_conv3d_scratch_elems(int tl, int bs, int h, int w);
 DIS_API int dis_conv3d_gather_forward(const float* xyz, const float* feat, const float* mask, float* xyz_nb,
                                       float* feat_nb, uint8_t* idx, float* scratch, int tl, int bs, int C, int h,
                                       int w, int ksize, int stride, int neighbors, void* stream);
+/* The two halves of dis_conv3d_gather_forward.  The selection (xyz_nb, idx) depends on xyz and mask only: the Conv3D layers
+ * of one FuseNet level (multi_frame_networks.py:520-560 call the layer twice per level on the same xyz / mask) and the
+ * checkpoint recompute can rank once and gather features per call. */
+DIS_API int dis_conv3d_rank(const float* xyz, const float* mask, float* xyz_nb, uint8_t* idx, float* scratch, int tl,
+                            int bs, int h, int w, int ksize, int stride, int neighbors, void* stream);
+DIS_API int dis_conv3d_gather_features(const float* feat, const uint8_t* idx, float* feat_nb, int tl, int bs, int C,
+                                       int h, int w, int ksize, int stride, int neighbors, void* stream);
 DIS_API int dis_conv3d_gather_backward(const float* g_xyz_nb, const float* g_feat_nb, const uint8_t* idx,
                                        float* g_xyz, float* g_feat, int tl, int bs, int C, int h, int w,
                                        int ksize, int stride, int neighbors, void* stream);

@@ -1001,6 +1001,33 @@ def test_fused_pattern_loss_window_sizes(mods, k, lt):
         assert_close(dd[s].grad, o32["grad_disp"], 1e-5, f"grad k={k}", outlier_frac=0)
 
 
+def test_conv3d_rank_is_reusable_across_feature_stacks(mods):
+    """The neighbour selection depends on xyz and mask only: conv3d_rank() once, then conv3d_gather(rank=...) per feature
+    stack (the Conv3D layers of one FuseNet level, the checkpoint recompute) must equal the one-call path bit for bit,
+    outputs and gradients (w.r.t. features AND xyz)."""
+    _, _, mf = mods
+    torch.manual_seed(4)
+    tl, bs, C, hw = 4, 3, 16, (20, 26)
+    xyz = torch.randn(tl, bs, 3, *hw, device="cuda") * 0.1
+    xyz[:, :, 2] += 1.5
+    mask = (torch.rand(tl, bs, 1, *hw, device="cuda") > 0.1).float()
+    rank = mf.conv3d_rank(xyz, mask, 3, 1, 9)
+    for seed in (0, 1):
+        torch.manual_seed(10 + seed)
+        feat = torch.randn(tl, bs, C, *hw, device="cuda")
+        x1, f1 = xyz.clone().requires_grad_(True), feat.clone().requires_grad_(True)
+        x2, f2 = xyz.clone().requires_grad_(True), feat.clone().requires_grad_(True)
+        a = mf.conv3d_gather(x1, f1, mask, 3, 1, 9)
+        b = mf.conv3d_gather(x2, f2, mask, 3, 1, 9, rank=rank)
+        assert all(torch.equal(u, v) for u, v in zip(a, b))
+        gx, gf = torch.randn_like(a[0]), torch.randn_like(a[1])
+        torch.autograd.backward([a[0], a[1]], [gx, gf])
+        torch.autograd.backward([b[0], b[1]], [gx, gf])
+        assert torch.equal(f1.grad, f2.grad) and torch.equal(x1.grad, x2.grad)
+    with pytest.raises(ValueError):
+        mf.conv3d_gather(xyz[:, :2].contiguous(), feat[:, :2].contiguous(), mask[:, :2].contiguous(), 3, 1, 9, rank=rank)
+
+
 @pytest.mark.parametrize("lt", ["mse", "sad"])
 @pytest.mark.parametrize("use_std", [True, False])
 def test_point_pattern_loss_matches_the_tile_kernel_and_the_oracle(mods, lt, use_std):

@@ -32,6 +32,7 @@ FEAT = ((HW[0] // 2, HW[1] // 2), (HW[0] // 4, HW[1] // 4))   # 256x216, 128x108
 C_FEAT, BLOCKS = 32, 4
 ALL_FRAMES = True
 CONV3D = False
+RANK_ONCE = True
 
 
 def build(bs, dev, group=None):
@@ -129,17 +130,22 @@ def step(w):
         x.grad = None
         for _ in range(BLOCKS):
             if ALL_FRAMES:       # one gather for all target frames (the tidx loop of fwd_3d_1 / fwd_3d_2 as one op)
+                if CONV3D and RANK_ONCE and _ == 0:
+                    # the selection depends on the level's xyz / mask only: ranked once per (level, target frame) and step,
+                    # shared by the Conv3D layers of the level and by the checkpoint recompute
+                    ranks = [mfn.conv3d_rank(w["xyz_lvl"][lvl], w["mask_lvl"][lvl], 3, 1, 9) for tidx in range(TL)]
+                rk = (lambda t: ranks[t]) if (CONV3D and RANK_ONCE) else (lambda t: None)
                 with torch.no_grad():
                     warped = mfn.gather_warped_all(x, fl)
                     if CONV3D:   # Conv3D's neighbour selection + gather on every target frame (checkpointed forward)
                         for tidx in range(TL):
-                            mfn.conv3d_gather(w["xyz_lvl"][lvl], warped[tidx], w["mask_lvl"][lvl], 3, 1, 9)
+                            mfn.conv3d_gather(w["xyz_lvl"][lvl], warped[tidx], w["mask_lvl"][lvl], 3, 1, 9, rank=rk(tidx))
                 warped = mfn.gather_warped_all(x, fl)
                 if CONV3D:
                     g_acc = torch.zeros_like(warped)
                     for tidx in range(TL):
                         wf = warped[tidx].detach().requires_grad_(True)
-                        _, feat_nb, _ = mfn.conv3d_gather(w["xyz_lvl"][lvl], wf, w["mask_lvl"][lvl], 3, 1, 9)
+                        _, feat_nb, _ = mfn.conv3d_gather(w["xyz_lvl"][lvl], wf, w["mask_lvl"][lvl], 3, 1, 9, rank=rk(tidx))
                         feat_nb.backward(w["g_nb"][lvl])
                         g_acc[tidx] = wf.grad
                     warped.backward(g_acc)
@@ -342,13 +348,16 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--per-frame-gathers", action="store_true", help="one gather call per target frame (reference loop shape)")
+    ap.add_argument("--conv3d-rank-per-call", action="store_true", help="with --conv3d: rank the neighbours in every call (round-1 behaviour) "
+                    "instead of once per level, target frame and step")
     ap.add_argument("--conv3d", action="store_true", help="also run Conv3D's neighbour selection + gather (SURVEY 8(f) row 3) on every "
                     "gathered stack: forward, checkpoint recompute and backward")
     ap.add_argument("--sf", action="store_true", help="time the DIS-SF loss WITH its 12 flow-consistency terms instead (bs 64 = 256 frames)")
     a = ap.parse_args()
-    global ALL_FRAMES, CONV3D
+    global ALL_FRAMES, CONV3D, RANK_ONCE
     ALL_FRAMES = not a.per_frame_gathers
     CONV3D = a.conv3d
+    RANK_ONCE = not a.conv3d_rank_per_call
     dev = torch.device("cuda")
     run_step = step_sf if a.sf else step
     if a.sf and a.bs == [4, 32]:
