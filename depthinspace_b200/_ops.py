@@ -317,24 +317,47 @@ def sobel_backward(grad_out, ksize):
     return gx
 
 
-def smooth_loss_forward(disp, im, want_grad, grad_scale=1.0, accumulate_into=None):
+def smooth_loss_buffers(disp, want_grad):
+    """Outputs of smooth_loss_forward allocated ahead of the launch -> (out3, gsum | None, partials)."""
+    disp = _chk(disp, "disp")
+    N, _, H, W = disp.shape
+    with _on(disp) as lib:
+        npart = lib.dis_smooth_loss_num_partials(N, H, W)
+    return (torch.empty(3, dtype=torch.float32, device=disp.device), torch.empty_like(disp) if want_grad else None,
+            torch.empty(2 * max(npart, 1), dtype=torch.float32, device=disp.device))
+
+
+def smooth_loss_forward(disp, im, want_grad, grad_scale=1.0, accumulate_into=None, launch_stream=None, buffers=None):
     """-> (out3 [sum, count, mean], grad_sum * grad_scale | None); accumulate_into: an existing gradient tensor of disp's
-    shape that the scaled gradient is ADDED to (returned in place of a fresh tensor)."""
+    shape that the scaled gradient is ADDED to (returned in place of a fresh tensor).
+    launch_stream + buffers: launch on another torch.cuda.Stream than the current one, into outputs from
+    smooth_loss_buffers().  The buffers must have been allocated BEFORE the point of the current stream that
+    launch_stream waits for: memory handed out later may still be in use by work queued on the current stream."""
     disp, im = _chk(disp, "disp"), _chk(im, "im")
     if disp.shape != im.shape or disp.shape[1] != 1:
         raise ValueError(f"disp and im must both be [N,1,H,W]; got {tuple(disp.shape)} and {tuple(im.shape)}")
+    if (launch_stream is None) != (buffers is None):
+        raise ValueError("launch_stream and buffers go together")
     N, _, H, W = disp.shape
     if accumulate_into is not None:
         gsum = _chk(accumulate_into, "accumulate_into")
         if gsum.shape != disp.shape or gsum.data_ptr() != accumulate_into.data_ptr():
             raise ValueError("accumulate_into must be a contiguous tensor of disp's shape")
+    elif buffers is not None:
+        gsum = buffers[1]
+        if want_grad and gsum is None:
+            raise ValueError("buffers were allocated without a gradient plane")
+        if not want_grad:
+            gsum = None
     else:
         gsum = torch.empty_like(disp) if want_grad else None
-    out3 = torch.empty(3, dtype=torch.float32, device=disp.device)
+    out3 = buffers[0] if buffers is not None else torch.empty(3, dtype=torch.float32, device=disp.device)
     with _on(disp) as lib:
         npart = lib.dis_smooth_loss_num_partials(N, H, W)
-        partials = torch.empty(2 * max(npart, 1), dtype=torch.float32, device=disp.device)
-        s = _stream(disp)
+        partials = buffers[2] if buffers is not None else torch.empty(2 * max(npart, 1), dtype=torch.float32, device=disp.device)
+        if partials.numel() < 2 * max(npart, 1):
+            raise ValueError("partials buffer too small")
+        s = _stream(disp) if launch_stream is None else launch_stream.cuda_stream
         _lib.check(lib.dis_smooth_loss_forward_scaled(_ptr(disp), _ptr(im), _ptr(gsum), _ptr(partials), N, H, W,
                                                       float(grad_scale), int(accumulate_into is not None), s))
         _lib.check(lib.dis_reduce_pairs(_ptr(partials), npart, _ptr(out3), s))

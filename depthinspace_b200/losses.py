@@ -7,6 +7,8 @@
 Same weights and the same list-of-0-dim-tensors return convention (the worker sums it,
 model/worker.py:522).  The geometric (flow-consistency) terms are appended by the caller.
 """
+import os
+
 import torch
 
 from . import _ops
@@ -142,6 +144,33 @@ class _HotPathLoss(torch.nn.Module):
         self.ge_loss = (self.ge_class(K, Ki, im_height, im_width, clamp=ge_clamp, process_group=process_group)
                         if K is not None else None)
         self.d2d = DispToDepth(float(focal_length), float(baseline)) if focal_length is not None else None
+        self._side_streams = {}
+
+    # ---- smoothness on a side stream ------------------------------------------------------------------------------------
+    # The photometric kernel's 2048 CTAs take 4.6 waves of the 444 resident slots: two fifths of its last wave are idle
+    # SM time.  The smoothness kernel does not depend on it, so it is launched right behind it on a second stream and its
+    # CTAs fill that tail.  DIS_OVERLAP_SMOOTH=0 (or overlap_smoothness = False) keeps everything on one stream.
+    overlap_smoothness = os.environ.get("DIS_OVERLAP_SMOOTH", "1") != "0"
+
+    def _fork_point(self, disp0, amb):
+        """Event on the current stream BEFORE the photometric launch: what the side stream has to wait for.  Both inputs of
+        the smoothness term must exist by then, in the layout the kernel reads (no copy may be queued behind the event)."""
+        if not (self.overlap_smoothness and amb.is_cuda and disp0.is_contiguous() and amb.is_contiguous()
+                and disp0.dtype == torch.float32 and amb.dtype == torch.float32) or torch.cuda.is_current_stream_capturing():
+            return None
+        bufs = _ops.smooth_loss_buffers(disp0, disp0.requires_grad and torch.is_grad_enabled())   # before the event, see _SmoothLoss
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(amb.device))
+        return ev, bufs
+
+    def _smooth_term(self, disp0, amb, fork):
+        if fork is None:
+            return self.disparity_loss(disp0, amb) * self.smooth_weight
+        dev = disp0.device
+        side = self._side_streams.get(dev)
+        if side is None:
+            side = self._side_streams[dev] = torch.cuda.Stream(device=dev)
+        return self.disparity_loss(disp0, amb, fork, side) * self.smooth_weight
 
     def _geometric_terms(self, disp_tl, R, t, amb, flow_out, primary_disp=None):
         """The pair loop of the workers (single_frame_worker.py:127-149, multi_frame_worker.py:128-157):
@@ -249,9 +278,11 @@ class SingleFrameLoss(_HotPathLoss):
         if not isinstance(out, (tuple, list)):
             out = [out]
         im, std, amb = _merge(im_lcn)[:, 0:1], _merge(std), _merge(ambient)
-        ph = self.ph_loss.forward_multi([_merge(o) for o in out], im, std)   # :108-115, all scales fused
+        disps = [_merge(o) for o in out]
+        fork = self._fork_point(disps[0], amb)
+        ph = self.ph_loss.forward_multi(disps, im, std)                      # :108-115, all scales fused
         vals = [v / (2 ** s) for s, v in enumerate(ph)]
-        vals.append(self.disparity_loss(_merge(out[0]), amb) * self.smooth_weight)   # :118-124 (scale 0 only)
+        vals.append(self._smooth_term(disps[0], amb, fork))                  # :118-124 (scale 0 only)
         if flow_out is not None:                                      # :127-149
             vals += self._geometric_terms(out[0], R, t, ambient, flow_out)
         if pseudo_gt is not None:                                     # :152-155 (DIS-FTSF)
@@ -279,9 +310,11 @@ class MultiFrameLoss(_HotPathLoss):
         if not isinstance(out, (tuple, list)):
             out = [out]
         im, std, amb = _merge(im_lcn)[:, 0:1], _merge(std), _merge(ambient)
-        ph = self.ph_loss.forward_multi([_merge(o) for o in out], im, std)   # :110-117
+        disps = [_merge(o) for o in out]
+        fork = self._fork_point(disps[0], amb)
+        ph = self.ph_loss.forward_multi(disps, im, std)                      # :110-117
         vals = [v / (2 ** s) for s, v in enumerate(ph)]
-        vals.append(self.disparity_loss(_merge(out[0]), amb) * self.smooth_weight)   # :120-126
+        vals.append(self._smooth_term(disps[0], amb, fork))                  # :120-126
         if flow_out is not None:                                      # :128-157 (needs primary_disp)
             vals += self._geometric_terms(out[0], R, t, ambient, flow_out, primary_disp=primary_disp)
         if primary_disp is not None and warmup:                       # :160-165 (first two epochs)

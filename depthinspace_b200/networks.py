@@ -237,8 +237,20 @@ class SobelFilter(torch.nn.Module):
 
 class _SmoothLoss(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, disp, im, group):
-        out3, gsum = _ops.smooth_loss_forward(disp, im, want_grad=ctx.needs_input_grad[0])
+    def forward(ctx, disp, im, group, fork, side):
+        # fork = (event, buffers), side = stream (optional).  The kernel is then launched on `side` once the event has passed,
+        # so that it shares the GPU with work queued on the current stream after the event (losses._HotPathLoss: the tail
+        # wave of the photometric kernel).  Its outputs were allocated BEFORE the event was recorded (memory handed out
+        # later could still be in use by that queued work); the streams are joined right here, so every later reuse of the
+        # tensors involved is ordered behind the side stream's work.  The autograd node belongs to the current stream.
+        want = ctx.needs_input_grad[0]
+        if side is None or (want and fork[1][1] is None):
+            out3, gsum = _ops.smooth_loss_forward(disp, im, want_grad=want)
+        else:
+            main = torch.cuda.current_stream(disp.device)
+            side.wait_event(fork[0])
+            out3, gsum = _ops.smooth_loss_forward(disp, im, want_grad=want, launch_stream=side, buffers=fork[1])
+            main.wait_stream(side)
         if group is not None:
             all_reduce_sum_(out3[:2], group)
             val = out3[0] / out3[1]
@@ -250,7 +262,7 @@ class _SmoothLoss(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g_val):
         gsum, out3 = ctx.saved_tensors
-        return _ops.scale_by_device_scalar(gsum, g_val, out3[1:2]), None, None
+        return _ops.scale_by_device_scalar(gsum, g_val, out3[1:2]), None, None, None, None
 
 
 class DisparitySmoothLoss(torch.nn.Module):
@@ -261,8 +273,8 @@ class DisparitySmoothLoss(torch.nn.Module):
         super().__init__()
         self.process_group = process_group
 
-    def forward(self, disp, im):
-        return _SmoothLoss.apply(disp, im.contiguous(), self.process_group)
+    def forward(self, disp, im, fork=None, side_stream=None):
+        return _SmoothLoss.apply(disp, im.contiguous(), self.process_group, fork, side_stream)
 
     tforward = forward
 
