@@ -155,7 +155,8 @@ class _HotPathLoss(torch.nn.Module):
     def _fork_point(self, disp0, amb):
         """Event on the current stream BEFORE the photometric launch: what the side stream has to wait for.  Both inputs of
         the smoothness term must exist by then, in the layout the kernel reads (no copy may be queued behind the event)."""
-        if not (self.overlap_smoothness and amb.is_cuda and disp0.is_contiguous() and amb.is_contiguous()
+        # (small batches are launch-bound: the extra event / stream calls would cost more than the overlap returns)
+        if not (self.overlap_smoothness and amb.is_cuda and disp0.numel() >= (1 << 22) and disp0.is_contiguous() and amb.is_contiguous()
                 and disp0.dtype == torch.float32 and amb.dtype == torch.float32) or torch.cuda.is_current_stream_capturing():
             return None
         bufs = _ops.smooth_loss_buffers(disp0, disp0.requires_grad and torch.is_grad_enabled())   # before the event, see _SmoothLoss
