@@ -57,35 +57,50 @@ __global__ void __launch_bounds__(256) box_weight_v_kernel(const float* __restri
   }
 }
 
-// horizontal pass over V, scaled by 1 / k^2: one thread per pixel (neighbouring threads share their loads in L1),
-// BW_RUN rows per CTA.  grid (columns / 256, rows of all frames / BW_RUN)
+// horizontal pass over V, scaled by 1 / k^2: one thread per 4 consecutive pixels of a row (aligned 128-bit loads of the
+// 4 + 2R values in reach, sliding sum, one 128-bit store), BW_RUN rows per CTA.  grid (quads / 128, rows of all frames / BW_RUN)
 template <int R>
-__global__ void __launch_bounds__(256) box_weight_h_kernel(const float* __restrict__ V, float* __restrict__ M, int W, float inv_k2,
-                                                           size_t rows) {
-  const int x = blockIdx.x * 256 + threadIdx.x;
-  if (x >= W) return;
+__global__ void __launch_bounds__(128) box_weight_h_kernel(const float* __restrict__ V, float* __restrict__ M, int W, float inv_k2,
+                                                           size_t rows, int vec_ok) {
+  constexpr int PAD = 4 * ((R + 3) / 4), NV = 1 + 2 * ((R + 3) / 4);   // floats before x0 / float4 loads per row
+  const int x0 = 4 * (blockIdx.x * 128 + threadIdx.x);
+  if (x0 >= W) return;
   const size_t r0 = (size_t)blockIdx.y * BW_RUN;
-  const bool interior = x - R >= 1 && x + R <= W - 2;     // no padded column in reach: plain window, no bounds checks
+  // no padded column in reach and every load inside the row: plain window, no bounds checks
+  const bool interior = vec_ok && x0 - R >= 1 && x0 + 3 + R <= W - 2 && x0 - PAD >= 0 && x0 + 4 + PAD <= W;
 #pragma unroll 4
   for (int k = 0; k < BW_RUN; ++k) {
     if (r0 + k >= rows) break;
     const float* row = V + (r0 + k) * W;
-    float v = 0.f;
+    float* mrow = M + (r0 + k) * W;
     if (interior) {
+      float v[4 * NV];
 #pragma unroll
-      for (int d = -R; d <= R; ++d) v += __ldg(row + x + d);
-    } else {
-      auto vz = [&](int c) -> float { return (c >= 0 && c < W) ? __ldg(row + c) : 0.0f; };
-      auto window = [&](int c) -> float {
-        float s = 0.f;
-        for (int d = -R; d <= R; ++d) s += vz(c + d);
-        return s;
-      };
-      v = window(x);
+      for (int q = 0; q < NV; ++q) {
+        const float4 t = __ldg(reinterpret_cast<const float4*>(row + x0 - PAD) + q);
+        v[4 * q] = t.x; v[4 * q + 1] = t.y; v[4 * q + 2] = t.z; v[4 * q + 3] = t.w;
+      }
+      float o[4], s = 0.f;
+#pragma unroll
+      for (int d = 0; d <= 2 * R; ++d) s += v[PAD - R + d];
+      o[0] = s;
+#pragma unroll
+      for (int c = 1; c < 4; ++c) { s += v[PAD + R + c] - v[PAD - R + c - 1]; o[c] = s; }
+      __stcs(reinterpret_cast<float4*>(mrow + x0), make_float4(o[0] * inv_k2, o[1] * inv_k2, o[2] * inv_k2, o[3] * inv_k2));
+      continue;
+    }
+    auto vz = [&](int c) -> float { return (c >= 0 && c < W) ? __ldg(row + c) : 0.0f; };
+    auto window = [&](int c) -> float {
+      float s = 0.f;
+      for (int d = -R; d <= R; ++d) s += vz(c + d);
+      return s;
+    };
+    for (int x = x0; x < min(x0 + 4, W); ++x) {
+      float v = window(x);
       if (x == 0) for (int c = -R; c < 0; ++c) v += window(c);
       if (x == W - 1) for (int c = W; c < W + R; ++c) v += window(c);
+      mrow[x] = v * inv_k2;
     }
-    M[(r0 + k) * W + x] = v * inv_k2;
   }
 }
 
@@ -210,11 +225,12 @@ int box_weight(const float* std_in, float* workspace, float* wbox, int N, int H,
   const size_t rows = (size_t)N * H, per_launch = (size_t)65535 * BW_RUN;
   for (size_t r0 = 0; r0 < rows; r0 += per_launch) {
     const size_t nr = rows - r0 < per_launch ? rows - r0 : per_launch;
-    const dim3 grid((W + 255) / 256, (unsigned)((nr + BW_RUN - 1) / BW_RUN));
+    const dim3 grid(((W + 3) / 4 + 127) / 128, (unsigned)((nr + BW_RUN - 1) / BW_RUN));
     const float* v = workspace + r0 * W;
     float* m = wbox + r0 * W;
+    const int vec_ok = (W % 4 == 0) && ((reinterpret_cast<uintptr_t>(v) | reinterpret_cast<uintptr_t>(m)) & 15) == 0;
     switch (R) {
-#define DIS_BW_CASE(R_) case R_: box_weight_h_kernel<R_><<<grid, 256, 0, s>>>(v, m, W, inv_k2, nr); break;
+#define DIS_BW_CASE(R_) case R_: box_weight_h_kernel<R_><<<grid, 128, 0, s>>>(v, m, W, inv_k2, nr, vec_ok); break;
       DIS_BW_CASE(0) DIS_BW_CASE(1) DIS_BW_CASE(2) DIS_BW_CASE(3) DIS_BW_CASE(4) DIS_BW_CASE(5) DIS_BW_CASE(6) DIS_BW_CASE(7)
 #undef DIS_BW_CASE
     }
