@@ -39,6 +39,9 @@ namespace dis {
 constexpr int MV = 2;                  // rows per thread per step
 constexpr int MARCH_MAX_WARPS = 8;     // CTA <= 256 threads
 constexpr int MARCH_CTAS_PER_SM = 3;
+#ifndef DIS_MARCH_SIGN_CLAMP
+#define DIS_MARCH_SIGN_CLAMP 0
+#endif
 #ifndef DIS_MARCH_UNROLL
 #define DIS_MARCH_UNROLL 9
 #endif
@@ -190,7 +193,15 @@ __device__ __forceinline__ void march_scales(const MCell<NS / 2>& ec, const MCel
       if (TYPE == CENSUS_SAD) {
         float q0, q1;
         upk2(r3, q0, q1);
+#if DIS_MARCH_SIGN_CLAMP
+        // sign(d) * q with sign(0) = 0 as clamp(d * 2^96, -q, q): one packed FMUL for two scales + two FMNMX per scale
+        // instead of LOP3 + FSETP + FSEL (a non-zero d is >= 2^-60 here and q = rsqrt^3 <= eps^-1.5: exact for eps >= 1e-12)
+        float t0, t1;
+        upk2(mul2(diff, bc2(7.9228162514264338e28f)), t0, t1);
+        u = pk2(fminf(fmaxf(t0, -q0), q0), fminf(fmaxf(t1, -q1), q1));
+#else
         u = pk2(signed_mag(q0, d0), signed_mag(q1, d1));
+#endif
       } else {
         u = mul2(diff, r3);
       }

@@ -368,7 +368,7 @@ def test_pattern_loss_is_deterministic_and_batch_separable(mods):
 
 
 # ----------------------------------------------------------------------------- LCN (a1)
-@pytest.mark.parametrize("hw,radius", [((512, 432), 5), ((37, 53), 3), ((480, 640), 7), ((20, 24), 1), ((64, 64), 8)])
+@pytest.mark.parametrize("hw,radius", [((512, 432), 5), ((37, 53), 3), ((480, 640), 7), ((20, 24), 1), ((64, 64), 8), ((30, 1000), 5), ((200, 9), 2)])
 def test_lcn_vs_fp64_oracle(mods, hw, radius):
     net, _, _ = mods
     d = synth.make_frames(2, hw, "default", seed=radius)
@@ -404,7 +404,7 @@ def _rough_disp(d, seed=0):
     return (d["disp_gt"] + rng.standard_normal(d["disp_gt"].shape)).astype(np.float32)
 
 
-@pytest.mark.parametrize("hw", [(512, 432), (45, 70), (5, 9), (33, 64)])
+@pytest.mark.parametrize("hw", [(512, 432), (45, 70), (5, 9), (33, 64), (40, 700), (130, 217), (70, 3), (6, 40)])
 def test_smooth_loss_vs_oracle(mods, hw):
     net, _, _ = mods
     d = synth.make_frames(2, hw, seed=hw[0])
