@@ -176,7 +176,7 @@ DIS_API int dis_mul(const float* a, const float* b, float* out, size_t n, void* 
  * dis_sobel_forward: x [N,1,H,W] -> out [N,2,H,W] (gx, gy), replicate padding, ksize 3 or 5.
  * dis_sobel_backward: adjoint, grad_out [N,2,H,W] -> grad_x [N,1,H,W].
  * dis_smooth_loss_forward: one pass producing per-CTA partial sums of
- *   | sobel(disp) * exp(-|255 sobel(im)|) |  (pairs (sum, 0)) and, when grad_sum != NULL,
+ *   | sobel(disp) * exp(-|255 sobel(im)|) |  (pairs (sum, element count = 2 per pixel)) and, when grad_sum != NULL,
  *   d(sum)/d disp [N,1,H,W]  (divide by 2*N*H*W for the mean, :431). */
 DIS_API int dis_sobel_forward(const float* x, float* out, int N, int H, int W, int ksize, void* stream);
 DIS_API int dis_sobel_backward(const float* grad_out, float* grad_x, int N, int H, int W, int ksize,
